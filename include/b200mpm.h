@@ -1,0 +1,233 @@
+/*
+ * b200mpm.h — C ABI of the B200-native MPM substep (drop-in for wgsparkl's hot path).
+ *
+ * Every entry point replaces one piece of the reference's Rust/wgpu surface; the
+ * reference location is cited as (file:line) relative to the wgsparkl source tree.
+ * Plain pointers and sizes only; no torch / CUDA types cross this boundary.
+ *
+ *   - all functions return 0 (B200MPM_OK) or a negative b200mpm_status;
+ *   - b200mpm_last_error() returns a static, thread-local, human-readable message;
+ *   - handles are NOT thread-safe; distinct handles may be used from distinct threads;
+ *   - input pointers are borrowed for the duration of the call, outputs are
+ *     caller-allocated HOST buffers unless the name says `_device`.
+ *
+ * There is no CPU fallback behind this ABI: if no sm_100 device is present,
+ * b200mpm_pipeline_create() fails with B200MPM_ERR_NO_DEVICE.
+ */
+#ifndef B200MPM_H
+#define B200MPM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MPM_MAX_BODIES 16u /* rigid_impulses.rs:42, collide.wgsl:36 (CPIC bitmask width) */
+#define B200MPM_NONE 0xffffffffu /* grid.wgsl:80 */
+
+typedef enum b200mpm_status {
+    B200MPM_OK = 0,
+    B200MPM_ERR_INVALID_ARGUMENT = -1,
+    B200MPM_ERR_NO_DEVICE = -2,
+    B200MPM_ERR_CUDA = -3,
+    B200MPM_ERR_OUT_OF_MEMORY = -4,
+    B200MPM_ERR_GRID_OVERFLOW = -5, /* reported by b200mpm_data_status only; stepping never aborts */
+    B200MPM_ERR_COMM = -6
+} b200mpm_status;
+
+/* ---- plain-old-data mirrors of the reference's public structs ------------------ */
+
+/* SimulationParams (src/solver/params.rs:6-16). 2D uses gravity[0..2]. */
+typedef struct b200mpm_sim_params {
+    float gravity[3];
+    float dt;
+} b200mpm_sim_params;
+
+/* Constitutive model selector (additive; the reference hard-wires corotated:
+ * src/solver/particle_update.wgsl:7-8). */
+enum { B200MPM_MODEL_COROTATED = 0, B200MPM_MODEL_NEO_HOOKEAN = 1 };
+
+/*
+ * One MPM particle = Particle (src/solver/particle3d.rs:53-60 / particle2d.rs:49-56)
+ * flattened: position + ParticleDynamics (particle3d.rs:16-26) + Cdf (43-50) +
+ * ElasticCoefficients (models/mod.rs:63-68) + DruckerPrager (models/drucker_prager.rs:6-15)
+ * + DruckerPragerPlasticState (36-42) + ParticlePhase (solver/particle_update.rs:37-42).
+ * Matrices are column-major DIMxDIM packed in the first DIM*DIM floats (nalgebra order).
+ * `Option::None` must be resolved by the caller exactly like GpuModels::from_particles
+ * (models/mod.rs:20-36): plasticity None -> DruckerPrager::new(-1,-1); phase None -> {0,-1}.
+ */
+typedef struct b200mpm_particle {
+    float position[3];
+    float velocity[3];
+    float def_grad[9];
+    float affine[9];
+    float cdf_normal[3];
+    float cdf_rigid_vel[3];
+    float cdf_signed_distance;
+    uint32_t cdf_affinity;
+    float init_volume;
+    float init_radius;
+    float mass;
+    float lambda; /* ElasticCoefficients */
+    float mu;
+    float dp_h0, dp_h1, dp_h2, dp_h3, dp_lambda, dp_mu; /* DruckerPrager */
+    float plastic_det, plastic_hardening, plastic_log_vol_gain; /* DruckerPragerPlasticState */
+    float phase, max_stretch; /* ParticlePhase */
+    uint32_t model; /* B200MPM_MODEL_* */
+} b200mpm_particle;
+
+/* Analytic collider shapes handled by collide() (src/collision/collide.wgsl:23-55). */
+enum { B200MPM_SHAPE_BALL = 0, B200MPM_SHAPE_CUBOID = 1, B200MPM_SHAPE_CAPSULE = 2 };
+
+/*
+ * One coupled collider + its parent body = one BodyCouplingEntry (src/pipeline.rs:107-117);
+ * replaces what GpuBodySet::from_rapier uploads (src/pipeline.rs:141). Index in the array is
+ * the CPIC collider index (bit position in the affinity masks).
+ *   shape_a: ball -> unused; cuboid -> half extents; capsule -> segment endpoint a (local)
+ *   shape_b: capsule -> segment endpoint b (local)
+ *   rotation: 3D unit quaternion (i,j,k,w); 2D unit complex (re,im,0,0)
+ *   inv_inertia: 3D local-frame inverse inertia tensor, column-major 3x3; 2D scalar in [0]
+ *   inv_mass: per-axis inverse mass (0 for fixed / kinematic bodies)
+ */
+typedef struct b200mpm_body {
+    uint32_t shape_type;
+    float shape_a[3];
+    float shape_b[3];
+    float radius;
+    float translation[3];
+    float rotation[4];
+    float linvel[3];
+    float angvel[3];
+    float inv_mass[3];
+    float inv_inertia[9];
+    float local_com[3];
+    uint32_t two_ways; /* BodyCoupling::TwoWays (pipeline.rs:114); 0 = the MPM never moves the body */
+} b200mpm_body;
+
+/* GpuSim pose as written by the testbed each frame (src_testbed/step.rs:79-96). */
+typedef struct b200mpm_pose {
+    float translation[3];
+    float rotation[4];
+} b200mpm_pose;
+
+/* GpuVelocity (src_testbed/step.rs:98-119). */
+typedef struct b200mpm_velocity {
+    float linear[3];
+    float angular[3];
+} b200mpm_velocity;
+
+/* One active grid block in canonical form (debug / parity tooling). */
+typedef struct b200mpm_block_info {
+    int32_t vid[3]; /* BlockVirtualId (grid.wgsl:55-61) */
+    uint32_t first_particle; /* ActiveBlockHeader.first_particle (grid.wgsl:215-219) */
+    uint32_t num_particles;
+} b200mpm_block_info;
+
+/* Grid node (grid.wgsl:257-267): momentum/velocity + mass, then NodeCdf (233-240). */
+typedef struct b200mpm_node {
+    float momentum_velocity_mass[4]; /* 2D: xy + mass in [2] */
+    float cdf_distance;
+    uint32_t cdf_affinities;
+    uint32_t cdf_closest_id;
+} b200mpm_node;
+
+/* The reference's ten timed passes (src/pipeline.rs:201-271, src_testbed/lib.rs:133-146). */
+enum {
+    B200MPM_PASS_UPDATE_RIGID_PARTICLES = 0,
+    B200MPM_PASS_GRID_SORT = 1,
+    B200MPM_PASS_GRID_UPDATE_CDF = 2,
+    B200MPM_PASS_P2G_CDF = 3,
+    B200MPM_PASS_G2P_CDF = 4,
+    B200MPM_PASS_P2G = 5,
+    B200MPM_PASS_GRID_UPDATE = 6,
+    B200MPM_PASS_G2P = 7,
+    B200MPM_PASS_PARTICLES_UPDATE = 8,
+    B200MPM_PASS_INTEGRATE_BODIES = 9,
+    B200MPM_NUM_PASSES = 10
+};
+
+typedef struct b200mpm_pipeline b200mpm_pipeline; /* MpmPipeline (src/pipeline.rs:24-39) */
+typedef struct b200mpm_data b200mpm_data; /* MpmData (src/pipeline.rs:84-95) */
+
+/* ---- pipeline ------------------------------------------------------------------ */
+
+/* MpmPipeline::new(&Device) (src/pipeline.rs:176-193). `device` is the CUDA ordinal, dim is 2 or 3. */
+int b200mpm_pipeline_create(int device, int dim, b200mpm_pipeline** out);
+void b200mpm_pipeline_destroy(b200mpm_pipeline* p);
+const char* b200mpm_last_error(void);
+/* Kernel launches issued by this pipeline since creation (bench bookkeeping). */
+uint64_t b200mpm_pipeline_launch_count(const b200mpm_pipeline* p);
+
+/* ---- data ---------------------------------------------------------------------- */
+
+/* MpmData::with_select_coupling (src/pipeline.rs:130-168): copies particles and bodies to
+ * the device. grid_capacity is rounded up to a power of two (src/grid/grid.rs:283). */
+int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params,
+                        const b200mpm_particle* particles, size_t num_particles,
+                        const b200mpm_body* bodies, size_t num_bodies, float cell_width,
+                        uint32_t grid_capacity, b200mpm_data** out);
+void b200mpm_data_destroy(b200mpm_data* d);
+size_t b200mpm_data_num_particles(const b200mpm_data* d);
+size_t b200mpm_data_num_bodies(const b200mpm_data* d);
+
+/* ---- stepping ------------------------------------------------------------------ */
+
+/* MpmPipeline::queue_step + `for _ in 0..num_substeps { queue.encode }` + submit
+ * (src/pipeline.rs:195-281, src_testbed/step.rs:122-128,169): enqueues `num_substeps`
+ * substeps on the pipeline's stream and returns without waiting. */
+int b200mpm_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps);
+/* device.poll(Maintain::Wait) (src/pipeline.rs:339). */
+int b200mpm_sync(b200mpm_pipeline* p);
+/* Toggle per-pass CUDA-event timestamps (queue.compute_pass(name, add_timestamps),
+ * src/pipeline.rs:201); off by default. */
+int b200mpm_set_timestamps(b200mpm_pipeline* p, int enabled);
+/* Accumulated ms per reference pass since the last call (src_testbed/step.rs:219-254). Syncs. */
+int b200mpm_get_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_PASSES]);
+
+/* ---- per-frame host writes / reads (src_testbed/step.rs:79-119,175-176, ui.rs:98-103) -- */
+int b200mpm_write_sim_params(b200mpm_data* d, const b200mpm_sim_params* params);
+int b200mpm_write_body_poses(b200mpm_data* d, const b200mpm_pose* poses, size_t n);
+int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_t n);
+int b200mpm_read_body_poses(b200mpm_data* d, b200mpm_pose* poses, size_t n);
+int b200mpm_read_body_vels(b200mpm_data* d, b200mpm_velocity* vels, size_t n);
+
+/* ---- readback of particle / grid state (tests, renderer hand-off) ------------------ */
+
+/* particles.positions (src/solver/particle3d.rs:177): vec4 per particle (2D: xy00), in the
+ * caller's original particle order. `out` holds 4*num_particles floats. */
+int b200mpm_read_positions(b200mpm_data* d, float* out);
+/* Full particle state, original order. */
+int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out);
+/* Sparse grid after the last substep, in the device's own block order.
+ * blocks: capacity entries max; nodes: 64 per block. Returns the count in *num_blocks. */
+int b200mpm_read_grid(b200mpm_data* d, b200mpm_block_info* blocks, b200mpm_node* nodes,
+                      size_t capacity, size_t* num_blocks);
+/* sorted_particle_ids (src/solver/particle3d.rs:179) expressed in ORIGINAL particle ids. */
+int b200mpm_read_sorted_ids(b200mpm_data* d, uint32_t* out);
+/* Number of active blocks after the last substep; B200MPM_ERR_GRID_OVERFLOW if the
+ * block capacity was exceeded at any point (the reference drops blocks silently,
+ * grid.wgsl:126-128). */
+int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks);
+
+/* Run only the "grid sort" pass (WgGrid::queue_sort, src/grid/grid.rs:30-207) — mirrors the
+ * reference's gpu_grid_sort smoke test (grid.rs:347-402). */
+int b200mpm_sort_only(b200mpm_pipeline* p, b200mpm_data* d);
+
+/* WgPrefixSum::queue on a host vector (src/grid/prefix_sum.rs:20-69): in-place exclusive scan
+ * ("as if a 0 was prepended", prefix_sum.rs:7-8) computed on the device. */
+int b200mpm_prefix_sum_u32(b200mpm_pipeline* p, uint32_t* data, size_t len);
+
+/* ---- multi-GPU slab sharding (new) ----------------------------------- */
+
+/* Attach this rank's data to a slab decomposition along block-x. The data owns particles whose
+ * block x-index lies in [x_lo, x_hi). Exchange buffers are plain host-visible staging areas:
+ * the caller (torch.distributed / NCCL in the Python host, NCCL in a Rust host) moves them
+ * between ranks. See INTEGRATION.md. */
+int b200mpm_slab_configure(b200mpm_data* d, int rank, int world, int32_t x_lo, int32_t x_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MPM_H */

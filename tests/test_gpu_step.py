@@ -1,0 +1,183 @@
+"""GPU parity of whole substeps (MpmPipeline::queue_step, src/pipeline.rs:195-281) against the oracle.
+
+Primary gate: ONE substep from an identical, developed state, fields within
+1e-5 relative (norm-wise, relative to the largest magnitude of the field). Secondary: positions within
+1e-4 after 100 substeps on an elastic scene. Tolerances are f32 summation-order / SVD-conditioning
+bounds, written next to each assertion. All calls go through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import parity
+from wgsparkl_b200 import abi, scenes
+from wgsparkl_b200.pipeline import MpmData
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # BASELINE.md §5 primary gate
+
+
+def developed_state(oracle_mod, scene, substeps):
+    """Advance the scene with the oracle so that F, affine, velocities and cdf are non-trivial, and
+    return the particle array to be used as the common initial state."""
+    sim = oracle_mod.OracleSim(scene["dim"], scene["params"], scene["particles"], scene["bodies"], scene["cell_width"],
+                               scene["grid_capacity"])
+    sim.step(substeps)
+    parts = sim.read_particles()
+    poses, vels = sim.read_body_poses(), sim.read_body_vels()
+    sim.close()
+    return parts, poses, vels
+
+
+def one_substep_both(oracle_mod, pipe, scene, particles, n=1):
+    data = MpmData(pipe, scene["params"], particles, scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    sim = oracle_mod.OracleSim(scene["dim"], scene["params"], particles, scene["bodies"], scene["cell_width"],
+                               scene["grid_capacity"])
+    pipe.queue_step(data, n)
+    pipe.sync()
+    sim.step(n)
+    return data, sim
+
+
+def test_reference_pipeline_queue_step_scene(pipe3, oracle_mod):
+    """The reference's pipeline_queue_step smoke test (pipeline.rs:296-343): 10^3 lattice on round() ties,
+    plasticity None / phase None => Drucker-Prager with lambda = mu = -1. 3 substeps."""
+    scene = scenes.reference_test_lattice()
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, scene["particles"], n=3)
+    g, o = data.read_particles(), sim.read_particles()
+    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6})
+    assert data.status()[0] == sim.num_active_blocks()
+    for f in ("plastic_det", "plastic_hardening", "plastic_log_vol_gain"):
+        assert parity.field_rel_err(g[f], o[f]) <= 1e-5
+    data.close()
+
+
+@pytest.mark.parametrize("ground", [False, True])
+def test_one_substep_elastic_cube(pipe3, oracle_mod, ground):
+    """Config-2 physics at test size: corotated elasticity, cube resting on / bouncing off the ground cuboid."""
+    scene = scenes.elastic_cube_3d(16, y_offset=-6.0 if ground else 3.0, ground=ground)
+    scene["particles"]["velocity"][:, 1] = -4.0
+    parts, _, _ = developed_state(oracle_mod, scene, 60)
+    if ground:
+        # Push part of the contact layer through the ground surface (y = -3): their colour is latched
+        # "outside" (g2p_cdf.wgsl:179-188), so the next substep sees negative signed distances and runs
+        # the CPIC projection + penalty branches (particle_update.wgsl:64-83).
+        low = (parts["cdf_affinity"] != 0) & (parts["position"][:, 1] < -2.8) & (parts["position"][:, 0] > 0.0)
+        assert low.sum() > 20
+        parts["position"][low, 1] -= 0.25
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, parts)
+    g, o = data.read_particles(), sim.read_particles()
+    gb, gn = data.read_grid()
+    ob, on = sim.read_grid()
+    parity.assert_grid_close(gb, gn, ob, on, TOL)
+    # position: 2e-6 of the domain extent = a few f32 ulps; affine: stress term carries the f32 SVD
+    # conditioning 2 mu eps (see DESIGN.md "Tolerances")
+    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-4})
+    if ground:
+        assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
+        assert (o["cdf_affinity"] != 0).sum() > 100, "test scene must exercise CPIC"
+        assert (o["cdf_signed_distance"] < -0.05).sum() > 20, "test scene must exercise penetration"
+        for f in ("cdf_normal", "cdf_signed_distance", "cdf_rigid_vel"):
+            assert parity.field_rel_err(g[f], o[f]) <= 1e-4, f
+    data.close()
+
+
+def test_one_substep_sand(pipe3, oracle_mod):
+    """Config-3 physics at test size: Drucker-Prager sand on the ground cuboid, developed for 60 substeps."""
+    scene = scenes.sand_column_3d(12, 24, 12, y_offset=-5.0)
+    parts, _, _ = developed_state(oracle_mod, scene, 60)
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, parts)
+    g, o = data.read_particles(), sim.read_particles()
+    errs = parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-3, "def_grad": 1e-4})
+    # plastic state: hardening accumulates |strain| ~ 1e-3 increments computed from log(sigma) of
+    # sigma ~ 1 +- 1e-3 in f32 => absolute 1e-7 / relative 1e-4 of the increment
+    assert parity.field_rel_err(g["plastic_hardening"], o["plastic_hardening"]) <= 1e-4, errs
+    assert parity.field_rel_err(g["plastic_log_vol_gain"], o["plastic_log_vol_gain"]) <= 1e-2
+    assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
+    data.close()
+
+
+def test_hundred_substeps_elastic(pipe3, oracle_mod):
+    """Secondary gate: positions within 1e-4 (relative to the domain extent) after 100 substeps."""
+    scene = scenes.elastic_cube_3d(12, y_offset=-5.0)
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, scene["particles"], n=100)
+    g, o = data.read_particles(), sim.read_particles()
+    assert parity.field_rel_err(g["position"], o["position"]) <= 1e-4
+    assert parity.field_rel_err(g["velocity"], o["velocity"]) <= 1e-2
+    data.close()
+
+
+def test_one_substep_2d(pipe2, oracle_mod):
+    """Config 1 (2D elastic block on a cuboid) at test size."""
+    scene = scenes.elastic_block_2d(40)
+    scene["particles"]["position"][:, 1] -= 9.9  # start in contact with the ground
+    parts, _, _ = developed_state(oracle_mod, scene, 40)
+    data, sim = one_substep_both(oracle_mod, pipe2, scene, parts)
+    g, o = data.read_particles(), sim.read_particles()
+    gb, gn = data.read_grid()
+    ob, on = sim.read_grid()
+    parity.assert_grid_close(gb, gn, ob, on, TOL)
+    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-4})
+    assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
+    data.close()
+
+
+def test_two_way_coupling_bodies(pipe3, oracle_mod):
+    """Config-4 physics at test size: sand + Neo-Hookean solids, kinematic rotating cuboid and dynamic
+    cuboids; body poses / velocities integrated on the device (rigid_impulses.wgsl:94-137)."""
+    scene = scenes.mixed_coupled_3d(12, 12, 12, n_dynamic=2)
+    # drop the dynamic bodies right onto the material so that impulses flow within the test window
+    scene["bodies"]["translation"][2:, 1] = 12.0
+    parts, poses, vels = developed_state(oracle_mod, scene, 30)
+    scene2 = dict(scene)
+    bodies = scene["bodies"].copy()
+    bodies["translation"] = poses["translation"]
+    bodies["rotation"] = poses["rotation"]
+    bodies["linvel"] = vels["linear"]
+    bodies["angvel"] = vels["angular"]
+    scene2["bodies"] = bodies
+    data, sim = one_substep_both(oracle_mod, pipe3, scene2, parts, n=1)
+    g, o = data.read_particles(), sim.read_particles()
+    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-3, "def_grad": 1e-4})
+    gp, op = data.read_body_poses(), sim.read_body_poses()
+    gv, ov = data.read_body_vels(), sim.read_body_vels()
+    assert parity.field_rel_err(gp["translation"], op["translation"]) <= 1e-6
+    assert parity.field_rel_err(gp["rotation"], op["rotation"]) <= 1e-6
+    # impulses are accumulated as i32(x * 1e5) per node (rigid_impulses.wgsl:50-58); the CUDA path
+    # truncates per (node, contributing block): a few 1e-5 absolute per node
+    assert parity.field_rel_err(gv["linear"], ov["linear"]) <= 1e-4
+    assert parity.field_rel_err(gv["angular"], ov["angular"]) <= 1e-4
+    data.close()
+
+
+def test_host_writes_take_effect(pipe3):
+    scene = scenes.elastic_cube_3d(8, y_offset=3.0)
+    data = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    poses = data.read_body_poses()
+    poses["translation"][0] = [1.0, -5.0, 2.0]
+    data.write_body_poses(poses)
+    vels = data.read_body_vels()
+    vels["linear"][0] = [0.5, 0.0, 0.0]
+    data.write_body_vels(vels)
+    assert np.allclose(data.read_body_poses()["translation"][0], [1.0, -5.0, 2.0])
+    assert np.allclose(data.read_body_vels()["linear"][0], [0.5, 0.0, 0.0])
+    from wgsparkl_b200 import SimulationParams
+
+    data.write_sim_params(SimulationParams([0.0, 0.0, 0.0], 1e-3))
+    pipe3.queue_step(data, 5)
+    pipe3.sync()
+    out = data.read_particles()
+    assert np.abs(out["velocity"]).max() < 1e-3  # gravity switched off
+    data.close()
+
+
+def test_timings_use_reference_pass_names(pipe3):
+    scene = scenes.elastic_cube_3d(8, y_offset=3.0)
+    data = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    pipe3.set_timestamps(True)
+    pipe3.queue_step(data, 4)
+    t = pipe3.timings_ms()
+    pipe3.set_timestamps(False)
+    assert tuple(t.keys()) == abi.PASS_NAMES
+    assert t["p2g"] > 0.0 and t["g2p"] > 0.0 and t["grid sort"] > 0.0
+    data.close()

@@ -1,0 +1,720 @@
+// C ABI (include/b200mpm.h) and host-side orchestration of one MPM substep.
+// Mirrors MpmPipeline / MpmData (src/pipeline.rs:24-39, 84-95) — see INTEGRATION.md for the
+// Rust-side binding. No CPU fallback: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "launch.h"
+
+using namespace b2;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            int _code = (_e == cudaErrorMemoryAllocation) ? B200MPM_ERR_OUT_OF_MEMORY : B200MPM_ERR_CUDA; \
+            return fail(_code, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+        }                                                                                              \
+    } while (0)
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int pass;
+};
+
+} // namespace
+
+struct b200mpm_pipeline {
+    int device = 0;
+    int dim = 3;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    bool timestamps = false;
+    std::vector<EventPair> events;
+    std::vector<cudaEvent_t> event_pool;
+    double pass_ms[B200MPM_NUM_PASSES] = {0};
+    // scratch for b200mpm_prefix_sum_u32
+    LaunchCfg cfg() { return LaunchCfg{dim, num_sms, stream, &launches}; }
+};
+
+struct b200mpm_data {
+    b200mpm_pipeline* pipe = nullptr;
+    DeviceData dev{};
+    int cur = 0;
+    bool sorted_indirect = true; // sorted_ids is an indirection into `cur` (no full substep since the last sort)
+    uint32_t num_bodies = 0;
+    std::vector<void*> allocs;
+    void* staging = nullptr; // device staging for readbacks / host writes
+    size_t staging_bytes = 0;
+    void* pinned = nullptr; // pinned host mirror of small transfers
+    size_t pinned_bytes = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(b200mpm_data* d, T** out, size_t count, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    CU_TRY(cudaMalloc(&p, bytes));
+    d->allocs.push_back(p);
+    if (zero) CU_TRY(cudaMemsetAsync(p, 0, bytes, d->pipe->stream));
+    *out = (T*)p;
+    return 0;
+}
+
+int ensure_staging(b200mpm_data* d, size_t bytes) {
+    if (d->staging_bytes >= bytes) return 0;
+    if (d->staging) cudaFree(d->staging);
+    d->staging = nullptr;
+    d->staging_bytes = 0;
+    CU_TRY(cudaMalloc(&d->staging, bytes));
+    d->staging_bytes = bytes;
+    return 0;
+}
+int ensure_pinned(b200mpm_data* d, size_t bytes) {
+    if (d->pinned_bytes >= bytes) return 0;
+    if (d->pinned) cudaFreeHost(d->pinned);
+    d->pinned = nullptr;
+    d->pinned_bytes = 0;
+    CU_TRY(cudaMallocHost(&d->pinned, bytes));
+    d->pinned_bytes = bytes;
+    return 0;
+}
+
+struct PassTimer { // queue.compute_pass(name, add_timestamps) (src/pipeline.rs:201)
+    b200mpm_pipeline* p;
+    cudaEvent_t a = nullptr;
+    int pass;
+    PassTimer(b200mpm_pipeline* pipe, int pass_id) : p(pipe), pass(pass_id) {
+        if (!p->timestamps) return;
+        a = take();
+        cudaEventRecord(a, p->stream);
+    }
+    cudaEvent_t take() {
+        if (!p->event_pool.empty()) {
+            cudaEvent_t e = p->event_pool.back();
+            p->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    ~PassTimer() {
+        if (!p->timestamps) return;
+        cudaEvent_t b = take();
+        cudaEventRecord(b, p->stream);
+        p->events.push_back(EventPair{a, b, pass});
+    }
+};
+
+void fold_events(b200mpm_pipeline* p) {
+    if (p->events.empty()) return;
+    cudaStreamSynchronize(p->stream);
+    for (auto& e : p->events) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        p->pass_ms[e.pass] += ms;
+        p->event_pool.push_back(e.a);
+        p->event_pool.push_back(e.b);
+    }
+    p->events.clear();
+}
+
+void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
+    LaunchCfg c = p->cfg();
+    {
+        PassTimer t(p, B200MPM_PASS_GRID_SORT);
+        launch_clear(c, d->dev);
+        launch_touch(c, d->dev, d->cur);
+        launch_count(c, d->dev);
+        launch_scan_cells(c, d->dev);
+        launch_scatter(c, d->dev);
+    }
+    {
+        PassTimer t(p, B200MPM_PASS_GRID_UPDATE_CDF);
+        launch_block_prepare(c, d->dev);
+    }
+}
+
+void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
+    LaunchCfg c = p->cfg();
+    {
+        PassTimer t(p, B200MPM_PASS_UPDATE_RIGID_PARTICLES);
+        launch_begin_substep(c, d->dev);
+    }
+    run_sort(p, d);
+    {
+        PassTimer t(p, B200MPM_PASS_G2P_CDF);
+        launch_g2p_cdf(c, d->dev, d->cur);
+    }
+    {
+        PassTimer t(p, B200MPM_PASS_P2G);
+        launch_p2g(c, d->dev, d->cur);
+    }
+    {
+        PassTimer t(p, B200MPM_PASS_G2P); // grid_update + g2p + particles_update are one kernel here
+        launch_g2p_update(c, d->dev, d->cur);
+    }
+    {
+        PassTimer t(p, B200MPM_PASS_INTEGRATE_BODIES);
+        launch_integrate_bodies(c, d->dev);
+    }
+    d->cur ^= 1;
+    d->sorted_indirect = false;
+    if (p->timestamps && p->events.size() > 4096) fold_events(p);
+}
+
+bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
+
+} // namespace
+
+extern "C" {
+
+const char* b200mpm_last_error(void) { return g_last_error.c_str(); }
+
+int b200mpm_pipeline_create(int device, int dim, b200mpm_pipeline** out) {
+    if (!out) return fail(B200MPM_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(B200MPM_ERR_INVALID_ARGUMENT, "dim must be 2 or 3");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(B200MPM_ERR_NO_DEVICE, "no CUDA device is visible; this library has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(B200MPM_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(B200MPM_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100; kernels are built for sm_100a only");
+    CU_TRY(cudaSetDevice(device));
+    auto* p = new b200mpm_pipeline();
+    p->device = device;
+    p->dim = dim;
+    p->num_sms = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(B200MPM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = p;
+    return B200MPM_OK;
+}
+
+void b200mpm_pipeline_destroy(b200mpm_pipeline* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    for (auto& e : p->events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    for (auto e : p->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+uint64_t b200mpm_pipeline_launch_count(const b200mpm_pipeline* p) { return p ? p->launches : 0; }
+
+int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, const b200mpm_particle* particles,
+                        size_t num_particles, const b200mpm_body* bodies, size_t num_bodies, float cell_width,
+                        uint32_t grid_capacity, b200mpm_data** out) {
+    if (!p || !params || !out) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (num_particles && !particles) return fail(B200MPM_ERR_INVALID_ARGUMENT, "particles is null");
+    if (num_bodies && !bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "bodies is null");
+    if (num_bodies > B200MPM_MAX_BODIES)
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "at most 16 coupled colliders are supported (rigid_impulses.rs:42)");
+    if (!(cell_width > 0.0f)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "cell_width must be positive");
+    if (grid_capacity == 0 || grid_capacity > (1u << 24))
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "grid_capacity must be in [1, 2^24]");
+    if (num_particles >= (1ull << 31)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "too many particles");
+    for (size_t i = 0; i < num_bodies; ++i)
+        if (bodies[i].shape_type > B200MPM_SHAPE_CAPSULE)
+            return fail(B200MPM_ERR_INVALID_ARGUMENT, "unsupported collider shape (ball, cuboid, capsule only)");
+    CU_TRY(cudaSetDevice(p->device));
+
+    uint32_t capacity = 1;
+    while (capacity < grid_capacity) capacity <<= 1; // grid.rs:283
+    const int D = p->dim;
+    const uint32_t n = (uint32_t)num_particles;
+
+    auto* d = new b200mpm_data();
+    d->pipe = p;
+    d->num_bodies = (uint32_t)num_bodies;
+    DeviceData& dev = d->dev;
+    dev.n = n;
+    dev.capacity = capacity;
+    dev.has_bodies = num_bodies > 0;
+
+    // ---- material table (dedup of the per-particle model buffers) + SoA staging on the host
+    std::vector<Material> materials;
+    std::unordered_map<std::string, uint32_t> mat_index;
+    std::vector<float4> pos4(n), vel4(n), Fa(n), Ca(n), Fb, Cb, plastic;
+    std::vector<float> Fc, Cc;
+    std::vector<uint32_t> aff;
+    std::vector<float4> cdf_nd, cdf_rv;
+    if (D == 3) {
+        Fb.resize(n);
+        Cb.resize(n);
+        Fc.resize(n);
+        Cc.resize(n);
+    }
+    bool has_plastic = false;
+    plastic.resize(n);
+    if (dev.has_bodies) {
+        aff.resize(n);
+        cdf_nd.resize(n);
+        cdf_rv.resize(n);
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const b200mpm_particle& q = particles[i];
+        Material m{};
+        m.mass = q.mass;
+        m.init_volume = q.init_volume;
+        m.init_radius = q.init_radius;
+        m.lambda = q.lambda;
+        m.mu = q.mu;
+        m.dp_h0 = q.dp_h0, m.dp_h1 = q.dp_h1, m.dp_h2 = q.dp_h2, m.dp_h3 = q.dp_h3;
+        m.dp_lambda = q.dp_lambda, m.dp_mu = q.dp_mu;
+        m.phase = q.phase;
+        m.max_stretch = q.max_stretch;
+        m.model = q.model;
+        std::string key((const char*)&m, sizeof(Material));
+        auto it = mat_index.find(key);
+        uint32_t mid;
+        if (it == mat_index.end()) {
+            mid = (uint32_t)materials.size();
+            if (mid > MAT_ID_MASK) {
+                delete d;
+                return fail(B200MPM_ERR_INVALID_ARGUMENT, "too many distinct materials");
+            }
+            materials.push_back(m);
+            mat_index.emplace(std::move(key), mid);
+        } else {
+            mid = it->second;
+        }
+        // A particle can reach phase == 0 (plastic) if it starts there or can break by stretch
+        // (particle_update.wgsl:101-122).
+        if (q.phase == 0.0f || (q.phase > 0.0f && q.max_stretch > 0.0f && q.max_stretch < 3.0e38f)) has_plastic = true;
+        union {
+            uint32_t u;
+            float f;
+        } mb, ob;
+        mb.u = mid;
+        ob.u = i;
+        pos4[i] = make_float4(q.position[0], q.position[1], D == 3 ? q.position[2] : 0.0f, mb.f);
+        vel4[i] = make_float4(q.velocity[0], q.velocity[1], D == 3 ? q.velocity[2] : 0.0f, ob.f);
+        Fa[i] = make_float4(q.def_grad[0], q.def_grad[1], q.def_grad[2], q.def_grad[3]);
+        Ca[i] = make_float4(q.affine[0], q.affine[1], q.affine[2], q.affine[3]);
+        if (D == 3) {
+            Fb[i] = make_float4(q.def_grad[4], q.def_grad[5], q.def_grad[6], q.def_grad[7]);
+            Fc[i] = q.def_grad[8];
+            Cb[i] = make_float4(q.affine[4], q.affine[5], q.affine[6], q.affine[7]);
+            Cc[i] = q.affine[8];
+        }
+        plastic[i] = make_float4(q.plastic_det, q.plastic_hardening, q.plastic_log_vol_gain, 0.0f);
+        if (dev.has_bodies) {
+            aff[i] = q.cdf_affinity;
+            cdf_nd[i] = make_float4(q.cdf_normal[0], q.cdf_normal[1], D == 3 ? q.cdf_normal[2] : 0.0f, q.cdf_signed_distance);
+            cdf_rv[i] = make_float4(q.cdf_rigid_vel[0], q.cdf_rigid_vel[1], D == 3 ? q.cdf_rigid_vel[2] : 0.0f, 0.0f);
+        }
+    }
+    dev.has_plastic = has_plastic;
+    dev.num_materials = (uint32_t)materials.size();
+
+#define ALLOC(ptr, count)                                     \
+    do {                                                      \
+        int _r = dev_alloc(d, &(ptr), (count));               \
+        if (_r != 0) {                                        \
+            b200mpm_data_destroy(d);                          \
+            return _r;                                        \
+        }                                                     \
+    } while (0)
+#define UPLOAD(ptr, vec)                                                                                          \
+    do {                                                                                                          \
+        if (!(vec).empty()) {                                                                                     \
+            cudaError_t _e = cudaMemcpyAsync((ptr), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, p->stream); \
+            if (_e != cudaSuccess) {                                                                              \
+                b200mpm_data_destroy(d);                                                                          \
+                return fail(B200MPM_ERR_CUDA, cudaGetErrorString(_e));                                            \
+            }                                                                                                     \
+        }                                                                                                         \
+    } while (0)
+
+    for (int s = 0; s < 2; ++s) {
+        ALLOC(dev.pos4[s], n);
+        ALLOC(dev.vel4[s], n);
+        ALLOC(dev.Fa[s], n);
+        ALLOC(dev.Ca[s], n);
+        if (D == 3) {
+            ALLOC(dev.Fb[s], n);
+            ALLOC(dev.Fc[s], n);
+            ALLOC(dev.Cb[s], n);
+            ALLOC(dev.Cc[s], n);
+        }
+        if (has_plastic) ALLOC(dev.plastic[s], n);
+        if (dev.has_bodies) ALLOC(dev.cdf_aff[s], n);
+    }
+    if (dev.has_bodies) {
+        ALLOC(dev.cdf_nd, n);
+        ALLOC(dev.cdf_rv, n);
+    }
+    Material* dmat = nullptr;
+    ALLOC(dmat, materials.size());
+    dev.materials = dmat;
+    ALLOC(dev.pkey, n);
+    ALLOC(dev.rank, n);
+    ALLOC(dev.sorted_ids, n);
+    ALLOC(dev.hkeys, capacity);
+    ALLOC(dev.hvals, capacity);
+    ALLOC(dev.block_vid, capacity);
+    ALLOC(dev.cell_start, (size_t)capacity * CELLS_PER_BLOCK + 1);
+    ALLOC(dev.nbr, (size_t)capacity * (D == 2 ? 4 : 8));
+    ALLOC(dev.node_mv, (size_t)capacity * CELLS_PER_BLOCK);
+    if (dev.has_bodies) ALLOC(dev.node_cdf, (size_t)capacity * CELLS_PER_BLOCK);
+    ALLOC(dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2);
+    ALLOC(dev.bodies, B200MPM_MAX_BODIES);
+    ALLOC(dev.sim, 1);
+    ALLOC(dev.counters, 1);
+
+    UPLOAD(dev.pos4[0], pos4);
+    UPLOAD(dev.vel4[0], vel4);
+    UPLOAD(dev.Fa[0], Fa);
+    UPLOAD(dev.Ca[0], Ca);
+    if (D == 3) {
+        UPLOAD(dev.Fb[0], Fb);
+        UPLOAD(dev.Fc[0], Fc);
+        UPLOAD(dev.Cb[0], Cb);
+        UPLOAD(dev.Cc[0], Cc);
+    }
+    if (has_plastic) UPLOAD(dev.plastic[0], plastic);
+    if (dev.has_bodies) {
+        UPLOAD(dev.cdf_aff[0], aff);
+        UPLOAD(dev.cdf_nd, cdf_nd);
+        UPLOAD(dev.cdf_rv, cdf_rv);
+    }
+    UPLOAD(dmat, materials);
+
+    std::vector<BodyDev> hb(B200MPM_MAX_BODIES);
+    std::memset(hb.data(), 0, hb.size() * sizeof(BodyDev));
+    for (size_t i = 0; i < num_bodies; ++i) {
+        const b200mpm_body& s = bodies[i];
+        BodyDev& b = hb[i];
+        b.shape_type = s.shape_type;
+        for (int k = 0; k < 3; ++k) {
+            b.shape_a[k] = s.shape_a[k];
+            b.shape_b[k] = s.shape_b[k];
+            b.trans[k] = s.translation[k];
+            b.linvel[k] = s.linvel[k];
+            b.angvel[k] = s.angvel[k];
+            b.local_inv_mass[k] = s.two_ways ? s.inv_mass[k] : 0.0f;
+            b.local_com[k] = s.local_com[k];
+        }
+        b.radius = s.radius;
+        for (int k = 0; k < 4; ++k) b.rot_raw[k] = s.rotation[k];
+        for (int k = 0; k < 9; ++k) b.local_inv_inertia[k] = s.two_ways ? s.inv_inertia[k] : 0.0f;
+        if (D == 2) {
+            b.rot[0] = s.rotation[0], b.rot[1] = s.rotation[1], b.rot[2] = -s.rotation[1], b.rot[3] = s.rotation[0];
+        } else {
+            float i_ = s.rotation[0], j_ = s.rotation[1], k_ = s.rotation[2], w_ = s.rotation[3];
+            b.rot[0] = 1.0f - 2.0f * (j_ * j_ + k_ * k_);
+            b.rot[1] = 2.0f * (i_ * j_ + k_ * w_);
+            b.rot[2] = 2.0f * (i_ * k_ - j_ * w_);
+            b.rot[3] = 2.0f * (i_ * j_ - k_ * w_);
+            b.rot[4] = 1.0f - 2.0f * (i_ * i_ + k_ * k_);
+            b.rot[5] = 2.0f * (j_ * k_ + i_ * w_);
+            b.rot[6] = 2.0f * (i_ * k_ + j_ * w_);
+            b.rot[7] = 2.0f * (j_ * k_ - i_ * w_);
+            b.rot[8] = 1.0f - 2.0f * (i_ * i_ + j_ * j_);
+        }
+        for (int k = 0; k < 3; ++k) b.com[k] = b.trans[k]; // refreshed by the first substep
+    }
+    UPLOAD(dev.bodies, hb);
+    std::vector<SimState> hs(1);
+    hs[0].gravity[0] = params->gravity[0];
+    hs[0].gravity[1] = params->gravity[1];
+    hs[0].gravity[2] = (D == 3) ? params->gravity[2] : 0.0f;
+    hs[0].dt = params->dt;
+    hs[0].cell_width = cell_width;
+    hs[0].num_bodies = (uint32_t)num_bodies;
+    UPLOAD(dev.sim, hs);
+#undef ALLOC
+#undef UPLOAD
+    cudaError_t e = cudaStreamSynchronize(p->stream); // host vectors go out of scope
+    if (e != cudaSuccess) {
+        b200mpm_data_destroy(d);
+        return fail(B200MPM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = d;
+    return B200MPM_OK;
+}
+
+void b200mpm_data_destroy(b200mpm_data* d) {
+    if (!d) return;
+    cudaSetDevice(d->pipe->device);
+    cudaStreamSynchronize(d->pipe->stream);
+    for (void* p : d->allocs) cudaFree(p);
+    if (d->staging) cudaFree(d->staging);
+    if (d->pinned) cudaFreeHost(d->pinned);
+    delete d;
+}
+
+size_t b200mpm_data_num_particles(const b200mpm_data* d) { return d ? d->dev.n : 0; }
+size_t b200mpm_data_num_bodies(const b200mpm_data* d) { return d ? d->num_bodies : 0; }
+
+int b200mpm_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps) {
+    if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
+    CU_TRY(cudaSetDevice(p->device));
+    for (uint32_t s = 0; s < num_substeps; ++s) run_substep(p, d);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_sort_only(b200mpm_pipeline* p, b200mpm_data* d) {
+    if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
+    CU_TRY(cudaSetDevice(p->device));
+    LaunchCfg c = p->cfg();
+    launch_begin_substep(c, d->dev);
+    run_sort(p, d);
+    d->sorted_indirect = true;
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_sync(b200mpm_pipeline* p) {
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null pipeline");
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_set_timestamps(b200mpm_pipeline* p, int enabled) {
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null pipeline");
+    if (!enabled) fold_events(p);
+    p->timestamps = enabled != 0;
+    return B200MPM_OK;
+}
+
+int b200mpm_get_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_PASSES]) {
+    if (!p || !ms) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    fold_events(p);
+    for (int i = 0; i < B200MPM_NUM_PASSES; ++i) {
+        ms[i] = p->pass_ms[i];
+        p->pass_ms[i] = 0.0;
+    }
+    return B200MPM_OK;
+}
+
+int b200mpm_write_sim_params(b200mpm_data* d, const b200mpm_sim_params* params) {
+    if (!d || !params) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    int r = ensure_pinned(d, 4096);
+    if (r) return r;
+    CU_TRY(cudaStreamSynchronize(p->stream)); // the pinned mirror may still be in flight
+    float* h = (float*)d->pinned;
+    h[0] = params->gravity[0];
+    h[1] = params->gravity[1];
+    h[2] = (p->dim == 3) ? params->gravity[2] : 0.0f;
+    h[3] = params->dt;
+    CU_TRY(cudaMemcpyAsync(d->dev.sim, h, 4 * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_write_body_poses(b200mpm_data* d, const b200mpm_pose* poses, size_t n) {
+    if (!d || (!poses && n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (n > d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "more poses than bodies");
+    if (n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    int r = ensure_pinned(d, 4096);
+    if (r) return r;
+    r = ensure_staging(d, 4096);
+    if (r) return r;
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    std::memcpy(d->pinned, poses, n * sizeof(b200mpm_pose));
+    CU_TRY(cudaMemcpyAsync(d->staging, d->pinned, n * sizeof(b200mpm_pose), cudaMemcpyHostToDevice, p->stream));
+    launch_write_poses(p->cfg(), d->dev, (const b200mpm_pose*)d->staging, (uint32_t)n);
+    CU_TRY(cudaStreamSynchronize(p->stream)); // staging is reused by the next write
+    return B200MPM_OK;
+}
+
+int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_t n) {
+    if (!d || (!vels && n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (n > d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "more velocities than bodies");
+    if (n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    int r = ensure_pinned(d, 4096);
+    if (r) return r;
+    r = ensure_staging(d, 4096);
+    if (r) return r;
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    std::memcpy(d->pinned, vels, n * sizeof(b200mpm_velocity));
+    CU_TRY(cudaMemcpyAsync(d->staging, d->pinned, n * sizeof(b200mpm_velocity), cudaMemcpyHostToDevice, p->stream));
+    launch_write_vels(p->cfg(), d->dev, (const b200mpm_velocity*)d->staging, (uint32_t)n);
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+static int read_body_state(b200mpm_data* d, b200mpm_pose* poses, b200mpm_velocity* vels, size_t n) {
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (n > d->num_bodies) n = d->num_bodies;
+    if (n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    int r = ensure_pinned(d, 4096);
+    if (r) return r;
+    r = ensure_staging(d, 4096);
+    if (r) return r;
+    b200mpm_pose* dp = (b200mpm_pose*)d->staging;
+    b200mpm_velocity* dv = (b200mpm_velocity*)((char*)d->staging + 2048);
+    launch_read_poses(p->cfg(), d->dev, poses ? dp : nullptr, vels ? dv : nullptr, (uint32_t)n);
+    CU_TRY(cudaMemcpyAsync(d->pinned, d->staging, 4096, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    if (poses) std::memcpy(poses, d->pinned, n * sizeof(b200mpm_pose));
+    if (vels) std::memcpy(vels, (char*)d->pinned + 2048, n * sizeof(b200mpm_velocity));
+    return B200MPM_OK;
+}
+int b200mpm_read_body_poses(b200mpm_data* d, b200mpm_pose* poses, size_t n) {
+    if (!poses && n) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    return read_body_state(d, poses, nullptr, n);
+}
+int b200mpm_read_body_vels(b200mpm_data* d, b200mpm_velocity* vels, size_t n) {
+    if (!vels && n) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    return read_body_state(d, nullptr, vels, n);
+}
+
+int b200mpm_read_positions(b200mpm_data* d, float* out) {
+    if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (d->dev.n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    size_t bytes = (size_t)d->dev.n * sizeof(float4);
+    int r = ensure_staging(d, bytes);
+    if (r) return r;
+    launch_gather_positions(p->cfg(), d->dev, d->cur, (float4*)d->staging);
+    CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out) {
+    if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (d->dev.n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    size_t bytes = (size_t)d->dev.n * sizeof(b200mpm_particle);
+    int r = ensure_staging(d, bytes);
+    if (r) return r;
+    launch_gather_particles(p->cfg(), d->dev, d->cur, (b200mpm_particle*)d->staging);
+    CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks) {
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    Counters c;
+    CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    if (num_active_blocks) *num_active_blocks = std::min(c.num_active_blocks, d->dev.capacity);
+    if (c.overflow) return fail(B200MPM_ERR_GRID_OVERFLOW, "grid block capacity exceeded: blocks were dropped");
+    return B200MPM_OK;
+}
+
+int b200mpm_read_grid(b200mpm_data* d, b200mpm_block_info* blocks, b200mpm_node* nodes, size_t capacity,
+                      size_t* num_blocks) {
+    if (!d || !num_blocks) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    uint32_t nb = 0;
+    int st = b200mpm_data_status(d, &nb);
+    if (st != B200MPM_OK && st != B200MPM_ERR_GRID_OVERFLOW) return st;
+    size_t take = std::min<size_t>(nb, capacity);
+    *num_blocks = take;
+    if (take == 0) return B200MPM_OK;
+    if (!blocks || !nodes) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null output");
+    b200mpm_pipeline* p = d->pipe;
+    size_t bbytes = take * sizeof(b200mpm_block_info);
+    size_t boff = (bbytes + 255) & ~(size_t)255;
+    size_t nbytes = take * CELLS_PER_BLOCK * sizeof(b200mpm_node);
+    int r = ensure_staging(d, boff + nbytes);
+    if (r) return r;
+    b200mpm_block_info* db = (b200mpm_block_info*)d->staging;
+    b200mpm_node* dn = (b200mpm_node*)((char*)d->staging + boff);
+    launch_gather_grid(p->cfg(), d->dev, db, dn, (uint32_t)take);
+    CU_TRY(cudaMemcpyAsync(blocks, db, bbytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaMemcpyAsync(nodes, dn, nbytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_read_sorted_ids(b200mpm_data* d, uint32_t* out) {
+    if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (d->dev.n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    size_t bytes = (size_t)d->dev.n * sizeof(uint32_t);
+    int r = ensure_staging(d, bytes);
+    if (r) return r;
+    launch_gather_sorted_ids(p->cfg(), d->dev, d->cur, d->sorted_indirect ? 1 : 0, (uint32_t*)d->staging);
+    CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_prefix_sum_u32(b200mpm_pipeline* p, uint32_t* data, size_t len) {
+    if (!p || (!data && len)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (len == 0) return B200MPM_OK;
+    if (len >= (1ull << 31)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "vector too long");
+    CU_TRY(cudaSetDevice(p->device));
+    uint32_t* dd = nullptr;
+    uint64_t* state = nullptr;
+    uint32_t* ticket = nullptr;
+    uint32_t tiles = scan_num_tiles(len);
+    CU_TRY(cudaMalloc(&dd, len * sizeof(uint32_t)));
+    cudaError_t e1 = cudaMalloc(&state, (tiles + 2) * sizeof(uint64_t));
+    cudaError_t e2 = cudaMalloc(&ticket, sizeof(uint32_t));
+    int rc = B200MPM_OK;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        rc = fail(B200MPM_ERR_OUT_OF_MEMORY, "cudaMalloc failed");
+    } else {
+        cudaMemcpyAsync(dd, data, len * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream);
+        launch_exclusive_scan_u32(p->cfg(), dd, (uint32_t)len, state, ticket);
+        cudaMemcpyAsync(data, dd, len * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream);
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) rc = fail(B200MPM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dd);
+    if (state) cudaFree(state);
+    if (ticket) cudaFree(ticket);
+    return rc;
+}
+
+int b200mpm_slab_configure(b200mpm_data* d, int rank, int world, int32_t x_lo, int32_t x_hi) {
+    (void)d;
+    (void)rank;
+    (void)world;
+    (void)x_lo;
+    (void)x_hi;
+    return fail(B200MPM_ERR_INVALID_ARGUMENT, "slab sharding is not implemented yet");
+}
+
+} // extern "C"

@@ -1,0 +1,227 @@
+// Shared device-side types and helpers for the B200 MPM substep.
+// Reference citations are file:line relative to the wgsparkl source tree.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200mpm.h"
+
+namespace b2 {
+
+constexpr uint32_t NONE = 0xffffffffu; // grid.wgsl:80
+constexpr int CELLS_PER_BLOCK = 64; // grid.wgsl:43
+constexpr uint32_t MAT_ID_MASK = 0x0fffffffu;
+constexpr uint32_t FLAG_PHASE_BROKEN = 0x80000000u; // phases[i].phase was set to 0 (particle_update.wgsl:106,112)
+
+template <int D>
+struct Dim;
+template <>
+struct Dim<2> {
+    static constexpr int BLOCK = 8; // 8x8 cells per block (particle2d.wgsl:46)
+    static constexpr int TILE = 10; // p2g.wgsl:31
+    static constexpr int TILE_CELLS = 100;
+    static constexpr int NBH = 9; // kernel.wgsl:6
+    static constexpr int NASSOC = 4; // grid.wgsl:209
+    static constexpr int LOG_BLOCK = 3;
+};
+template <>
+struct Dim<3> {
+    static constexpr int BLOCK = 4; // 4x4x4 cells per block (particle3d.wgsl:43)
+    static constexpr int TILE = 6; // p2g.wgsl:38
+    static constexpr int TILE_CELLS = 216;
+    static constexpr int NBH = 27; // kernel.wgsl:22
+    static constexpr int NASSOC = 8; // grid.wgsl:211
+    static constexpr int LOG_BLOCK = 2;
+};
+
+// ---- per-material constants (dedup of the reference's per-particle model buffers) -------
+// ParticleDynamics.{init_volume,init_radius,mass} (particle3d.rs:23-25), ElasticCoefficients
+// (models/mod.rs:63-68), DruckerPrager (drucker_prager.rs:6-15), ParticlePhase
+// (particle_update.rs:37-42). 64 bytes.
+struct __align__(16) Material {
+    float mass, init_volume, init_radius, lambda;
+    float mu, dp_h0, dp_h1, dp_h2;
+    float dp_h3, dp_lambda, dp_mu, phase;
+    float max_stretch;
+    uint32_t model;
+    uint32_t pad0, pad1;
+};
+
+// ---- rigid bodies (wgrapier GpuBodySet + rigid_impulses.wgsl state), <= 16 ---------------
+struct BodyDev {
+    uint32_t shape_type;
+    float shape_a[3];
+    float shape_b[3];
+    float radius;
+    float rot[9]; // rotation matrix, column-major (2D: 2x2 in rot[0..3])
+    float trans[3];
+    float rot_raw[4]; // quaternion (i,j,k,w) / unit complex, what the host reads back
+    float linvel[3];
+    float angvel[3];
+    float local_inv_mass[3];
+    float local_inv_inertia[9];
+    float local_com[3];
+    // world-space mass properties (update_world_mass_properties, rigid_impulses.wgsl:139-150)
+    float com[3];
+    float inv_inertia[9];
+    // IntegerImpulseAtomic (rigid_impulses.wgsl:27-47)
+    int imp_lin[3];
+    int imp_ang[3];
+};
+
+struct SimState {
+    float gravity[3];
+    float dt;
+    float cell_width;
+    uint32_t num_bodies;
+};
+
+// ---- device-resident counters --------------------------------------------------------------
+struct Counters {
+    uint32_t num_active_blocks; // Grid.num_active_blocks (grid.wgsl:223)
+    uint32_t prev_active_blocks; // active count of the previous substep (what has to be cleared)
+    uint32_t overflow; // sticky: the block capacity / hash map was exceeded at least once
+    uint32_t scan_ticket; // dynamic tile id for the single-pass scan
+    uint32_t work_p2g; // dynamic block schedulers
+    uint32_t work_g2p;
+    uint32_t work_cdf;
+    uint32_t dropped_particles; // particles whose block was dropped (overflow)
+};
+
+// ---- all device pointers of one MpmData --------------------------------------------------
+struct DeviceData {
+    uint32_t n; // particles
+    uint32_t capacity; // block capacity == hash capacity (power of two; grid.rs:283)
+    uint32_t num_materials;
+    int has_plastic; // any particle can reach phase == 0
+    int has_bodies; // CPIC on
+
+    // particle state, ping-pong (index 0/1). Layout: see DESIGN.md "Data layout in HBM".
+    float4* pos4[2]; // x y z | bits(material id | flags)
+    float4* vel4[2]; // vx vy vz | bits(original particle id)
+    float4* Fa[2]; // F column-major elements 0..3
+    float4* Fb[2]; // 4..7   (3D only)
+    float* Fc[2]; // 8        (3D only)
+    float4* Ca[2]; // APIC affine (momentum form, particle_update.wgsl:132), elements 0..3
+    float4* Cb[2];
+    float* Cc[2];
+    float4* plastic[2]; // det, hardening, log_vol_gain, - (only if has_plastic)
+    uint32_t* cdf_aff[2]; // particle CPIC affinity (persists across substeps; only if has_bodies)
+    float4* cdf_nd; // normal xyz + signed distance, by sorted slot (only if has_bodies)
+    float4* cdf_rv; // rigid_vel, by sorted slot (only if has_bodies)
+    const Material* materials;
+
+    // sort scratch
+    uint32_t* pkey; // hash slot * 64 + cell-in-block, then (hid * 64 + cell)
+    uint32_t* rank; // rank of the particle inside its cell
+    uint32_t* sorted_ids; // sorted slot -> index into the current particle buffers
+
+    // sparse grid
+    uint32_t* hkeys; // packed block key or NONE (GridHashMapEntry.state, grid.wgsl:110-117)
+    uint32_t* hvals; // block header id
+    int4* block_vid; // ActiveBlockHeader.virtual_id (grid.wgsl:215-219)
+    uint32_t* cell_start; // capacity*64 + 1: per-cell particle counts, scanned in place
+    uint32_t* nbr; // capacity * NASSOC: header ids of blocks vid + {0,1}^D
+    float4* node_mv; // capacity*64: momentum xyz + mass (Node.momentum_velocity_mass, grid.wgsl:257-267)
+    uint4* node_cdf; // capacity*64: bits(distance), affinities, closest_id, - (NodeCdf, grid.wgsl:233-240)
+    uint64_t* scan_state; // single-pass scan tile descriptors
+
+    BodyDev* bodies;
+    SimState* sim;
+    Counters* counters;
+};
+
+// ---- small math --------------------------------------------------------------------------
+__host__ __device__ inline uint32_t pack_key2(int x, int y) { // grid.wgsl:83-86
+    return ((uint32_t)(x + 0x00007fff) & 0x0000ffffu) | (((uint32_t)(y + 0x00007fff) & 0x0000ffffu) << 16);
+}
+__host__ __device__ inline uint32_t pack_key3(int x, int y, int z) { // grid.wgsl:88-95
+    return ((uint32_t)(x + 0x000003ff) & 0x000007ffu) | (((uint32_t)(y + 0x000001ff) & 0x000003ffu) << 11) |
+           (((uint32_t)(z + 0x000003ff) & 0x000007ffu) << 21);
+}
+template <int D>
+__host__ __device__ inline uint32_t pack_key(int x, int y, int z) {
+    if (D == 2) return pack_key2(x, y);
+    return pack_key3(x, y, z);
+}
+__host__ __device__ inline uint32_t hash_key(uint32_t k) { // grid.wgsl:98-105 (murmur3 finaliser step)
+    k *= 0xcc9e2d51u;
+    k = (k << 15) | (k >> 17);
+    k *= 0x1b873593u;
+    return k;
+}
+
+// Associated cell of a coordinate: round(p / h) - 1 with round = ties-to-even and a true IEEE
+// division, bit-exact with grid.wgsl:285 / particle3d.wgsl:42 (never roundf).
+__device__ __forceinline__ int assoc_cell(float p, float h) { return (int)(rintf(__fdiv_rn(p, h)) - 1.0f); }
+
+__device__ __forceinline__ uint32_t find_block(const uint32_t* __restrict__ hkeys, const uint32_t* __restrict__ hvals,
+                                               uint32_t cap_mask, uint32_t packed) { // grid.wgsl:167-184
+    uint32_t slot = hash_key(packed) & cap_mask;
+    for (uint32_t k = 0; k <= cap_mask; ++k) {
+        uint32_t s = __ldg(hkeys + slot);
+        if (s == packed) return __ldg(hvals + slot);
+        if (s == NONE) return NONE;
+        slot = (slot + 1) & cap_mask;
+    }
+    return NONE;
+}
+
+// CPIC affinity words (grid.wgsl:230-255)
+__device__ __forceinline__ bool affinities_are_compatible(uint32_t a1, uint32_t a2) {
+    uint32_t common = a1 & a2 & 0xffffu;
+    return (((a1 >> 16) ^ (a2 >> 16)) & common) == 0u;
+}
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
+
+// project_velocity (grid.wgsl:390-404). For 2D pass z = 0.
+__device__ __forceinline__ V3 project_velocity(V3 vel, V3 n) {
+    float normal_vel = dot(vel, n);
+    if (normal_vel < 0.0f) {
+        const float friction = 20.0f;
+        V3 t = vel - n * normal_vel;
+        float len = length(t);
+        V3 dir = (len > 1.0e-8f) ? t * (1.0f / len) : v3(0, 0, 0);
+        return dir * fmaxf(0.0f, len + friction * normal_vel);
+    }
+    return vel;
+}
+
+// Body::velocity_at_point (wgrapier body.wgsl). 2D: angular in angvel[0].
+template <int D>
+__device__ __forceinline__ V3 velocity_at_point(const BodyDev& b, V3 pt) {
+    V3 d = pt - v3(b.com[0], b.com[1], b.com[2]);
+    if (D == 2) return v3(b.linvel[0] - d.y * b.angvel[0], b.linvel[1] + d.x * b.angvel[0], 0.0f);
+    V3 w = v3(b.angvel[0], b.angvel[1], b.angvel[2]);
+    return v3(b.linvel[0], b.linvel[1], b.linvel[2]) + cross(w, d);
+}
+
+// Quadratic B-spline weights (kernel.wgsl:61-67); x in [0.5, 1.5].
+__device__ __forceinline__ void bspline(float x, float& w0, float& w1, float& w2) {
+    float a = 1.5f - x, b = x - 1.0f, c = x - 0.5f;
+    w0 = 0.5f * a * a;
+    w1 = 0.75f - b * b;
+    w2 = 0.5f * c * c;
+}
+
+// flt2int (rigid_impulses.wgsl:52-54): i32(x * 1e5), truncating and saturating like WGSL.
+__device__ __forceinline__ int flt2int(float f) {
+    float x = f * 1e5f;
+    if (!(x == x)) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)x; // cvt.rzi
+}
+
+} // namespace b2

@@ -1,0 +1,48 @@
+// Host-callable launch wrappers, one per kernel. Implemented in sort.cu / p2g.cu / g2p.cu / misc.cu.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2 {
+
+struct LaunchCfg {
+    int dim;
+    int num_sms;
+    cudaStream_t stream;
+    uint64_t* launch_counter; // incremented once per kernel launch (b200mpm_pipeline_launch_count)
+};
+
+// "update rigid particles" pass + per-substep counter reset.
+void launch_begin_substep(const LaunchCfg& c, const DeviceData& d);
+// "grid sort" pass (WgGrid::queue_sort, src/grid/grid.rs:30-207).
+void launch_clear(const LaunchCfg& c, const DeviceData& d);
+void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur);
+void launch_count(const LaunchCfg& c, const DeviceData& d);
+void launch_scan_cells(const LaunchCfg& c, const DeviceData& d);
+void launch_block_prepare(const LaunchCfg& c, const DeviceData& d); // + "grid_update_cdf" pass
+void launch_scatter(const LaunchCfg& c, const DeviceData& d);
+// "g2p_cdf" pass.
+void launch_g2p_cdf(const LaunchCfg& c, const DeviceData& d, int cur);
+// "p2g" pass.
+void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur);
+// "grid_update" + "g2p" + "particles_update" passes (fused).
+void launch_g2p_update(const LaunchCfg& c, const DeviceData& d, int cur);
+// "integrate_bodies" pass.
+void launch_integrate_bodies(const LaunchCfg& c, const DeviceData& d);
+
+// Stand-alone exclusive scan of a device vector (b200mpm_prefix_sum_u32).
+void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len, uint64_t* scan_state,
+                               uint32_t* ticket);
+uint32_t scan_num_tiles(uint64_t len);
+
+// Readback helpers (device -> staging in caller order).
+void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out);
+void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out);
+void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_info* blocks, b200mpm_node* nodes,
+                        uint32_t max_blocks);
+void launch_gather_sorted_ids(const LaunchCfg& c, const DeviceData& d, int cur, int indirect, uint32_t* out);
+void launch_write_poses(const LaunchCfg& c, const DeviceData& d, const b200mpm_pose* poses, uint32_t n);
+void launch_write_vels(const LaunchCfg& c, const DeviceData& d, const b200mpm_velocity* vels, uint32_t n);
+void launch_read_poses(const LaunchCfg& c, const DeviceData& d, b200mpm_pose* poses, b200mpm_velocity* vels, uint32_t n);
+
+} // namespace b2

@@ -1,0 +1,168 @@
+// 2x2 / 3x3 singular value decompositions for the constitutive models.
+//
+// Replaces wgebra::svd2 / svd3 (dimforge/wgmath @ 6d17942b, not vendored; call sites
+// linear_elasticity.wgsl:15,29; drucker_prager.wgsl:80,139; particle_update.wgsl:103,109).
+// Contract: F = U diag(S) V^T with U, V proper rotations; the sign of
+// det(F) is carried by the last singular value. Every use on the path is invariant to the
+// ordering / sign convention.
+#pragma once
+
+#include "common.cuh"
+
+namespace b2 {
+
+// ---- 2x2, closed form. m = [a b; c d] column-major input {a, c, b, d}. -----------------------
+__host__ __device__ inline void svd2(const float* F, float* U, float* S, float* V) {
+    float a = F[0], c = F[1], b = F[2], d = F[3];
+    float e = (a + d) * 0.5f, f = (a - d) * 0.5f, g = (c + b) * 0.5f, h = (c - b) * 0.5f;
+    float q = sqrtf(e * e + h * h), r = sqrtf(f * f + g * g);
+    S[0] = q + r;
+    S[1] = q - r; // signed: carries det(F)
+    float a1 = atan2f(g, f), a2 = atan2f(h, e);
+    float theta = (a2 - a1) * 0.5f, phi = (a2 + a1) * 0.5f;
+    float sp, cp, st, ct;
+    sincosf(phi, &sp, &cp);
+    sincosf(theta, &st, &ct);
+    // U = rot(phi), V^T = rot(theta)  =>  V = rot(-theta)
+    U[0] = cp;
+    U[1] = sp;
+    U[2] = -sp;
+    U[3] = cp;
+    V[0] = ct;
+    V[1] = -st;
+    V[2] = st;
+    V[3] = ct;
+}
+
+// One Jacobi rotation on the symmetric matrix (app, aqq, apq, and the two other off-diagonals
+// apr, aqr), accumulated into columns p, q of V.
+__host__ __device__ inline void jacobi_rot(float& app, float& aqq, float& apq, float& apr, float& aqr, float* vp,
+                                           float* vq) {
+    float c = 1.0f, s = 0.0f;
+    float absq = fabsf(apq);
+    if (absq > 1e-30f) {
+        float tau = (aqq - app) / (2.0f * apq);
+        float t = copysignf(1.0f, tau) / (fabsf(tau) + sqrtf(1.0f + tau * tau));
+        c = rsqrtf(1.0f + t * t);
+        s = t * c;
+        // A' = J^T A J with J = [c s; -s c]
+        float t_apq = t * apq;
+        app -= t_apq;
+        aqq += t_apq;
+        apq = 0.0f;
+        float npr = c * apr - s * aqr;
+        float nqr = s * apr + c * aqr;
+        apr = npr;
+        aqr = nqr;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float a = vp[k], b = vq[k];
+            vp[k] = c * a - s * b;
+            vq[k] = s * a + c * b;
+        }
+    }
+}
+
+#if !defined(__CUDA_ARCH__)
+static inline float rsqrtf_host(float x) { return 1.0f / sqrtf(x); }
+#endif
+
+// ---- 3x3: cyclic Jacobi on F^T F for V, then U and S from B = F V. Column-major. -----------------
+template <int SWEEPS = 4>
+__host__ __device__ inline void svd3(const float* F, float* U, float* S, float* V) {
+    // A = F^T F (symmetric)
+    float a00 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+    float a11 = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
+    float a22 = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+    float a01 = F[0] * F[3] + F[1] * F[4] + F[2] * F[5];
+    float a02 = F[0] * F[6] + F[1] * F[7] + F[2] * F[8];
+    float a12 = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
+    float v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
+#pragma unroll
+    for (int sweep = 0; sweep < SWEEPS; ++sweep) {
+        jacobi_rot(a00, a11, a01, a02, a12, v0, v1);
+        jacobi_rot(a00, a22, a02, a01, a12, v0, v2);
+        jacobi_rot(a11, a22, a12, a01, a02, v1, v2);
+    }
+    // B = F V
+    float b0[3], b1[3], b2[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        b0[r] = F[r] * v0[0] + F[3 + r] * v0[1] + F[6 + r] * v0[2];
+        b1[r] = F[r] * v1[0] + F[3 + r] * v1[1] + F[6 + r] * v1[2];
+        b2[r] = F[r] * v2[0] + F[3 + r] * v2[1] + F[6 + r] * v2[2];
+    }
+    float n0 = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2];
+    float n1 = b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2];
+    float n2 = b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2];
+    // Sort columns by decreasing norm; a swap with one negation keeps det(V) = +1.
+#define B2_CSWAP(na, nb, ba, bb, va, vb)  \
+    if (na < nb) {                        \
+        float tn = na;                    \
+        na = nb;                          \
+        nb = tn;                          \
+        _Pragma("unroll") for (int k = 0; k < 3; ++k) { \
+            float tb = ba[k];             \
+            ba[k] = bb[k];                \
+            bb[k] = -tb;                  \
+            float tv = va[k];             \
+            va[k] = vb[k];                \
+            vb[k] = -tv;                  \
+        }                                 \
+    }
+    B2_CSWAP(n0, n1, b0, b1, v0, v1)
+    B2_CSWAP(n0, n2, b0, b2, v0, v2)
+    B2_CSWAP(n1, n2, b1, b2, v1, v2)
+#undef B2_CSWAP
+    float s0 = sqrtf(n0);
+    float u0[3], u1[3], u2[3];
+    if (s0 > 1e-30f) {
+        float inv = 1.0f / s0;
+        u0[0] = b0[0] * inv;
+        u0[1] = b0[1] * inv;
+        u0[2] = b0[2] * inv;
+    } else {
+        u0[0] = 1.0f;
+        u0[1] = 0.0f;
+        u0[2] = 0.0f;
+    }
+    // u1: b1 orthogonalised against u0
+    float d01 = u0[0] * b1[0] + u0[1] * b1[1] + u0[2] * b1[2];
+    float w[3] = {b1[0] - d01 * u0[0], b1[1] - d01 * u0[1], b1[2] - d01 * u0[2]};
+    float nw = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    if (nw > 1e-6f * s0 && nw > 1e-30f) {
+        float inv = 1.0f / nw;
+        u1[0] = w[0] * inv;
+        u1[1] = w[1] * inv;
+        u1[2] = w[2] * inv;
+    } else { // rank <= 1: any unit vector orthogonal to u0
+        float ax = fabsf(u0[0]), ay = fabsf(u0[1]), az = fabsf(u0[2]);
+        float e[3] = {0, 0, 0};
+        if (ax <= ay && ax <= az) e[0] = 1.0f;
+        else if (ay <= az) e[1] = 1.0f;
+        else e[2] = 1.0f;
+        float de = u0[0] * e[0] + u0[1] * e[1] + u0[2] * e[2];
+        float t[3] = {e[0] - de * u0[0], e[1] - de * u0[1], e[2] - de * u0[2]};
+        float inv = rsqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+        u1[0] = t[0] * inv;
+        u1[1] = t[1] * inv;
+        u1[2] = t[2] * inv;
+    }
+    u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
+    u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
+    u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+    S[0] = s0;
+    S[1] = u1[0] * b1[0] + u1[1] * b1[1] + u1[2] * b1[2];
+    S[2] = u2[0] * b2[0] + u2[1] * b2[1] + u2[2] * b2[2]; // signed
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        U[k] = u0[k];
+        U[3 + k] = u1[k];
+        U[6 + k] = u2[k];
+        V[k] = v0[k];
+        V[3 + k] = v1[k];
+        V[6 + k] = v2[k];
+    }
+}
+
+} // namespace b2

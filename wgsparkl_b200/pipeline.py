@@ -1,0 +1,276 @@
+"""Host-side mirror of wgsparkl's `pipeline` module (src/pipeline.rs): `MpmPipeline` and
+`MpmData`, bound to libb200mpm.so (include/b200mpm.h) through ctypes.
+
+There is no CPU fallback: if the library has not been built, or no sm_100 CUDA device is
+visible, constructing an `MpmPipeline` raises `B200MpmError`.
+"""
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .solver import SimulationParams, particles_to_abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libb200mpm.so")
+_lib = None
+
+
+class B200MpmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("b200mpm error %d: %s" % (code, message))
+        self.code = code
+
+
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_NO_DEVICE = -2
+ERR_CUDA = -3
+ERR_OUT_OF_MEMORY = -4
+ERR_GRID_OVERFLOW = -5
+
+# Every symbol include/b200mpm.h declares (tests check that the library exports all of them).
+EXPORTS = (
+    "b200mpm_pipeline_create",
+    "b200mpm_pipeline_destroy",
+    "b200mpm_last_error",
+    "b200mpm_pipeline_launch_count",
+    "b200mpm_data_create",
+    "b200mpm_data_destroy",
+    "b200mpm_data_num_particles",
+    "b200mpm_data_num_bodies",
+    "b200mpm_step",
+    "b200mpm_sync",
+    "b200mpm_set_timestamps",
+    "b200mpm_get_timings",
+    "b200mpm_write_sim_params",
+    "b200mpm_write_body_poses",
+    "b200mpm_write_body_vels",
+    "b200mpm_read_body_poses",
+    "b200mpm_read_body_vels",
+    "b200mpm_read_positions",
+    "b200mpm_read_particles",
+    "b200mpm_read_grid",
+    "b200mpm_read_sorted_ids",
+    "b200mpm_data_status",
+    "b200mpm_sort_only",
+    "b200mpm_prefix_sum_u32",
+    "b200mpm_slab_configure",
+)
+
+
+def load_library():
+    """dlopen libb200mpm.so and declare the prototypes. Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise B200MpmError(
+            ERR_NO_DEVICE,
+            "libb200mpm.so is not built (run `python -m wgsparkl_b200.build`); there is no CPU fallback",
+        )
+    L = ctypes.CDLL(_LIB_PATH)
+    vp, sz, u32, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+    L.b200mpm_last_error.restype = ctypes.c_char_p
+    L.b200mpm_pipeline_create.argtypes = [i32, i32, ctypes.POINTER(vp)]
+    L.b200mpm_pipeline_destroy.argtypes = [vp]
+    L.b200mpm_pipeline_destroy.restype = None
+    L.b200mpm_pipeline_launch_count.argtypes = [vp]
+    L.b200mpm_pipeline_launch_count.restype = ctypes.c_uint64
+    L.b200mpm_data_create.argtypes = [vp, vp, vp, sz, vp, sz, ctypes.c_float, u32, ctypes.POINTER(vp)]
+    L.b200mpm_data_destroy.argtypes = [vp]
+    L.b200mpm_data_destroy.restype = None
+    L.b200mpm_data_num_particles.argtypes = [vp]
+    L.b200mpm_data_num_particles.restype = sz
+    L.b200mpm_data_num_bodies.argtypes = [vp]
+    L.b200mpm_data_num_bodies.restype = sz
+    L.b200mpm_step.argtypes = [vp, vp, u32]
+    L.b200mpm_sync.argtypes = [vp]
+    L.b200mpm_set_timestamps.argtypes = [vp, i32]
+    L.b200mpm_get_timings.argtypes = [vp, vp]
+    L.b200mpm_write_sim_params.argtypes = [vp, vp]
+    for name in ("b200mpm_write_body_poses", "b200mpm_write_body_vels", "b200mpm_read_body_poses",
+                 "b200mpm_read_body_vels"):
+        getattr(L, name).argtypes = [vp, vp, sz]
+    L.b200mpm_read_positions.argtypes = [vp, vp]
+    L.b200mpm_read_particles.argtypes = [vp, vp]
+    L.b200mpm_read_grid.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
+    L.b200mpm_read_sorted_ids.argtypes = [vp, vp]
+    L.b200mpm_data_status.argtypes = [vp, ctypes.POINTER(u32)]
+    L.b200mpm_sort_only.argtypes = [vp, vp]
+    L.b200mpm_prefix_sum_u32.argtypes = [vp, vp, sz]
+    L.b200mpm_slab_configure.argtypes = [vp, i32, i32, ctypes.c_int32, ctypes.c_int32]
+    _lib = L
+    return L
+
+
+def _check(code):
+    if code != OK:
+        raise B200MpmError(code, load_library().b200mpm_last_error().decode("utf-8", "replace"))
+
+
+class MpmPipeline:
+    """MpmPipeline (src/pipeline.rs:24-39,176-281). One CUDA stream on one device."""
+
+    def __init__(self, device: int = 0, dim: int = 3):
+        L = load_library()
+        self.dim = dim
+        self.device = device
+        h = ctypes.c_void_p()
+        _check(L.b200mpm_pipeline_create(device, dim, ctypes.byref(h)))
+        self._h = h
+
+    # MpmPipeline::new(&Device) (pipeline.rs:176)
+    @staticmethod
+    def new(device: int = 0, dim: int = 3) -> "MpmPipeline":
+        return MpmPipeline(device, dim)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().b200mpm_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def queue_step(self, data: "MpmData", num_substeps: int = 1, add_timestamps: Optional[bool] = None):
+        """queue_step + `for _ in 0..num_substeps { queue.encode }` + submit
+        (pipeline.rs:195-281, src_testbed/step.rs:122-128,169). Asynchronous."""
+        if add_timestamps is not None:
+            self.set_timestamps(add_timestamps)
+        _check(load_library().b200mpm_step(self._h, data._h, int(num_substeps)))
+
+    step = queue_step
+
+    def sort_only(self, data: "MpmData"):
+        """WgGrid::queue_sort alone (grid.rs:30-207), as in the gpu_grid_sort test (grid.rs:347-402)."""
+        _check(load_library().b200mpm_sort_only(self._h, data._h))
+
+    def sync(self):
+        _check(load_library().b200mpm_sync(self._h))
+
+    def set_timestamps(self, enabled: bool):
+        _check(load_library().b200mpm_set_timestamps(self._h, 1 if enabled else 0))
+
+    def timings_ms(self):
+        """Accumulated milliseconds per reference pass name (src_testbed/lib.rs:133-146)."""
+        out = np.zeros(len(abi.PASS_NAMES), dtype=np.float64)
+        _check(load_library().b200mpm_get_timings(self._h, abi.ptr(out)))
+        return dict(zip(abi.PASS_NAMES, out.tolist()))
+
+    def launch_count(self) -> int:
+        return int(load_library().b200mpm_pipeline_launch_count(self._h))
+
+    def prefix_sum(self, v) -> np.ndarray:
+        """WgPrefixSum::queue (prefix_sum.rs:20-69) on a host vector; returns the scanned copy."""
+        out = np.ascontiguousarray(v, dtype=np.uint32).copy()
+        _check(load_library().b200mpm_prefix_sum_u32(self._h, abi.ptr(out), out.size))
+        return out
+
+
+class MpmData:
+    """MpmData (src/pipeline.rs:84-172): owns every device buffer of one simulation."""
+
+    def __init__(self, pipeline: MpmPipeline, params: SimulationParams, particles, bodies=None,
+                 cell_width: float = 1.0, grid_capacity: int = 60_000):
+        L = load_library()
+        self.pipeline = pipeline
+        self.dim = pipeline.dim
+        if not isinstance(particles, np.ndarray):
+            particles = particles_to_abi(particles, self.dim)
+        particles = np.ascontiguousarray(particles, dtype=abi.particle_dtype)
+        if bodies is None:
+            bodies = np.zeros(0, dtype=abi.body_dtype)
+        bodies = np.ascontiguousarray(bodies, dtype=abi.body_dtype)
+        p = params.to_abi() if hasattr(params, "to_abi") else params
+        self.num_particles = int(particles.shape[0])
+        self.num_bodies = int(bodies.shape[0])
+        self.capacity = 1
+        while self.capacity < grid_capacity:
+            self.capacity <<= 1
+        h = ctypes.c_void_p()
+        _check(L.b200mpm_data_create(pipeline._h, abi.ptr(p), abi.ptr(particles), self.num_particles,
+                                     abi.ptr(bodies), self.num_bodies, ctypes.c_float(cell_width),
+                                     int(grid_capacity), ctypes.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def new(pipeline, params, particles, bodies, colliders, cell_width, grid_capacity):
+        """MpmData::new(device, params, particles, &RigidBodySet, &ColliderSet, cell_width, capacity)
+        (pipeline.rs:98-128): every collider with a parent body is coupled, TwoWays."""
+        from .rapier import bodies_to_abi
+
+        return MpmData(pipeline, params, particles, bodies_to_abi(bodies, colliders, pipeline.dim), cell_width,
+                       grid_capacity)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().b200mpm_data_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- per-frame host writes / reads (src_testbed/step.rs:79-119,175-176; ui.rs:98-103)
+    def write_sim_params(self, params):
+        p = params.to_abi() if hasattr(params, "to_abi") else params
+        _check(load_library().b200mpm_write_sim_params(self._h, abi.ptr(p)))
+
+    def write_body_poses(self, poses):
+        poses = np.ascontiguousarray(poses, dtype=abi.pose_dtype)
+        _check(load_library().b200mpm_write_body_poses(self._h, abi.ptr(poses), poses.shape[0]))
+
+    def write_body_vels(self, vels):
+        vels = np.ascontiguousarray(vels, dtype=abi.velocity_dtype)
+        _check(load_library().b200mpm_write_body_vels(self._h, abi.ptr(vels), vels.shape[0]))
+
+    def read_body_poses(self):
+        out = np.zeros(self.num_bodies, dtype=abi.pose_dtype)
+        _check(load_library().b200mpm_read_body_poses(self._h, abi.ptr(out), self.num_bodies))
+        return out
+
+    def read_body_vels(self):
+        out = np.zeros(self.num_bodies, dtype=abi.velocity_dtype)
+        _check(load_library().b200mpm_read_body_vels(self._h, abi.ptr(out), self.num_bodies))
+        return out
+
+    # ---- state readback
+    def read_positions(self, out: Optional[np.ndarray] = None):
+        if out is None:
+            out = np.zeros((self.num_particles, 4), dtype=np.float32)
+        _check(load_library().b200mpm_read_positions(self._h, abi.ptr(out)))
+        return out
+
+    def read_particles(self):
+        out = np.zeros(self.num_particles, dtype=abi.particle_dtype)
+        _check(load_library().b200mpm_read_particles(self._h, abi.ptr(out)))
+        return out
+
+    def status(self):
+        """(num_active_blocks, overflowed)."""
+        nb = ctypes.c_uint32(0)
+        code = load_library().b200mpm_data_status(self._h, ctypes.byref(nb))
+        if code not in (OK, ERR_GRID_OVERFLOW):
+            _check(code)
+        return int(nb.value), code == ERR_GRID_OVERFLOW
+
+    def read_grid(self):
+        nb, _ = self.status()
+        blocks = np.zeros(nb, dtype=abi.block_info_dtype)
+        nodes = np.zeros(nb * 64, dtype=abi.node_dtype)
+        got = ctypes.c_size_t(0)
+        _check(load_library().b200mpm_read_grid(self._h, abi.ptr(blocks), abi.ptr(nodes), nb, ctypes.byref(got)))
+        return blocks[: got.value], nodes.reshape(-1, 64)[: got.value]
+
+    def read_sorted_ids(self):
+        out = np.zeros(self.num_particles, dtype=np.uint32)
+        _check(load_library().b200mpm_read_sorted_ids(self._h, abi.ptr(out)))
+        return out

@@ -1,0 +1,250 @@
+"""A minimal stand-in for the parts of rapier{2,3}d that wgsparkl's scene constructors use
+(RigidBodyBuilder / ColliderBuilder / RigidBodySet / ColliderSet; e.g.
+crates/wgsparkl3d/examples/sand3.rs:62-103) and for what GpuBodySet::from_rapier extracts
+from them (src/pipeline.rs:141): shape, pose, velocity and mass properties per coupled
+collider. In a Rust host the real rapier sets fill `b200mpm_body` instead."""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+
+f32 = np.float32
+
+FIXED, DYNAMIC, KINEMATIC_VELOCITY_BASED = 0, 1, 2
+
+
+def quat_from_scaled_axis(v):
+    v = np.asarray(v, dtype=np.float64)
+    a = np.linalg.norm(v)
+    if a == 0.0:
+        return np.array([0, 0, 0, 1], dtype=np.float64)
+    s = np.sin(a / 2) / a
+    return np.array([v[0] * s, v[1] * s, v[2] * s, np.cos(a / 2)])
+
+
+def quat_to_matrix(q):
+    i, j, k, w = [float(x) for x in q]
+    return np.array(
+        [
+            [1 - 2 * (j * j + k * k), 2 * (i * j - k * w), 2 * (i * k + j * w)],
+            [2 * (i * j + k * w), 1 - 2 * (i * i + k * k), 2 * (j * k - i * w)],
+            [2 * (i * k - j * w), 2 * (j * k + i * w), 1 - 2 * (i * i + j * j)],
+        ]
+    )
+
+
+@dataclass
+class RigidBody:
+    body_type: int = FIXED
+    translation: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    rotation: object = None  # 3D: scaled-axis vector; 2D: angle
+    linvel: np.ndarray = field(default_factory=lambda: np.zeros(3))
+    angvel: object = None
+
+    def is_dynamic(self):
+        return self.body_type == DYNAMIC
+
+
+class RigidBodyBuilder:
+    def __init__(self, body_type):
+        self._rb = RigidBody(body_type=body_type)
+
+    @staticmethod
+    def fixed():
+        return RigidBodyBuilder(FIXED)
+
+    @staticmethod
+    def dynamic():
+        return RigidBodyBuilder(DYNAMIC)
+
+    @staticmethod
+    def kinematic_velocity_based():
+        return RigidBodyBuilder(KINEMATIC_VELOCITY_BASED)
+
+    def translation(self, t):
+        tt = np.zeros(3)
+        tt[: len(t)] = t
+        self._rb.translation = tt
+        return self
+
+    def rotation(self, r):
+        self._rb.rotation = r
+        return self
+
+    def linvel(self, v):
+        vv = np.zeros(3)
+        vv[: len(v)] = v
+        self._rb.linvel = vv
+        return self
+
+    def angvel(self, w):
+        self._rb.angvel = w
+        return self
+
+    def build(self):
+        return self._rb
+
+
+@dataclass
+class Collider:
+    shape_type: int
+    shape_a: np.ndarray
+    shape_b: np.ndarray
+    radius: float
+    density: float = 1.0
+    parent: Optional[int] = None
+
+
+class ColliderBuilder:
+    def __init__(self, c):
+        self._c = c
+
+    @staticmethod
+    def cuboid(*half_extents):
+        a = np.zeros(3)
+        a[: len(half_extents)] = half_extents
+        return ColliderBuilder(Collider(abi.SHAPE_CUBOID, a, np.zeros(3), 0.0))
+
+    @staticmethod
+    def ball(radius):
+        return ColliderBuilder(Collider(abi.SHAPE_BALL, np.zeros(3), np.zeros(3), float(radius)))
+
+    @staticmethod
+    def capsule_y(half_height, radius):
+        return ColliderBuilder(
+            Collider(abi.SHAPE_CAPSULE, np.array([0.0, -half_height, 0.0]), np.array([0.0, half_height, 0.0]), float(radius))
+        )
+
+    def density(self, d):
+        self._c.density = float(d)
+        return self
+
+    def build(self):
+        return self._c
+
+
+class RigidBodySet:
+    def __init__(self):
+        self.bodies: List[RigidBody] = []
+
+    def insert(self, rb):
+        if isinstance(rb, RigidBodyBuilder):
+            rb = rb.build()
+        self.bodies.append(rb)
+        return len(self.bodies) - 1
+
+    def __getitem__(self, h):
+        return self.bodies[h]
+
+    def __len__(self):
+        return len(self.bodies)
+
+
+class ColliderSet:
+    def __init__(self):
+        self.colliders: List[Collider] = []
+
+    def insert_with_parent(self, co, parent, bodies=None):
+        if isinstance(co, ColliderBuilder):
+            co = co.build()
+        co.parent = parent
+        self.colliders.append(co)
+        return len(self.colliders) - 1
+
+    def insert(self, co):
+        if isinstance(co, ColliderBuilder):
+            co = co.build()
+        self.colliders.append(co)
+        return len(self.colliders) - 1
+
+    def __iter__(self):
+        return iter(enumerate(self.colliders))
+
+    def __getitem__(self, h):
+        return self.colliders[h]
+
+    def __len__(self):
+        return len(self.colliders)
+
+
+def _mass_properties(co: Collider, dim: int):
+    """(mass, local_com, local inertia tensor) of a collider, as parry computes them."""
+    rho = co.density
+    if co.shape_type == abi.SHAPE_CUBOID:
+        he = co.shape_a
+        if dim == 3:
+            m = rho * 8.0 * he[0] * he[1] * he[2]
+            inertia = np.diag([he[1] ** 2 + he[2] ** 2, he[0] ** 2 + he[2] ** 2, he[0] ** 2 + he[1] ** 2]) * m / 3.0
+        else:
+            m = rho * 4.0 * he[0] * he[1]
+            inertia = np.array([[m * (he[0] ** 2 + he[1] ** 2) / 3.0]])
+        return m, np.zeros(3), inertia
+    if co.shape_type == abi.SHAPE_BALL:
+        r = co.radius
+        if dim == 3:
+            m = rho * 4.0 / 3.0 * np.pi * r**3
+            inertia = np.eye(3) * (2.0 / 5.0 * m * r * r)
+        else:
+            m = rho * np.pi * r * r
+            inertia = np.array([[m * r * r / 2.0]])
+        return m, np.zeros(3), inertia
+    # capsule along local y: cylinder/rectangle + two half balls
+    hh = abs(co.shape_b[1] - co.shape_a[1]) / 2.0
+    r = co.radius
+    if dim == 3:
+        m_cyl = rho * np.pi * r * r * 2 * hh
+        m_sph = rho * 4.0 / 3.0 * np.pi * r**3
+        iy = m_cyl * r * r / 2.0 + m_sph * 2.0 / 5.0 * r * r
+        ix = (
+            m_cyl * (3 * r * r + 4 * hh * hh) / 12.0
+            + m_sph * (2.0 / 5.0 * r * r + hh * hh + 3.0 / 8.0 * 2 * hh * r)
+        )
+        return m_cyl + m_sph, np.zeros(3), np.diag([ix, iy, ix])
+    m_rect = rho * 2 * r * 2 * hh
+    m_circ = rho * np.pi * r * r
+    i = m_rect * ((2 * r) ** 2 + (2 * hh) ** 2) / 12.0 + m_circ * (r * r / 2.0 + hh * hh)
+    return m_rect + m_circ, np.zeros(3), np.array([[i]])
+
+
+def bodies_to_abi(bodies: RigidBodySet, colliders: ColliderSet, dim: int, coupling=None) -> np.ndarray:
+    """What MpmData::new derives from the rapier sets (src/pipeline.rs:107-117,141): one entry per
+    collider that has a parent body, in collider-set order, BodyCoupling::TwoWays."""
+    if coupling is None:
+        coupling = [(co.parent, h, True) for h, co in colliders if co.parent is not None]
+    if len(coupling) > abi.MAX_BODIES:
+        raise ValueError("CPIC supports at most 16 coupled colliders (rigid_impulses.rs:42)")
+    out = np.zeros(len(coupling), dtype=abi.body_dtype)
+    for i, (bh, ch, two_ways) in enumerate(coupling):
+        rb, co = bodies[bh], colliders[ch]
+        o = out[i]
+        o["shape_type"] = co.shape_type
+        o["shape_a"] = co.shape_a.astype(f32)
+        o["shape_b"] = co.shape_b.astype(f32)
+        o["radius"] = co.radius
+        o["translation"] = rb.translation.astype(f32)
+        if dim == 3:
+            q = quat_from_scaled_axis(rb.rotation if rb.rotation is not None else np.zeros(3))
+            o["rotation"] = q.astype(f32)
+            w = np.zeros(3)
+            if rb.angvel is not None:
+                w[:] = rb.angvel
+            o["angvel"] = w.astype(f32)
+        else:
+            a = float(rb.rotation) if rb.rotation is not None else 0.0
+            o["rotation"] = np.array([np.cos(a), np.sin(a), 0, 0], dtype=f32)
+            o["angvel"] = np.array([float(rb.angvel) if rb.angvel is not None else 0.0, 0, 0], dtype=f32)
+        o["linvel"] = rb.linvel.astype(f32)
+        m, com, inertia = _mass_properties(co, dim)
+        if rb.body_type == DYNAMIC and m > 0:
+            o["inv_mass"][:dim] = f32(1.0 / m)
+            inv = np.zeros((3, 3))
+            if dim == 3:
+                inv = np.linalg.inv(inertia)
+                o["inv_inertia"] = inv.T.reshape(-1).astype(f32)  # column-major
+            else:
+                o["inv_inertia"][0] = f32(1.0 / inertia[0, 0])
+        o["local_com"] = com.astype(f32)
+        o["two_ways"] = 1 if two_ways else 0
+    return out
