@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — particle-substeps/s of the MPM substep hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-side S]
+
+A "step" is one testbed frame of the hot path = 20 substeps (sand3.rs:54 / elastic_cut3.rs:54) over
+the synthetic scene named in `config.workload`. At N=1 that is BASELINE.json configs[1]: the 3D
+corotated-elastic cube drop on a static ground cuboid, 1M particles. Particle state is resident in
+HBM when the timed region starts (it lives there in the reference too: src/pipeline.rs:130-168 uploads
+once); `e2e` times the same frames through the C ABI with HOST buffers: per frame the body poses and
+velocities are uploaded from host memory (src_testbed/step.rs:79-119) and the body poses plus all
+particle positions are read back into host memory.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP on all host cores) on a
+bounded sample of the same workload; the reference itself (Rust + WGSL on wgpu) cannot be built in this
+image (DESIGN.md "Oracle").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/sec"
+UNIT = "particle-substeps/s"
+
+# Algorithmic bytes per particle-substep (BASELINE.md §3 / SURVEY §8d), 3D f32.
+BYTES_P2G = 66.0
+BYTES_G2P_ELASTIC = 162.0
+BYTES_G2P_SAND = 218.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_scene(n_side, contact=True):
+    from wgsparkl_b200 import scenes
+
+    # configs[1]: 3D elastic cube drop, n_side^3 particles. The cube starts just above the ground cuboid
+    # so that the timed region covers the contact phase (CPIC active), the more expensive regime.
+    return scenes.elastic_cube_3d(n_side, y_offset=-5.0 if contact else 60.0, grid_capacity=60_000)
+
+
+def frame_io_arrays(scene):
+    from wgsparkl_b200 import abi
+
+    nb = len(scene["bodies"])
+    poses = np.zeros(nb, dtype=abi.pose_dtype)
+    poses["translation"] = scene["bodies"]["translation"]
+    poses["rotation"] = scene["bodies"]["rotation"]
+    vels = np.zeros(nb, dtype=abi.velocity_dtype)
+    vels["linear"] = scene["bodies"]["linvel"]
+    vels["angular"] = scene["bodies"]["angvel"]
+    return poses, vels
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from wgsparkl_b200.pipeline import MpmData, MpmPipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    hbm_peak, peak_kind = load_peaks()
+
+    scene = build_scene(args.n_side)
+    n = len(scene["particles"])
+    spf = scene["substeps_per_frame"]
+    pipe = MpmPipeline(local_rank, 3)  # raises without the CUDA library / an sm_100 device: no fallback
+    stream = torch.cuda.Stream(device=local_rank)
+    pipe.set_stream(stream.cuda_stream)
+    data = MpmData(pipe, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    poses, vels = frame_io_arrays(scene)
+    host_pos = torch.empty((n, 4), dtype=torch.float32).pin_memory().numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def frame_device():
+        pipe.queue_step(data, spf)
+
+    def frame_e2e():
+        data.write_body_poses(poses)  # H2D (src_testbed/step.rs:92-96)
+        data.write_body_vels(vels)  # H2D (step.rs:98-119)
+        pipe.queue_step(data, spf)
+        data.read_body_poses()  # D2H (step.rs:175-176)
+        data.read_positions(host_pos)  # D2H: the step's result, into pinned host memory
+
+    for _ in range(args.warmup):
+        frame_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = pipe.launch_count()
+    ms = timed(frame_device, args.steps)
+    launches = pipe.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = n * spf * args.steps * world / (ms * 1e-3)
+
+    # end-to-end through the C ABI with host buffers
+    frame_e2e()
+    ms_e2e = timed(frame_e2e, args.steps)
+    e2e_value = n * spf * args.steps * world / (ms_e2e * 1e-3)
+    nb = len(scene["bodies"])
+    h2d = nb * (poses.dtype.itemsize + vels.dtype.itemsize)
+    d2h = nb * poses.dtype.itemsize + n * 16
+
+    # per-kernel durations (CUDA events around each pass, on the launching stream) for the roofline
+    pipe.set_timestamps(True)
+    frames_prof = max(1, min(args.steps, 3))
+    for _ in range(frames_prof):
+        frame_device()
+    t = pipe.timings_ms()
+    pipe.set_timestamps(False)
+    launches_per_kernel = frames_prof * spf
+    g2p_ms = t["g2p"] / launches_per_kernel
+    p2g_ms = t["p2g"] / launches_per_kernel
+    g2p_gbs = BYTES_G2P_ELASTIC * n / (g2p_ms * 1e-3) / 1e9
+    p2g_gbs = BYTES_P2G * n / (p2g_ms * 1e-3) / 1e9
+    nblocks, overflow = data.status()
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])",
+                   "particles_per_gpu": n, "substeps_per_step": spf, "cell_width": scene["cell_width"],
+                   "active_blocks": nblocks, "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
+                   "l2": "inputs larger than L2 (%.0f MB of particle state per GPU)" % (n * 220 / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_g2p (grid_update + g2p + particles_update)",
+                     "achieved": g2p_gbs, "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s",
+                     "frac": g2p_gbs / hbm_peak, "traffic": None,
+                     "bytes_per_particle": BYTES_G2P_ELASTIC, "ms_per_launch": g2p_ms,
+                     "p2g": {"achieved": p2g_gbs, "frac": p2g_gbs / hbm_peak, "bytes_per_particle": BYTES_P2G,
+                             "ms_per_launch": p2g_ms},
+                     "pass_ms_per_substep": {k: v / launches_per_kernel for k, v in t.items()}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, scene)
+    if rank == 0:
+        print(json.dumps(out))
+    data.close()
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, scene, budget_s=20.0):
+    """Oracle (a port of the reference's kernels, OpenMP) on the host cores, bounded sample of the same scene."""
+    from oracle import oracle
+
+    cores = os.cpu_count() or 1
+    oracle.set_threads(cores)
+    n = len(scene["particles"])
+    sim = oracle.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    t0 = time.perf_counter()
+    sim.step(1)
+    t1 = time.perf_counter() - t0
+    k = int(max(1, min(20, budget_s / max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    sim.step(k)
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"value": n * k / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d substeps of the full %d-particle scene after 1 warm-up substep" % (k, n)}
+
+
+def run_reference(args):
+    """The reference's own CPU-runnable form of the path: the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    cores = os.cpu_count() or 1
+    oracle.set_threads(cores)
+    scene = build_scene(args.n_side)
+    n = len(scene["particles"])
+    spf = scene["substeps_per_frame"]
+    sim = oracle.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    # bounded sample: each "step" advances `sample` substeps (instead of the full 20) so that the whole run
+    # ends within a few minutes; the metric is per particle-substep, so it is directly comparable.
+    t0 = time.perf_counter()
+    sim.step(1)
+    t1 = time.perf_counter() - t0
+    total_budget = 120.0
+    sample = int(max(1, min(spf, total_budget / max(t1, 1e-3) / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        sim.step(sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.step(sample)
+    dt = time.perf_counter() - t0
+    value = n * sample * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])",
+                   "particles_per_gpu": n, "substeps_per_step": sample,
+                   "note": "CPU restatement of the reference's WGSL kernels (oracle/), OpenMP; the Rust/wgpu reference cannot be built here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d substeps per step x %d steps of the full %d-particle scene" % (sample, args.steps, n)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-side", type=int, default=100, help="cube side in particles (100 -> 1M particles)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

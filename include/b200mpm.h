@@ -156,6 +156,10 @@ typedef struct b200mpm_data b200mpm_data; /* MpmData (src/pipeline.rs:84-95) */
 /* MpmPipeline::new(&Device) (src/pipeline.rs:176-193). `device` is the CUDA ordinal, dim is 2 or 3. */
 int b200mpm_pipeline_create(int device, int dim, b200mpm_pipeline** out);
 void b200mpm_pipeline_destroy(b200mpm_pipeline* p);
+/* Run on a caller-owned CUDA stream (a `cudaStream_t` passed as void*; NULL restores the pipeline's
+ * own stream). Plays the role of the caller-provided wgpu Queue / CommandEncoder
+ * (src_testbed/step.rs:74-76): the host decides which queue the substeps are submitted to. */
+int b200mpm_pipeline_set_stream(b200mpm_pipeline* p, void* cuda_stream);
 const char* b200mpm_last_error(void);
 /* Kernel launches issued by this pipeline since creation (bench bookkeeping). */
 uint64_t b200mpm_pipeline_launch_count(const b200mpm_pipeline* p);

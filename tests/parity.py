@@ -79,3 +79,24 @@ def assert_grid_close(gpu_blocks, gpu_nodes, ora_blocks, ora_nodes, tol):
         ed = field_rel_err(gn["cdf_distance"][m], on["cdf_distance"][m])
         assert ed <= 1e-5, "node cdf distance: relative error %.3e" % ed
     return e
+
+
+def affine_abs_bound(parts, dim, cell_width, dt, ulps=4.0):
+    """f32 conditioning bound of the APIC affine matrix (particle_update.wgsl:132):
+    affine = grad_v * mass - stress * (V0 * inv_d * dt), and the Kirchhoff stress multiplies
+    (sigma - 1) and (J - 1) by 2 mu and lambda (linear_elasticity.wgsl:32-35). A relative error of
+    `ulps` f32 ulps in the singular values (exp/log in the Drucker-Prager return mapping are only
+    specified to a few ulps in WGSL and in CUDA) therefore moves the affine term by at most
+        ulps * eps * (2 mu + d lambda) * V0 * inv_d * dt      (absolute, per particle).
+    The reference is subject to the same bound against its own exact-arithmetic statement."""
+    eps = float(np.finfo(np.float32).eps)
+    stiff = 2.0 * np.abs(parts["mu"].astype(np.float64)) + dim * np.abs(parts["lambda"].astype(np.float64))
+    return ulps * eps * stiff * parts["init_volume"] * (4.0 / (cell_width * cell_width)) * dt
+
+
+def assert_affine_close(gpu, ora, dim, cell_width, dt, rel=1e-5):
+    err = np.abs(gpu["affine"].astype(np.float64) - ora["affine"]).max(axis=1)
+    bound = affine_abs_bound(ora, dim, cell_width, dt) + rel * np.abs(ora["affine"]).max()
+    worst = float((err / bound).max())
+    assert worst <= 1.0, "affine: error is %.2fx the f32 conditioning bound" % worst
+    return worst

@@ -45,9 +45,15 @@ def test_reference_pipeline_queue_step_scene(pipe3, oracle_mod):
     scene = scenes.reference_test_lattice()
     data, sim = one_substep_both(oracle_mod, pipe3, scene, scene["particles"], n=3)
     g, o = data.read_particles(), sim.read_particles()
-    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6})
+    # With lambda = mu = -1 the return mapping runs on F = I + O(eps): every singular value it produces
+    # is 1 +- a few ulps, and the corotated stress turns each ulp into 2 mu eps of force. The velocity
+    # tolerance is that conditioning bound (4 ulps * 2 mu * V0 * inv_d * dt / mass * h per substep ~ 1e-4
+    # absolute on |v| = 0.05), not a property of either implementation.
+    parity.assert_particles_close(g, o, TOL, fields=("position", "def_grad"), tols={"position": 2e-6})
+    assert parity.field_rel_err(g["velocity"], o["velocity"]) <= 5e-3
+    parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
     assert data.status()[0] == sim.num_active_blocks()
-    for f in ("plastic_det", "plastic_hardening", "plastic_log_vol_gain"):
+    for f in ("plastic_det", "plastic_hardening"):
         assert parity.field_rel_err(g[f], o[f]) <= 1e-5
     data.close()
 
@@ -70,9 +76,10 @@ def test_one_substep_elastic_cube(pipe3, oracle_mod, ground):
     gb, gn = data.read_grid()
     ob, on = sim.read_grid()
     parity.assert_grid_close(gb, gn, ob, on, TOL)
-    # position: 2e-6 of the domain extent = a few f32 ulps; affine: stress term carries the f32 SVD
-    # conditioning 2 mu eps (see DESIGN.md "Tolerances")
-    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-4})
+    # position: 2e-6 of the domain extent = a few f32 ulps; affine: f32 conditioning bound of the
+    # stress term (parity.affine_abs_bound, DESIGN.md "Tolerances")
+    parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
     if ground:
         assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
         assert (o["cdf_affinity"] != 0).sum() > 100, "test scene must exercise CPIC"
@@ -88,11 +95,13 @@ def test_one_substep_sand(pipe3, oracle_mod):
     parts, _, _ = developed_state(oracle_mod, scene, 60)
     data, sim = one_substep_both(oracle_mod, pipe3, scene, parts)
     g, o = data.read_particles(), sim.read_particles()
-    errs = parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-3, "def_grad": 1e-4})
-    # plastic state: hardening accumulates |strain| ~ 1e-3 increments computed from log(sigma) of
-    # sigma ~ 1 +- 1e-3 in f32 => absolute 1e-7 / relative 1e-4 of the increment
-    assert parity.field_rel_err(g["plastic_hardening"], o["plastic_hardening"]) <= 1e-4, errs
-    assert parity.field_rel_err(g["plastic_log_vol_gain"], o["plastic_log_vol_gain"]) <= 1e-2
+    errs = parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
+    # plastic state: log_vol_gain accumulates log(det) differences of singular values 1 +- 1e-3 in f32:
+    # absolute 1e-7 on values of order 1e-4
+    assert parity.field_rel_err(g["plastic_det"], o["plastic_det"]) <= 1e-5, errs
+    assert parity.field_rel_err(g["plastic_hardening"], o["plastic_hardening"]) <= 1e-5, errs
+    assert parity.field_rel_err(g["plastic_log_vol_gain"], o["plastic_log_vol_gain"]) <= 5e-3
     assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
     data.close()
 
@@ -103,7 +112,18 @@ def test_hundred_substeps_elastic(pipe3, oracle_mod):
     data, sim = one_substep_both(oracle_mod, pipe3, scene, scene["particles"], n=100)
     g, o = data.read_particles(), sim.read_particles()
     assert parity.field_rel_err(g["position"], o["position"]) <= 1e-4
-    assert parity.field_rel_err(g["velocity"], o["velocity"]) <= 1e-2
+    assert parity.field_rel_err(g["velocity"], o["velocity"]) <= 1e-4
+    data.close()
+
+
+def test_hundred_substeps_sand_reported(pipe3, oracle_mod):
+    """Sand is chaotic (hard branches in drucker_prager.wgsl:118,125 amplify summation-order noise,
+    SURVEY §7): positions still have to stay within the 1e-4 bound, velocities are only sanity-checked."""
+    scene = scenes.sand_column_3d(12, 24, 12, y_offset=-5.0)
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, scene["particles"], n=100)
+    g, o = data.read_particles(), sim.read_particles()
+    assert parity.field_rel_err(g["position"], o["position"]) <= 1e-4
+    assert parity.field_rel_err(g["velocity"], o["velocity"]) <= 5e-2
     data.close()
 
 
@@ -117,7 +137,8 @@ def test_one_substep_2d(pipe2, oracle_mod):
     gb, gn = data.read_grid()
     ob, on = sim.read_grid()
     parity.assert_grid_close(gb, gn, ob, on, TOL)
-    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-4})
+    parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 2, scene["cell_width"], float(scene["params"].dt))
     assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
     data.close()
 
@@ -138,7 +159,9 @@ def test_two_way_coupling_bodies(pipe3, oracle_mod):
     scene2["bodies"] = bodies
     data, sim = one_substep_both(oracle_mod, pipe3, scene2, parts, n=1)
     g, o = data.read_particles(), sim.read_particles()
-    parity.assert_particles_close(g, o, TOL, tols={"position": 2e-6, "affine": 1e-3, "def_grad": 1e-4})
+    parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
+    assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
     gp, op = data.read_body_poses(), sim.read_body_poses()
     gv, ov = data.read_body_vels(), sim.read_body_vels()
     assert parity.field_rel_err(gp["translation"], op["translation"]) <= 1e-6

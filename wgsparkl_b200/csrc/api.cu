@@ -41,6 +41,7 @@ struct b200mpm_pipeline {
     int dim = 3;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
     bool timestamps = false;
     std::vector<EventPair> events;
@@ -206,11 +207,12 @@ int b200mpm_pipeline_create(int device, int dim, b200mpm_pipeline** out) {
     p->device = device;
     p->dim = dim;
     p->num_sms = prop.multiProcessorCount;
-    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete p;
         return fail(B200MPM_ERR_CUDA, cudaGetErrorString(e));
     }
+    p->stream = p->own_stream;
     *out = p;
     return B200MPM_OK;
 }
@@ -224,8 +226,17 @@ void b200mpm_pipeline_destroy(b200mpm_pipeline* p) {
         cudaEventDestroy(e.b);
     }
     for (auto e : p->event_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(p->stream);
+    cudaStreamDestroy(p->own_stream);
     delete p;
+}
+
+int b200mpm_pipeline_set_stream(b200mpm_pipeline* p, void* cuda_stream) {
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null pipeline");
+    CU_TRY(cudaSetDevice(p->device));
+    fold_events(p);
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+    return B200MPM_OK;
 }
 
 uint64_t b200mpm_pipeline_launch_count(const b200mpm_pipeline* p) { return p ? p->launches : 0; }

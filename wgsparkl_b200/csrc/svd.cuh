@@ -16,8 +16,11 @@ __host__ __device__ inline void svd2(const float* F, float* U, float* S, float* 
     float a = F[0], c = F[1], b = F[2], d = F[3];
     float e = (a + d) * 0.5f, f = (a - d) * 0.5f, g = (c + b) * 0.5f, h = (c - b) * 0.5f;
     float q = sqrtf(e * e + h * h), r = sqrtf(f * f + g * g);
-    S[0] = q + r;
-    S[1] = q - r; // signed: carries det(F)
+    // q - 1 = (e^2 + h^2 - 1) / (q + 1), the numerator formed in f64 (same motivation as svd3 below)
+    const double ed = ((double)a + (double)d) * 0.5, hd = ((double)c - (double)b) * 0.5;
+    float qm1 = (float)(ed * ed + hd * hd - 1.0) / (q + 1.0f);
+    S[0] = 1.0f + (qm1 + r);
+    S[1] = 1.0f + (qm1 - r); // signed: carries det(F)
     float a1 = atan2f(g, f), a2 = atan2f(h, e);
     float theta = (a2 - a1) * 0.5f, phi = (a2 + a1) * 0.5f;
     float sp, cp, st, ct;
@@ -67,16 +70,26 @@ __host__ __device__ inline void jacobi_rot(float& app, float& aqq, float& apq, f
 static inline float rsqrtf_host(float x) { return 1.0f / sqrtf(x); }
 #endif
 
-// ---- 3x3: cyclic Jacobi on F^T F for V, then U and S from B = F V. Column-major. -----------------
+// ---- 3x3: cyclic Jacobi for V, then U and S from B = F V. Column-major. ------------------------------
+// The iteration runs on the SHIFTED matrix M = F^T F - I: Jacobi rotations are invariant under the
+// shift, and the eigenvalues mu_i of M give
+//   sigma_i - 1 = mu_i / (1 + sqrt(1 + mu_i))
+// with an error relative to |sigma_i - 1| instead of relative to 1. Stiff materials multiply
+// (sigma - 1) by ~1e7..1e9 (linear_elasticity.wgsl:32-35), so an f32 SVD whose singular values are only
+// good to 1 ulp of 1.0 injects force noise; here sigma is correctly rounded in all but rare cases, which
+// is what the exact-arithmetic statement of the reference's formula evaluates to.
 template <int SWEEPS = 4>
 __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* V) {
-    // A = F^T F (symmetric)
-    float a00 = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
-    float a11 = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
-    float a22 = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
-    float a01 = F[0] * F[3] + F[1] * F[4] + F[2] * F[5];
-    float a02 = F[0] * F[6] + F[1] * F[7] + F[2] * F[8];
-    float a12 = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
+    // Products of two f32 are exact in f64, so M is formed to ~1e-16 and then rounded ONCE to f32:
+    // the result is accurate relative to |M| even when F is a large rotation times a small stretch
+    // (E = F - I is then O(1) and an f32 assembly would cancel catastrophically). 18 DFMA per particle.
+    const double f0 = F[0], f1 = F[1], f2 = F[2], f3 = F[3], f4 = F[4], f5 = F[5], f6 = F[6], f7 = F[7], f8 = F[8];
+    float a00 = (float)(f0 * f0 + f1 * f1 + f2 * f2 - 1.0);
+    float a11 = (float)(f3 * f3 + f4 * f4 + f5 * f5 - 1.0);
+    float a22 = (float)(f6 * f6 + f7 * f7 + f8 * f8 - 1.0);
+    float a01 = (float)(f0 * f3 + f1 * f4 + f2 * f5);
+    float a02 = (float)(f0 * f6 + f1 * f7 + f2 * f8);
+    float a12 = (float)(f3 * f6 + f4 * f7 + f5 * f8);
     float v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
 #pragma unroll
     for (int sweep = 0; sweep < SWEEPS; ++sweep) {
@@ -84,6 +97,22 @@ __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* 
         jacobi_rot(a00, a22, a02, a01, a12, v0, v2);
         jacobi_rot(a11, a22, a12, a01, a02, v1, v2);
     }
+    // Sort eigenpairs by decreasing eigenvalue; a swap with one negation keeps det(V) = +1.
+#define B2_CSWAP(na, nb, va, vb)          \
+    if (na < nb) {                        \
+        float tn = na;                    \
+        na = nb;                          \
+        nb = tn;                          \
+        _Pragma("unroll") for (int k = 0; k < 3; ++k) { \
+            float tv = va[k];             \
+            va[k] = vb[k];                \
+            vb[k] = -tv;                  \
+        }                                 \
+    }
+    B2_CSWAP(a00, a11, v0, v1)
+    B2_CSWAP(a00, a22, v0, v2)
+    B2_CSWAP(a11, a22, v1, v2)
+#undef B2_CSWAP
     // B = F V
     float b0[3], b1[3], b2[3];
 #pragma unroll
@@ -92,32 +121,21 @@ __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* 
         b1[r] = F[r] * v1[0] + F[3 + r] * v1[1] + F[6 + r] * v1[2];
         b2[r] = F[r] * v2[0] + F[3 + r] * v2[1] + F[6 + r] * v2[2];
     }
-    float n0 = b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2];
-    float n1 = b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2];
-    float n2 = b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2];
-    // Sort columns by decreasing norm; a swap with one negation keeps det(V) = +1.
-#define B2_CSWAP(na, nb, ba, bb, va, vb)  \
-    if (na < nb) {                        \
-        float tn = na;                    \
-        na = nb;                          \
-        nb = tn;                          \
-        _Pragma("unroll") for (int k = 0; k < 3; ++k) { \
-            float tb = ba[k];             \
-            ba[k] = bb[k];                \
-            bb[k] = -tb;                  \
-            float tv = va[k];             \
-            va[k] = vb[k];                \
-            vb[k] = -tv;                  \
-        }                                 \
+    // sigma_i = sqrt(1 + mu_i), sigma_i - 1 = mu_i / (1 + sigma_i); for strongly compressed directions
+    // (sigma < ~0.7) 1 + mu_i cancels, and |F v_i| is the accurate expression instead.
+    float s0, s1, s2;
+    {
+        float nb0 = sqrtf(b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2]);
+        float nb1 = sqrtf(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+        float nb2 = sqrtf(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+        s0 = (a00 > -0.5f) ? 1.0f + a00 / (1.0f + sqrtf(1.0f + a00)) : nb0;
+        s1 = (a11 > -0.5f) ? 1.0f + a11 / (1.0f + sqrtf(1.0f + a11)) : nb1;
+        s2 = (a22 > -0.5f) ? 1.0f + a22 / (1.0f + sqrtf(1.0f + a22)) : nb2;
     }
-    B2_CSWAP(n0, n1, b0, b1, v0, v1)
-    B2_CSWAP(n0, n2, b0, b2, v0, v2)
-    B2_CSWAP(n1, n2, b1, b2, v1, v2)
-#undef B2_CSWAP
-    float s0 = sqrtf(n0);
     float u0[3], u1[3], u2[3];
-    if (s0 > 1e-30f) {
-        float inv = 1.0f / s0;
+    float n0 = sqrtf(b0[0] * b0[0] + b0[1] * b0[1] + b0[2] * b0[2]);
+    if (n0 > 1e-30f) {
+        float inv = 1.0f / n0;
         u0[0] = b0[0] * inv;
         u0[1] = b0[1] * inv;
         u0[2] = b0[2] * inv;
@@ -130,7 +148,7 @@ __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* 
     float d01 = u0[0] * b1[0] + u0[1] * b1[1] + u0[2] * b1[2];
     float w[3] = {b1[0] - d01 * u0[0], b1[1] - d01 * u0[1], b1[2] - d01 * u0[2]};
     float nw = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-    if (nw > 1e-6f * s0 && nw > 1e-30f) {
+    if (nw > 1e-6f * n0 && nw > 1e-30f) {
         float inv = 1.0f / nw;
         u1[0] = w[0] * inv;
         u1[1] = w[1] * inv;
@@ -151,9 +169,11 @@ __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* 
     u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
     u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
     u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+    // det(F) < 0: the last singular value carries the sign.
+    if (u2[0] * b2[0] + u2[1] * b2[1] + u2[2] * b2[2] < 0.0f) s2 = -s2;
     S[0] = s0;
-    S[1] = u1[0] * b1[0] + u1[1] * b1[1] + u1[2] * b1[2];
-    S[2] = u2[0] * b2[0] + u2[1] * b2[1] + u2[2] * b2[2]; // signed
+    S[1] = s1;
+    S[2] = s2;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         U[k] = u0[k];

@@ -35,6 +35,7 @@ ERR_GRID_OVERFLOW = -5
 EXPORTS = (
     "b200mpm_pipeline_create",
     "b200mpm_pipeline_destroy",
+    "b200mpm_pipeline_set_stream",
     "b200mpm_last_error",
     "b200mpm_pipeline_launch_count",
     "b200mpm_data_create",
@@ -77,6 +78,7 @@ def load_library():
     L.b200mpm_pipeline_create.argtypes = [i32, i32, ctypes.POINTER(vp)]
     L.b200mpm_pipeline_destroy.argtypes = [vp]
     L.b200mpm_pipeline_destroy.restype = None
+    L.b200mpm_pipeline_set_stream.argtypes = [vp, vp]
     L.b200mpm_pipeline_launch_count.argtypes = [vp]
     L.b200mpm_pipeline_launch_count.restype = ctypes.c_uint64
     L.b200mpm_data_create.argtypes = [vp, vp, vp, sz, vp, sz, ctypes.c_float, u32, ctypes.POINTER(vp)]
@@ -153,6 +155,11 @@ class MpmPipeline:
 
     def sync(self):
         _check(load_library().b200mpm_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        """Submit to a caller-owned CUDA stream (an integer `cudaStream_t`, e.g.
+        `torch.cuda.current_stream().cuda_stream`); None restores the pipeline's own stream."""
+        _check(load_library().b200mpm_pipeline_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 
     def set_timestamps(self, enabled: bool):
         _check(load_library().b200mpm_set_timestamps(self._h, 1 if enabled else 0))
