@@ -2,6 +2,7 @@
 // Mirrors MpmPipeline / MpmData (src/pipeline.rs:24-39, 84-95) — see INTEGRATION.md for the
 // Rust-side binding. No CPU fallback: every entry point needs a CUDA device.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -44,6 +45,7 @@ struct b200mpm_pipeline {
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
     bool timestamps = false;
+    bool use_graphs = true;
     std::vector<EventPair> events;
     std::vector<cudaEvent_t> event_pool;
     double pass_ms[B200MPM_NUM_PASSES] = {0};
@@ -62,6 +64,13 @@ struct b200mpm_data {
     size_t staging_bytes = 0;
     void* pinned = nullptr; // pinned host mirror of small transfers
     size_t pinned_bytes = 0;
+    // One captured CUDA graph per ping-pong parity: the substep is recorded once and replayed, like the
+    // reference's KernelInvocationQueue (src_testbed/step.rs:122-128). Independent kernels sit on parallel
+    // branches of the graph.
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    uint64_t graph_launches[2] = {0, 0};
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -144,15 +153,87 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
         launch_touch(c, d->dev, d->cur);
         launch_count(c, d->dev);
         launch_scan_cells(c, d->dev);
-        launch_scatter(c, d->dev);
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_UPDATE_CDF);
         launch_block_prepare(c, d->dev);
     }
+    {
+        PassTimer t(p, B200MPM_PASS_GRID_SORT);
+        launch_scatter(c, d->dev, d->cur);
+    }
+}
+
+// Enqueues one substep. With `side` the independent kernels are forked onto a second stream:
+//   touch -> { block_prepare  ||  count -> scan } -> scatter -> { g2p_cdf -> p2g(cpic)  ||  p2g } -> g2p
+void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cudaStream_t side, uint64_t* counter) {
+    LaunchCfg c{p->dim, p->num_sms, main, counter};
+    LaunchCfg cs{p->dim, p->num_sms, side ? side : main, counter};
+    const DeviceData& dev = d->dev;
+    launch_begin_substep(c, dev);
+    launch_clear(c, dev);
+    launch_touch(c, dev, d->cur);
+    if (side) {
+        cudaEventRecord(d->ev[0], main);
+        cudaStreamWaitEvent(side, d->ev[0], 0);
+    }
+    launch_block_prepare(cs, dev);
+    if (side) cudaEventRecord(d->ev[1], side);
+    launch_count(c, dev);
+    launch_scan_cells(c, dev);
+    if (side) cudaStreamWaitEvent(main, d->ev[1], 0);
+    launch_scatter(c, dev, d->cur);
+    if (side && dev.has_bodies) {
+        cudaEventRecord(d->ev[2], main);
+        cudaStreamWaitEvent(side, d->ev[2], 0);
+    }
+    launch_g2p_cdf(cs, dev, d->cur);
+    launch_p2g_cpic(cs, dev, d->cur);
+    if (side && dev.has_bodies) cudaEventRecord(d->ev[3], side);
+    launch_p2g(c, dev, d->cur);
+    if (side && dev.has_bodies) cudaStreamWaitEvent(main, d->ev[3], 0);
+    launch_g2p_update(c, dev, d->cur);
+    launch_integrate_bodies(c, dev);
+}
+
+// Captures the substep for the current parity into a graph (once), then replays it.
+bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d) {
+    const int par = d->cur;
+    if (!d->graph_exec[par]) {
+        if (!d->side) {
+            if (cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking) != cudaSuccess) return false;
+            for (auto& e : d->ev)
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        cudaGraph_t graph = nullptr;
+        uint64_t count = 0;
+        if (cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        enqueue_substep(p, d, p->stream, d->side, &count);
+        if (cudaStreamEndCapture(p->stream, &graph) != cudaSuccess || !graph) {
+            cudaGetLastError();
+            return false;
+        }
+        cudaError_t e = cudaGraphInstantiate(&d->graph_exec[par], graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            d->graph_exec[par] = nullptr;
+            return false;
+        }
+        d->graph_launches[par] = count;
+    }
+    if (cudaGraphLaunch(d->graph_exec[par], p->stream) != cudaSuccess) return false;
+    p->launches += d->graph_launches[par];
+    d->cur ^= 1;
+    d->sorted_indirect = false;
+    return true;
 }
 
 void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
+    if (!p->timestamps && p->use_graphs && run_substep_graph(p, d)) return;
     LaunchCfg c = p->cfg();
     {
         PassTimer t(p, B200MPM_PASS_UPDATE_RIGID_PARTICLES);
@@ -165,6 +246,7 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
     }
     {
         PassTimer t(p, B200MPM_PASS_P2G);
+        launch_p2g_cpic(c, d->dev, d->cur);
         launch_p2g(c, d->dev, d->cur);
     }
     {
@@ -207,6 +289,7 @@ int b200mpm_pipeline_create(int device, int dim, b200mpm_pipeline** out) {
     p->device = device;
     p->dim = dim;
     p->num_sms = prop.multiProcessorCount;
+    p->use_graphs = getenv("B200MPM_NO_GRAPH") == nullptr; // debugging aid: plain launches
     cudaError_t e = cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete p;
@@ -398,6 +481,9 @@ int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, c
     ALLOC(dev.nbr, (size_t)capacity * (D == 2 ? 4 : 8));
     ALLOC(dev.node_mv, (size_t)capacity * CELLS_PER_BLOCK);
     if (dev.has_bodies) ALLOC(dev.node_cdf, (size_t)capacity * CELLS_PER_BLOCK);
+    ALLOC(dev.block_flags, capacity);
+    ALLOC(dev.block_f0, capacity);
+    ALLOC(dev.cpic_list, capacity);
     ALLOC(dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2);
     ALLOC(dev.bodies, B200MPM_MAX_BODIES);
     ALLOC(dev.sim, 1);
@@ -479,6 +565,11 @@ void b200mpm_data_destroy(b200mpm_data* d) {
     if (!d) return;
     cudaSetDevice(d->pipe->device);
     cudaStreamSynchronize(d->pipe->stream);
+    for (auto& g : d->graph_exec)
+        if (g) cudaGraphExecDestroy(g);
+    for (auto& e : d->ev)
+        if (e) cudaEventDestroy(e);
+    if (d->side) cudaStreamDestroy(d->side);
     for (void* p : d->allocs) cudaFree(p);
     if (d->staging) cudaFree(d->staging);
     if (d->pinned) cudaFreeHost(d->pinned);

@@ -10,7 +10,7 @@
 
 namespace b2 {
 
-constexpr int CDF_THREADS = 128;
+constexpr int CDF_THREADS = 256;
 
 template <int Q>
 struct SmallMat {
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
     __shared__ uint32_t s_nbr[NA];
     __shared__ uint32_t s_next;
     const int t = threadIdx.x;
-    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+    const uint32_t ncpic = d.counters->num_cpic_blocks;
     const uint32_t num_bodies = d.sim->num_bodies;
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
         __syncthreads();
         if (t == 0) s_next = atomicAdd(&d.counters->work_cdf, 1u);
         __syncthreads();
-        const uint32_t b = s_next;
-        if (b >= nb) break;
+        if (s_next >= ncpic) break;
+        const uint32_t b = d.cpic_list[s_next];
         const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
         const uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
         if (first == last) continue;

@@ -68,6 +68,9 @@ struct BodyDev {
     // IntegerImpulseAtomic (rigid_impulses.wgsl:27-47)
     int imp_lin[3];
     int imp_ang[3];
+    // 0 if an impulse cannot change anything observable: infinite mass AND zero velocity (then applyImpulse is
+    // a no-op and the velocity caps of rigid_impulses.wgsl:118-126 cannot trigger). Refreshed every substep.
+    uint32_t needs_impulse;
 };
 
 struct SimState {
@@ -84,8 +87,10 @@ struct Counters {
     uint32_t overflow; // sticky: the block capacity / hash map was exceeded at least once
     uint32_t scan_ticket; // dynamic tile id for the single-pass scan
     uint32_t work_p2g; // dynamic block schedulers
+    uint32_t work_p2g_cpic;
     uint32_t work_g2p;
     uint32_t work_cdf;
+    uint32_t num_cpic_blocks; // blocks (with particles) whose tile holds a collider this substep
     uint32_t dropped_particles; // particles whose block was dropped (overflow)
 };
 
@@ -126,6 +131,9 @@ struct DeviceData {
     float4* node_mv; // capacity*64: momentum xyz + mass (Node.momentum_velocity_mass, grid.wgsl:257-267)
     uint4* node_cdf; // capacity*64: bits(distance), affinities, closest_id, - (NodeCdf, grid.wgsl:233-240)
     uint64_t* scan_state; // single-pass scan tile descriptors
+    uint8_t* block_f0; // capacity: 1 if one of the block's own nodes is near / inside a collider (k_block_prepare)
+    uint8_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)
+    uint32_t* cpic_list; // capacity: compact list of flagged blocks that hold particles
 
     BodyDev* bodies;
     SimState* sim;

@@ -22,7 +22,7 @@ namespace b2 {
 constexpr int G2P_THREADS = 128;
 
 template <int D, bool PLASTIC, bool CPIC>
-__global__ void __launch_bounds__(G2P_THREADS) k_g2p(DeviceData d, int cur) {
+__global__ void __launch_bounds__(G2P_THREADS, 6) k_g2p(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC;
     __shared__ float4 tile_v[TC];
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(DeviceData d, int cur) {
         if (t < NA) s_nbr[t] = d.nbr[b * NA + t];
         __syncthreads();
         // Stage the tile; grid_update (grid_update.wgsl:45-64) on the fly.
-        int mine = 0;
+        const int any_cdf = CPIC ? (int)d.block_flags[b] : 0; // the tile holds a collider (k_scatter)
         for (int n = t; n < TC; n += G2P_THREADS) { // g2p.wgsl:72-132
             int x = n % T, y = (n / T) % T, z = n / (T * T);
             int ox = x >= B, oy = y >= B, oz = z >= B;
@@ -79,18 +79,15 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(DeviceData d, int cur) {
                     out.z = fminf(fmaxf(vz, -vel_limit), vel_limit);
                 }
                 out.w = mass;
-                if (CPIC) {
+                if (CPIC && any_cdf) {
                     uint4 g = d.node_cdf[node];
                     cdf = make_uint2(g.y, g.z);
                 }
             }
             tile_v[n] = out;
-            if (CPIC) {
-                tile_c[n] = cdf;
-                mine |= (cdf.x != 0u);
-            }
+            if (CPIC && any_cdf) tile_c[n] = cdf;
         }
-        const int any_cdf = CPIC ? __syncthreads_or(mine) : (__syncthreads(), 0);
+        __syncthreads();
 
         for (uint32_t k = first + t; k < last; k += G2P_THREADS) {
             const uint32_t id = __ldg(d.sorted_ids + k);
@@ -122,7 +119,6 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(DeviceData d, int cur) {
             uint32_t pa = 0u;
             V3 normal = v3(0, 0, 0);
             float sd = 0.0f;
-            const bool cpic_particle = CPIC && any_cdf;
             if (CPIC) {
                 if (any_cdf) pa = d.cdf_aff[nxt][k];
                 if (pa != 0u) {
@@ -143,60 +139,82 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(DeviceData d, int cur) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) mom[c][r] = 0.0f;
             }
+            if (!CPIC || pa == 0u) {
+                // Fast path (a zero affinity word is compatible with every node): fully unrolled,
+                // separable accumulation — ~4.3 FMA per node and component.
 #pragma unroll
-            for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz) {
-                float r0[D], rx[D], ry[D];
+                for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz) {
+                    float r0[D], rx[D], ry[D];
 #pragma unroll
-                for (int r = 0; r < D; ++r) r0[r] = rx[r] = ry[r] = 0.0f;
+                    for (int r = 0; r < D; ++r) r0[r] = rx[r] = ry[r] = 0.0f;
 #pragma unroll
-                for (int sy = 0; sy < 3; ++sy) {
-                    float t0[D], t1[D];
+                    for (int sy = 0; sy < 3; ++sy) {
+                        float t0[D], t1[D];
 #pragma unroll
-                    for (int r = 0; r < D; ++r) t0[r] = t1[r] = 0.0f;
+                        for (int r = 0; r < D; ++r) t0[r] = t1[r] = 0.0f;
 #pragma unroll
-                    for (int sx = 0; sx < 3; ++sx) {
-                        const int idx = tb + sx + T * sy + T * T * sz;
-                        const float4 cell = tile_v[idx];
-                        float cv[3] = {cell.x, cell.y, cell.z};
-                        if (CPIC) {
-                            if (cpic_particle) {
-                                const uint2 nc = tile_c[idx];
-                                if (!affinities_are_compatible(pa, nc.x)) { // g2p.wgsl:186-207
-                                    V3 ghost = pvel;
-                                    if (nc.y != NONE) {
-                                        const BodyDev& body = d.bodies[nc.y];
-                                        V3 center = v3(d0[0] + (float)sx * h, d0[1] + (float)sy * h,
-                                                       (D == 3) ? d0[D - 1] + (float)sz * h : 0.0f) + ppos;
-                                        V3 bpv = velocity_at_point<D>(body, center);
-                                        ghost = bpv + project_velocity(pvel - bpv, normal);
-                                    }
-                                    cv[0] = ghost.x, cv[1] = ghost.y, cv[2] = ghost.z;
-                                }
+                        for (int sx = 0; sx < 3; ++sx) {
+                            const float4 cell = tile_v[tb + sx + T * sy + T * T * sz];
+                            const float cv[3] = {cell.x, cell.y, cell.z};
+                            const float wx = w[0][sx];
+#pragma unroll
+                            for (int r = 0; r < D; ++r) {
+                                float wv = wx * cv[r];
+                                t0[r] += wv;
+                                if (sx > 0) t1[r] += (float)sx * wv;
                             }
                         }
-                        const float wx = w[0][sx];
+                        const float wy = w[1][sy];
 #pragma unroll
                         for (int r = 0; r < D; ++r) {
-                            float wv = wx * cv[r];
-                            t0[r] += wv;
-                            if (sx > 0) t1[r] += (float)sx * wv;
+                            r0[r] += wy * t0[r];
+                            rx[r] += wy * t1[r];
+                            if (sy > 0) ry[r] += ((float)sy * wy) * t0[r];
                         }
                     }
-                    const float wy = w[1][sy];
+                    const float wz = (D == 3) ? w[D - 1][sz] : 1.0f;
 #pragma unroll
                     for (int r = 0; r < D; ++r) {
-                        r0[r] += wy * t0[r];
-                        rx[r] += wy * t1[r];
-                        if (sy > 0) ry[r] += ((float)sy * wy) * t0[r];
+                        vs[r] += wz * r0[r];
+                        mom[0][r] += wz * rx[r];
+                        mom[1][r] += wz * ry[r];
+                        if (D == 3 && sz > 0) mom[D - 1][r] += ((float)sz * wz) * r0[r];
                     }
                 }
-                const float wz = (D == 3) ? w[D - 1][sz] : 1.0f;
+            } else {
+                // CPIC path (particles next to a collider only; g2p.wgsl:186-207): incompatible nodes
+                // contribute the particle's ghost velocity. Deliberately NOT unrolled: these particles are
+                // few, and the unrolled form triples the kernel's instruction-cache footprint.
+#pragma unroll 1
+                for (int n = 0; n < Dim<D>::NBH; ++n) {
+                    const int sx = n % 3, sy = (n / 3) % 3, sz = n / 9;
+                    const int idx = tb + sx + T * sy + T * T * sz;
+                    const float4 cell = tile_v[idx];
+                    const uint2 nc = tile_c[idx];
+                    float cv[3] = {cell.x, cell.y, cell.z};
+                    if (!affinities_are_compatible(pa, nc.x)) {
+                        V3 ghost = pvel;
+                        if (nc.y != NONE) {
+                            const BodyDev& body = d.bodies[nc.y];
+                            V3 center = v3(d0[0] + (float)sx * h, d0[1] + (float)sy * h,
+                                           (D == 3) ? d0[D - 1] + (float)sz * h : 0.0f) + ppos;
+                            V3 bpv = velocity_at_point<D>(body, center);
+                            ghost = bpv + project_velocity(pvel - bpv, normal);
+                        }
+                        cv[0] = ghost.x, cv[1] = ghost.y, cv[2] = ghost.z;
+                    }
+                    const float wxs = (sx == 0) ? w[0][0] : (sx == 1) ? w[0][1] : w[0][2];
+                    const float wys = (sy == 0) ? w[1][0] : (sy == 1) ? w[1][1] : w[1][2];
+                    const float wzs = (D == 3) ? ((sz == 0) ? w[D - 1][0] : (sz == 1) ? w[D - 1][1] : w[D - 1][2]) : 1.0f;
+                    const float wt = wxs * wys * wzs;
+                    const float sc[3] = {(float)sx, (float)sy, (float)sz};
 #pragma unroll
-                for (int r = 0; r < D; ++r) {
-                    vs[r] += wz * r0[r];
-                    mom[0][r] += wz * rx[r];
-                    mom[1][r] += wz * ry[r];
-                    if (D == 3 && sz > 0) mom[D - 1][r] += ((float)sz * wz) * r0[r];
+                    for (int r = 0; r < D; ++r) {
+                        const float wv = wt * cv[r];
+                        vs[r] += wv;
+#pragma unroll
+                        for (int c = 0; c < D; ++c) mom[c][r] += sc[c] * wv;
+                    }
                 }
             }
             float G[D * D]; // velocity gradient, column-major: G[c*D + r] = sum (w inv_d) v[r] dpt[c]
@@ -262,7 +280,6 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(DeviceData d, int cur) {
             }
             if (PLASTIC) d.plastic[nxt][k] = plastic;
             if (CPIC) {
-                if (!any_cdf) d.cdf_aff[nxt][k] = 0u; // (k_g2p_cdf already wrote it when any_cdf)
                 if (pa != 0u) d.cdf_rv[k] = make_float4(rigid_vel.x, rigid_vel.y, rigid_vel.z, 0.0f);
             }
         }

@@ -16,12 +16,22 @@ __global__ void k_begin_substep(DeviceData d) {
         c->num_active_blocks = 0;
         c->scan_ticket = 0;
         c->work_p2g = 0;
+        c->work_p2g_cpic = 0;
         c->work_g2p = 0;
         c->work_cdf = 0;
+        c->num_cpic_blocks = 0;
         c->dropped_particles = 0;
     }
     if (id < d.sim->num_bodies) {
         BodyDev& b = d.bodies[id];
+        {
+            float any = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) any += fabsf(b.local_inv_mass[k]) + fabsf(b.linvel[k]) + fabsf(b.angvel[k]);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) any += fabsf(b.local_inv_inertia[k]);
+            b.needs_impulse = (any != 0.0f || any != any) ? 1u : 0u;
+        }
 #pragma unroll
         for (int r = 0; r < D; ++r) {
             float s = b.rot[r] * b.local_com[0];

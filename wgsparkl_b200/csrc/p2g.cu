@@ -5,57 +5,87 @@
 // two barriers each, 16 hash probes per thread).
 //
 // B200 design: a block-local SCATTER over cell-sorted particles.
-//   * one CTA per active block, ONE THREAD PER CELL: the thread walks the contiguous run of its
-//     cell's particles and reduces their 3^D stencil contributions in REGISTERS
-//     (27 x 4 accumulators in 3D) — the segmented reduction over the cell's run never touches
-//     memory and costs ~8 issue slots per particle-node pair, against ~25 for a lane-per-node
-//     layout and ~44 for a shuffle-based segmented reduction;
+//   * one CTA per active block; the block's particles (a contiguous range of the sorted order) are
+//     staged into shared memory with cp.async (LDGSTS, 16 bytes per request, no register staging);
+//   * ONE THREAD PER CELL: the thread walks the contiguous run of its cell's particles and reduces
+//     their 3^D stencil contributions in REGISTERS (27 x 4 accumulators in 3D) — the segmented
+//     reduction over the cell's run never touches memory and costs ~8 issue slots per
+//     particle-node pair, against ~25 for a lane-per-node layout and ~44 for a shuffle-based
+//     segmented reduction;
 //   * the per-cell partial stencils are merged into the block's (BLOCK+2)^D shared-memory tile
 //     in 3^D conflict-free phases (in phase s every cell adds to node cell+s: all distinct), so the
 //     shared-memory reduction needs no atomics (shared f32 atomics are CAS loops on sm_100);
 //   * the tile is flushed with one vector reduction per node (RED.E.ADD.F32x4, sm_90+) into the
 //     2^D blocks it overlaps, found through the per-block neighbour table instead of hash probes.
 // CPIC-incompatible particle/node pairs (grid.wgsl:250-255) are skipped and turned into body
-// impulses exactly like p2g.wgsl:201-226; only blocks whose tile holds a collider run that path.
+// impulses exactly like p2g.wgsl:201-226; only the blocks whose tile holds a collider run that
+// instantiation (a second pass over the staged particles accumulates the per-node impulses with
+// the same register/phase scheme, so the impulse path has no floating-point atomics either).
 #include "launch.h"
 
 namespace b2 {
 
 constexpr int P2G_THREADS = CELLS_PER_BLOCK;
+constexpr int P2G_CHUNK = 512; // particles staged per pass (8 per cell = the reference's seeding density)
+constexpr int P2G_CHUNK_CPIC = 384;
 
-template <int D>
+enum { P2G_FAST = 0, P2G_CPIC_MOMENTUM = 1, P2G_CPIC_IMPULSE = 2 };
+
+template <int NBH, int W>
 struct P2GAcc {
-    float a[Dim<D>::NBH][D + 1];
+    float a[NBH][W];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int n = 0; n < NBH; ++n)
+#pragma unroll
+            for (int r = 0; r < W; ++r) a[n][r] = 0.0f;
+    }
 };
 
-template <int D, bool CPIC>
-__device__ __forceinline__ void p2g_accumulate(const DeviceData& d, int cur, uint32_t start, uint32_t end,
-                                               const float* cellpos, float h, float inv_h, int tb, const uint2* tcdf,
-                                               float* timp, P2GAcc<D>& acc) {
+// Staged particle record in shared memory (SoA of float4, 64 bytes per particle):
+//   sp = (x, y, z, mass)   sv = (vx, vy, vz, -)   sa = C[0..3]   sb = C[4..7]   sc = C[8]
+// Slot i is stored at i ^ ((i >> 3) & 7): a cell's run starts at ~8 t for thread t, so consecutive lanes
+// would otherwise hit the same bank group on every 16-byte load (8-way conflict).
+__device__ __forceinline__ int p2g_swz(int i) { return i ^ ((i >> 3) & 7); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Walks the staged particles [lo, hi) of one cell.
+//   MODE FAST / CPIC_MOMENTUM: acc[n] += w (affine dpt + m v, m)       (p2g.wgsl:188-230)
+//   MODE CPIC_IMPULSE        : acc[n] += (delta_impulse, delta_ang)     (p2g.wgsl:203-225)
+template <int D, int MODE, int W>
+__device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uint32_t base, int lo, int hi,
+                                               const float4* sp, const float4* sv, const float4* sa, const float4* sb,
+                                               const float* sc, const uint32_t* s_aff, const float* cellpos, float h, float inv_h, int tb,
+                                               const uint2* tcdf, P2GAcc<Dim<D>::NBH, W>& acc) {
     constexpr int T = Dim<D>::TILE;
-    const float4* __restrict__ pos4 = d.pos4[cur];
-    const float4* __restrict__ vel4 = d.vel4[cur];
-    const float4* __restrict__ Ca = d.Ca[cur];
-    const float4* __restrict__ Cb = d.Cb[cur];
-    const float* __restrict__ Cc = d.Cc[cur];
-    for (uint32_t q = start; q < end; ++q) {
-        const uint32_t id = __ldg(d.sorted_ids + q);
-        const float4 p4 = __ldg(pos4 + id);
-        const float4 v4 = __ldg(vel4 + id);
+    bool any_incompatible = false;
+    for (int i = lo; i < hi; ++i) {
+        const int s = p2g_swz(i);
+        const float4 p4 = sp[s];
+        const float4 v4 = sv[s];
         float C[D * D];
         {
-            float4 ca = __ldg(Ca + id);
+            float4 ca = sa[s];
             C[0] = ca.x, C[1] = ca.y, C[2] = ca.z, C[3] = ca.w;
             if (D == 3) {
-                float4 cb = __ldg(Cb + id);
+                float4 cb = sb[s];
                 C[4] = cb.x, C[5] = cb.y, C[6] = cb.z, C[7] = cb.w;
-                C[D * D - 1] = __ldg(Cc + id);
+                C[D * D - 1] = sc[s];
             }
         }
-        const float mass = __ldg(&d.materials[__float_as_uint(p4.w) & MAT_ID_MASK].mass);
+        const float mass = p4.w;
         const float pp[3] = {p4.x, p4.y, p4.z};
         const float vv[3] = {v4.x, v4.y, v4.z};
-        float d0[D], w[D][3], base[D];
+        float d0[D], w[D][3], bs[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             d0[k] = cellpos[k] - pp[k]; // dir_to_associated_grid_node (particle3d.wgsl:55-57)
@@ -63,27 +93,26 @@ __device__ __forceinline__ void p2g_accumulate(const DeviceData& d, int cur, uin
         }
 #pragma unroll
         for (int r = 0; r < D; ++r) {
-            float s = mass * vv[r];
+            float t = mass * vv[r];
 #pragma unroll
-            for (int c = 0; c < D; ++c) s += C[c * D + r] * d0[c];
-            base[r] = s; // affine * d0 + m v
+            for (int c = 0; c < D; ++c) t += C[c * D + r] * d0[c];
+            bs[r] = t; // affine * d0 + m v
         }
         uint32_t pa = 0;
         V3 normal = v3(0, 0, 0);
-        if (CPIC) {
-            pa = d.cdf_aff[cur ^ 1][q]; // this substep's affinity, written by k_g2p_cdf by sorted slot
-            if (pa != 0u) {
-                float4 nd = d.cdf_nd[q];
+        if (MODE != P2G_FAST) {
+            pa = s_aff[s];
+            if (MODE == P2G_CPIC_IMPULSE && pa == 0u) continue; // compatible with every node: no impulse
+            if (MODE == P2G_CPIC_IMPULSE) {
+                float4 nd = d.cdf_nd[base + (uint32_t)i];
                 normal = v3(nd.x, nd.y, (D == 3) ? nd.z : 0.0f);
             }
         }
-        // Stencil: node s = (sx, sy, sz) in {0,1,2}^D, dpt = d0 + s h,
-        // contribution w (affine dpt + m v, m) (p2g.wgsl:188-230).
 #pragma unroll
         for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz) {
             float az[D];
 #pragma unroll
-            for (int r = 0; r < D; ++r) az[r] = (D == 3) ? base[r] + (float)sz * h * C[(D - 1) * D + r] : base[r];
+            for (int r = 0; r < D; ++r) az[r] = (D == 3) ? bs[r] + (float)sz * h * C[(D - 1) * D + r] : bs[r];
             const float wz = (D == 3) ? w[D - 1][sz] : 1.0f;
 #pragma unroll
             for (int sy = 0; sy < 3; ++sy) {
@@ -95,14 +124,11 @@ __device__ __forceinline__ void p2g_accumulate(const DeviceData& d, int cur, uin
                 for (int sx = 0; sx < 3; ++sx) {
                     const int n = sx + 3 * sy + 9 * sz;
                     const float wt = w[0][sx] * wyz;
-                    float a[D];
-#pragma unroll
-                    for (int r = 0; r < D; ++r) a[r] = ay[r] + (float)sx * h * C[r];
-                    if (CPIC) {
-                        const int idx = tb + sx + T * sy + T * T * sz;
-                        const uint2 nc = tcdf[idx];
-                        if (!affinities_are_compatible(nc.x, pa)) {
-                            if (nc.y != NONE) { // p2g.wgsl:203-225
+                    if (MODE != P2G_FAST) {
+                        const uint2 nc = tcdf[tb + sx + T * sy + T * T * sz];
+                        const bool compatible = affinities_are_compatible(nc.x, pa);
+                        if (MODE == P2G_CPIC_IMPULSE) {
+                            if (!compatible && nc.y != NONE && d.bodies[nc.y].needs_impulse) { // p2g.wgsl:203-225
                                 const BodyDev& body = d.bodies[nc.y];
                                 V3 dpt = v3(d0[0] + (float)sx * h, d0[1] + (float)sy * h, (D == 3) ? d0[D - 1] + (float)sz * h : 0.0f);
                                 V3 pv = v3(vv[0], vv[1], (D == 3) ? vv[2] : 0.0f);
@@ -111,64 +137,130 @@ __device__ __forceinline__ void p2g_accumulate(const DeviceData& d, int cur, uin
                                 V3 ghost = bpv + project_velocity(pv - bpv, normal);
                                 V3 delta = (pv - ghost) * (wt * mass);
                                 V3 lever = v3(body.com[0], body.com[1], (D == 3) ? body.com[2] : 0.0f) - center;
-                                atomicAdd(timp + idx * 6 + 0, delta.x);
-                                atomicAdd(timp + idx * 6 + 1, delta.y);
+                                acc.a[n][0] += delta.x;
+                                acc.a[n][1] += delta.y;
                                 if (D == 3) {
                                     V3 ang = cross(delta, lever);
-                                    atomicAdd(timp + idx * 6 + 2, delta.z);
-                                    atomicAdd(timp + idx * 6 + 3, ang.x);
-                                    atomicAdd(timp + idx * 6 + 4, ang.y);
-                                    atomicAdd(timp + idx * 6 + 5, ang.z);
+                                    acc.a[n][2] += delta.z;
+                                    acc.a[n][3] += ang.x;
+                                    acc.a[n][4] += ang.y;
+                                    acc.a[n][W - 1] += ang.z;
                                 } else {
-                                    atomicAdd(timp + idx * 6 + 3, delta.x * lever.y - delta.y * lever.x);
+                                    acc.a[n][2] += delta.x * lever.y - delta.y * lever.x;
                                 }
                             }
                             continue;
                         }
+                        if (!compatible) {
+                            if (nc.y != NONE) any_incompatible = any_incompatible || (d.bodies[nc.y].needs_impulse != 0u);
+                            continue;
+                        }
                     }
+                    if (MODE != P2G_CPIC_IMPULSE) {
 #pragma unroll
-                    for (int r = 0; r < D; ++r) acc.a[n][r] += wt * a[r];
-                    acc.a[n][D] += wt * mass;
+                        for (int r = 0; r < D; ++r) acc.a[n][r] += wt * (ay[r] + (float)sx * h * C[r]);
+                        acc.a[n][D] += wt * mass;
+                    }
                 }
             }
         }
     }
+    return any_incompatible;
 }
 
+// CPIC = false: blocks whose tile holds no collider (block_flags == 0, or no bodies at all).
+// CPIC = true : the few blocks next to a collider (block_flags != 0).
 template <int D, bool CPIC>
 __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, LB = Dim<D>::LOG_BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
-    constexpr int NA = Dim<D>::NASSOC;
+    constexpr int NA = Dim<D>::NASSOC, NBH = Dim<D>::NBH;
+    constexpr int WI = (D == 3) ? 6 : 3; // impulse components per node
+    // 48 KB of static shared memory: the collider-side instantiation carries the cdf tile and the impulse
+    // tile, so it stages fewer particles per pass.
+    constexpr int CHUNK = CPIC ? P2G_CHUNK_CPIC : P2G_CHUNK;
+    constexpr int PER_THREAD = CHUNK / P2G_THREADS;
     __shared__ float4 tile[TC];
+    __shared__ float4 sp[CHUNK], sv[CHUNK], sa[CHUNK];
+    __shared__ float4 sb[D == 3 ? CHUNK : 1];
+    __shared__ float sc[D == 3 ? CHUNK : 1];
+    __shared__ uint32_t s_ids[CHUNK];
+    __shared__ uint32_t s_aff[CPIC ? CHUNK : 1]; // this substep's particle affinities (k_g2p_cdf, by sorted slot)
     __shared__ uint32_t s_nbr[NA];
     __shared__ uint32_t s_next;
     __shared__ uint2 tcdf[CPIC ? TC : 1];
-    __shared__ float timp[CPIC ? TC * 6 : 1];
+    __shared__ float timp[CPIC ? TC * WI : 1];
 
     const int t = threadIdx.x;
     const int lx = t & (B - 1), ly = (t >> LB) & (B - 1), lz = (D == 3) ? (t >> (2 * LB)) : 0;
     const int tb = lx + T * ly + T * T * lz;
-    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+    // A collider-side block is split into PARTS work items (each takes every cell's PARTS-th share of the
+    // run): these blocks are few, so their per-block latency — not throughput — is what shows up.
+    constexpr uint32_t PARTS = CPIC ? 4u : 1u;
+    const uint32_t nwork = CPIC ? d.counters->num_cpic_blocks * PARTS : min(d.counters->num_active_blocks, d.capacity);
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
+    uint32_t* work = CPIC ? &d.counters->work_p2g_cpic : &d.counters->work_p2g;
+    const float4* __restrict__ pos4 = d.pos4[cur];
+    const float4* __restrict__ vel4 = d.vel4[cur];
+    const float4* __restrict__ Ca = d.Ca[cur];
+    const float4* __restrict__ Cb = d.Cb[cur];
+    const float* __restrict__ Cc = d.Cc[cur];
+
+    // Stage one chunk of the sorted range into shared memory (gather through sorted_ids, a
+    // near-identity permutation of the current buffers).
+    auto stage = [&](uint32_t base, int cn) {
+        // ids go through shared memory so that the request loop below stays rolled (few live registers
+        // next to the 108 accumulators); each thread only reads back the ids it wrote itself.
+#pragma unroll
+        for (int j = 0; j < PER_THREAD; ++j) {
+            const int i = t + j * P2G_THREADS;
+            if (i < cn) s_ids[i] = __ldg(d.sorted_ids + base + i);
+        }
+#pragma unroll 1
+        for (int i = t; i < cn; i += P2G_THREADS) {
+            const uint32_t id = s_ids[i];
+            const int s = p2g_swz(i);
+            cp_async16(sp + s, pos4 + id);
+            cp_async16(sv + s, vel4 + id);
+            cp_async16(sa + s, Ca + id);
+            if (D == 3) {
+                cp_async16(sb + s, Cb + id);
+                cp_async4(sc + s, Cc + id);
+            }
+            if (CPIC) cp_async4(s_aff + s, d.cdf_aff[cur ^ 1] + base + i);
+        }
+        cp_async_wait_all();
+        // (x, y, z, material bits) -> (x, y, z, mass)
+#pragma unroll 1
+        for (int i = t; i < cn; i += P2G_THREADS) {
+            const int s = p2g_swz(i);
+            const uint32_t mbits = __float_as_uint(sp[s].w);
+            sp[s].w = __ldg(&d.materials[mbits & MAT_ID_MASK].mass);
+        }
+    };
 
     while (true) {
         __syncthreads();
-        if (t == 0) s_next = atomicAdd(&d.counters->work_p2g, 1u);
+        if (t == 0) s_next = atomicAdd(work, 1u);
         __syncthreads();
-        const uint32_t b = s_next;
-        if (b >= nb) break;
+        if (s_next >= nwork) break;
+        const uint32_t b = CPIC ? d.cpic_list[s_next / PARTS] : s_next;
+        const uint32_t part = s_next % PARTS;
+        if (!CPIC && d.has_bodies && d.block_flags[b] != 0) continue; // handled by the CPIC instantiation
         const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
         const uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
         if (first == last) continue; // halo block without particles: nothing to scatter
-        const uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + t];
-        const uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + t + 1];
+        uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + t];
+        uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + t + 1];
+        if (PARTS > 1) {
+            const uint32_t len = end - start;
+            end = start + (len * (part + 1)) / PARTS;
+            start = start + (len * part) / PARTS;
+        }
         if (t < NA) s_nbr[t] = d.nbr[b * NA + t];
         for (int n = t; n < TC; n += P2G_THREADS) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        int any_cdf = 0;
         if (CPIC) {
-            int mine = 0;
             for (int n = t; n < TC; n += P2G_THREADS) {
                 int x = n % T, y = (n / T) % T, z = n / (T * T);
                 int ox = x >= B, oy = y >= B, oz = z >= B;
@@ -179,41 +271,77 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
                     c = make_uint2(g.y, g.z);
                 }
                 tcdf[n] = c;
-                mine |= (c.x != 0u);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) timp[n * 6 + k] = 0.0f;
+                for (int k = 0; k < WI; ++k) timp[n * WI + k] = 0.0f;
             }
-            any_cdf = __syncthreads_or(mine);
         }
 
         const int4 vid = d.block_vid[b];
         const float cellpos[3] = {(float)(vid.x * B + lx) * h, (float)(vid.y * B + ly) * h, (float)(vid.z * B + lz) * h};
-        P2GAcc<D> acc;
+        bool incompatible = false;
+        {
+            P2GAcc<NBH, D + 1> acc;
+            acc.clear();
+            for (uint32_t base = first; base < last; base += CHUNK) {
+                const int cn = (int)min((uint32_t)CHUNK, last - base);
+                __syncthreads(); // the previous chunk is no longer in use; tcdf is complete
+                stage(base, cn);
+                __syncthreads();
+                const int lo = (int)(max(start, base) - base);
+                const int hi = (int)(min(end, base + (uint32_t)cn) - base);
+                incompatible |= p2g_accumulate<D, CPIC ? P2G_CPIC_MOMENTUM : P2G_FAST, D + 1>(
+                    d, cur, base, lo, hi, sp, sv, sa, sb, sc, s_aff, cellpos, h, inv_h, tb, tcdf, acc);
+            }
+            // Merge the per-cell stencils into the tile: 3^D conflict-free phases.
 #pragma unroll
-        for (int n = 0; n < Dim<D>::NBH; ++n)
+            for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz)
 #pragma unroll
-            for (int r = 0; r <= D; ++r) acc.a[n][r] = 0.0f;
-
-        if (CPIC && any_cdf) p2g_accumulate<D, true>(d, cur, start, end, cellpos, h, inv_h, tb, tcdf, timp, acc);
-        else p2g_accumulate<D, false>(d, cur, start, end, cellpos, h, inv_h, tb, nullptr, nullptr, acc);
-
-        // Merge the per-cell stencils into the tile: 3^D conflict-free phases.
+                for (int sy = 0; sy < 3; ++sy)
 #pragma unroll
-        for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz)
-#pragma unroll
-            for (int sy = 0; sy < 3; ++sy)
-#pragma unroll
-                for (int sx = 0; sx < 3; ++sx) {
-                    const int n = sx + 3 * sy + 9 * sz;
-                    const int idx = tb + sx + T * sy + T * T * sz;
-                    float4 c = tile[idx];
-                    c.x += acc.a[n][0];
-                    c.y += acc.a[n][1];
-                    c.z += acc.a[n][2];
-                    if (D == 3) c.w += acc.a[n][D];
-                    tile[idx] = c;
-                    __syncthreads();
+                    for (int sx = 0; sx < 3; ++sx) {
+                        const int n = sx + 3 * sy + 9 * sz;
+                        const int idx = tb + sx + T * sy + T * T * sz;
+                        float4 c = tile[idx];
+                        c.x += acc.a[n][0];
+                        c.y += acc.a[n][1];
+                        c.z += acc.a[n][2];
+                        if (D == 3) c.w += acc.a[n][D];
+                        tile[idx] = c;
+                        __syncthreads();
+                    }
+        }
+        if (CPIC) {
+            // Second pass, only if some particle/node pair of this block is CPIC-incompatible with a
+            // collider attached: per-node body impulses (p2g.wgsl:201-226).
+            if (__syncthreads_or(incompatible ? 1 : 0)) {
+                P2GAcc<NBH, WI> imp;
+                imp.clear();
+                const bool single_chunk = (last - first) <= (uint32_t)CHUNK; // still staged
+                for (uint32_t base = first; base < last; base += CHUNK) {
+                    const int cn = (int)min((uint32_t)CHUNK, last - base);
+                    if (!single_chunk) {
+                        __syncthreads();
+                        stage(base, cn);
+                        __syncthreads();
+                    }
+                    const int lo = (int)(max(start, base) - base);
+                    const int hi = (int)(min(end, base + (uint32_t)cn) - base);
+                    p2g_accumulate<D, P2G_CPIC_IMPULSE, WI>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, s_aff, cellpos, h, inv_h, tb, tcdf, imp);
                 }
+#pragma unroll
+                for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz)
+#pragma unroll
+                    for (int sy = 0; sy < 3; ++sy)
+#pragma unroll
+                        for (int sx = 0; sx < 3; ++sx) {
+                            const int n = sx + 3 * sy + 9 * sz;
+                            const int idx = tb + sx + T * sy + T * T * sz;
+#pragma unroll
+                            for (int k = 0; k < WI; ++k) timp[idx * WI + k] += imp.a[n][k];
+                            __syncthreads();
+                        }
+            }
+        }
 
         // Flush the tile: one 16-byte reduction per touched node.
         for (int n = t; n < TC; n += P2G_THREADS) {
@@ -223,18 +351,20 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
             if (hn == NONE) continue; // only after a capacity overflow
             uint32_t node = hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B;
             float4 c = tile[n];
-            if (D == 2) { // 2D stores (px, py, mass, 0)
-                c.w = 0.0f;
-            }
+            if (D == 2) c.w = 0.0f; // 2D stores (px, py, mass, 0)
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f) atomicAdd(d.node_mv + node, c);
-            if (CPIC && any_cdf) {
+            if (CPIC) {
                 uint32_t cid = tcdf[n].y;
-                if (cid != NONE) { // p2g.wgsl:142-155
+                if (cid != NONE) { // p2g.wgsl:142-155: integer atomics, i32(x * 1e5)
                     BodyDev& body = d.bodies[cid];
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        float li = timp[n * 6 + k], ai = timp[n * 6 + 3 + k];
+                    for (int k = 0; k < D; ++k) {
+                        float li = timp[n * WI + k];
                         if (li != 0.0f) atomicAdd(&body.imp_lin[k], flt2int(li));
+                    }
+#pragma unroll
+                    for (int k = 0; k < WI - D; ++k) {
+                        float ai = timp[n * WI + D + k];
                         if (ai != 0.0f) atomicAdd(&body.imp_ang[k], flt2int(ai));
                     }
                 }
@@ -245,14 +375,19 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
 
 void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
+    const int grid = c.num_sms * 6;
+    if (c.dim == 2) k_p2g<2, false><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
+    else k_p2g<3, false><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
+    ++*c.launch_counter;
+}
+
+// The blocks next to a collider (compact list built by k_scatter). Independent of launch_p2g: the two
+// instantiations touch disjoint blocks and meet only in the commutative node reductions.
+void launch_p2g_cpic(const LaunchCfg& c, const DeviceData& d, int cur) {
+    if (d.n == 0 || !d.has_bodies) return;
     const int grid = c.num_sms * 8;
-    if (c.dim == 2) {
-        if (d.has_bodies) k_p2g<2, true><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
-        else k_p2g<2, false><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
-    } else {
-        if (d.has_bodies) k_p2g<3, true><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
-        else k_p2g<3, false><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
-    }
+    if (c.dim == 2) k_p2g<2, true><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
+    else k_p2g<3, true><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 

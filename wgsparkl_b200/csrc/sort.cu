@@ -217,17 +217,38 @@ __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_block_prepare(DeviceData d)
                            (float)(vid.z * Dim<D>::BLOCK + lz) * h};
             NodeCdf c = collide<D>(d.bodies, num_bodies, h, pt);
             d.node_cdf[b * CELLS_PER_BLOCK + t] = make_uint4(__float_as_uint(c.distance), c.affinities, c.closest_id, 0u);
+            const int any = __syncthreads_or(c.affinities != 0u);
+            if (t == 0) d.block_f0[b] = any ? 1 : 0;
         }
     }
 }
 
 // ---- finalize_particles_sort (sort.wgsl:117-137): atomic-free scatter ------------------------------
-__global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d) {
+template <int D>
+__global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d.has_bodies) {
+        // CPIC work list: a block runs the collider-aware paths iff one of the 2^D blocks its tile overlaps
+        // has a node near / inside a collider. (i doubles as a block index here.)
+        const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+        if (i < nb) {
+            int flag = 0;
+#pragma unroll
+            for (int o = 0; o < Dim<D>::NASSOC; ++o) {
+                uint32_t hn = d.nbr[i * Dim<D>::NASSOC + o];
+                if (hn != NONE) flag |= d.block_f0[hn];
+            }
+            d.block_flags[i] = (uint8_t)flag;
+            if (flag && d.cell_start[i * CELLS_PER_BLOCK] != d.cell_start[(i + 1) * CELLS_PER_BLOCK])
+                d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
+        }
+    }
     if (i >= d.n) return;
     uint32_t ck = d.pkey[i];
     if (ck != NONE) {
-        d.sorted_ids[d.cell_start[ck] + d.rank[i]] = i;
+        const uint32_t dest = d.cell_start[ck] + d.rank[i];
+        d.sorted_ids[dest] = i;
+        if (d.has_bodies) d.cdf_aff[cur ^ 1][dest] = 0u; // default cdf; k_g2p_cdf overwrites the flagged blocks
     } else {
         // Particle of a dropped block (capacity overflow): parked after the sorted range so that
         // its state survives the ping-pong (see k_g2p tail).
@@ -271,9 +292,15 @@ void launch_block_prepare(const LaunchCfg& c, const DeviceData& d) {
     else k_block_prepare<3><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
-void launch_scatter(const LaunchCfg& c, const DeviceData& d) {
+void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
-    k_scatter<<<div_up(d.n, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d);
+    // (covers both the particles and, for the CPIC work list, the active blocks: blocks <= 2^D * particles,
+    // and in practice far fewer; the grid is sized for whichever is larger)
+    uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
+    if (max_blocks > d.capacity) max_blocks = d.capacity;
+    uint64_t threads = d.has_bodies ? (max_blocks > d.n ? max_blocks : d.n) : d.n;
+    if (c.dim == 2) k_scatter<2><<<div_up(threads, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d, cur);
+    else k_scatter<3><<<div_up(threads, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len, uint64_t* scan_state,

@@ -44,8 +44,17 @@ __host__ __device__ inline void jacobi_rot(float& app, float& aqq, float& apq, f
     float c = 1.0f, s = 0.0f;
     float absq = fabsf(apq);
     if (absq > 1e-30f) {
+        // The rotation angle only steers convergence; (c, s) is renormalised below, so the
+        // approximate division / square root of the device path cost no accuracy in V.
+#if defined(__CUDA_ARCH__)
+        float tau = __fdividef(aqq - app, 2.0f * apq);
+        float x = fmaf(tau, tau, 1.0f);
+        float t = __fdividef(copysignf(1.0f, tau), fabsf(tau) + x * rsqrtf(x));
+        if (fabsf(tau) > 1e18f) t = 0.0f; // tau^2 overflowed / __fdividef out of range: no rotation needed
+#else
         float tau = (aqq - app) / (2.0f * apq);
         float t = copysignf(1.0f, tau) / (fabsf(tau) + sqrtf(1.0f + tau * tau));
+#endif
         c = rsqrtf(1.0f + t * t);
         s = t * c;
         // A' = J^T A J with J = [c s; -s c]
