@@ -1,0 +1,258 @@
+// wgsparkl_b200.hpp — C++ host-side mirror of wgsparkl's public interface for the MPM substep hot path,
+// layered on the C ABI of include/b200mpm.h (header-only, no CUDA / torch types).
+//
+// The reference's host code is Rust; there is no Rust toolchain in this image, so the typed host layer
+// above the C ABI is written in C++ with the reference's names, argument meaning and error behaviour:
+//
+//   wgsparkl::models::ElasticCoefficients::from_young_modulus   (src/models/mod.rs:70-75)
+//   wgsparkl::models::DruckerPrager::new_                        (src/models/drucker_prager.rs:18-33)
+//   wgsparkl::solver::ParticleDynamics::with_density             (src/solver/particle3d.rs:28-42)
+//   wgsparkl::solver::{Particle, ParticlePhase, SimulationParams}
+//   wgsparkl::pipeline::MpmPipeline::{new_, queue_step}          (src/pipeline.rs:176-281)
+//   wgsparkl::pipeline::MpmData::{new_, with_select_coupling}    (src/pipeline.rs:98-172)
+//
+// The Rust binding a wgsparkl maintainer would add is rust/wgsparkl_b200_sys.rs + rust/backend.rs
+// (INTEGRATION.md); it has the same shape as this file.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200mpm.h"
+
+namespace wgsparkl {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+inline void check(int code) {
+    if (code != B200MPM_OK) throw Error(code, b200mpm_last_error());
+}
+
+namespace models {
+
+// lame_lambda_mu (src/models/mod.rs:52-61), f32 arithmetic like the original.
+inline void lame_lambda_mu(float young_modulus, float poisson_ratio, float& lambda, float& mu) {
+    lambda = young_modulus * poisson_ratio / ((1.0f + poisson_ratio) * (1.0f - 2.0f * poisson_ratio));
+    mu = young_modulus / (2.0f * (1.0f + poisson_ratio));
+}
+
+struct ElasticCoefficients { // src/models/mod.rs:63-75
+    float lambda = 0.0f, mu = 0.0f;
+    static ElasticCoefficients from_young_modulus(float young_modulus, float poisson_ratio) {
+        ElasticCoefficients e;
+        lame_lambda_mu(young_modulus, poisson_ratio, e.lambda, e.mu);
+        return e;
+    }
+};
+
+struct DruckerPrager { // src/models/drucker_prager.rs:6-33
+    float h0, h1, h2, h3, lambda, mu;
+    static DruckerPrager new_(float young_modulus, float poisson_ratio) {
+        DruckerPrager d;
+        if (young_modulus > 0.0f) lame_lambda_mu(young_modulus, poisson_ratio, d.lambda, d.mu);
+        else d.lambda = d.mu = -1.0f;
+        const float to_rad = 3.14159265358979323846f / 180.0f;
+        d.h0 = 35.0f * to_rad;
+        d.h1 = 9.0f * to_rad;
+        d.h2 = 0.2f;
+        d.h3 = 10.0f * to_rad;
+        return d;
+    }
+};
+
+struct DruckerPragerPlasticState { // src/models/drucker_prager.rs:36-52
+    float plastic_deformation_gradient_det = 1.0f, plastic_hardening = 1.0f, log_vol_gain = 0.0f;
+};
+
+} // namespace models
+
+namespace solver {
+
+template <int DIM>
+struct SimulationParamsT { // src/solver/params.rs:6-16
+    float gravity[DIM];
+    float dt;
+    b200mpm_sim_params to_abi() const {
+        b200mpm_sim_params p{};
+        for (int i = 0; i < DIM; ++i) p.gravity[i] = gravity[i];
+        p.dt = dt;
+        return p;
+    }
+};
+
+struct ParticlePhase { // src/solver/particle_update.rs:37-42
+    float phase, max_stretch;
+};
+
+template <int DIM>
+struct Cdf { // src/solver/particle3d.rs:43-50
+    float normal[DIM] = {}, rigid_vel[DIM] = {};
+    float signed_distance = 0.0f;
+    uint32_t affinity = 0;
+};
+
+template <int DIM>
+struct ParticleDynamics { // src/solver/particle3d.rs:16-42
+    float velocity[DIM] = {};
+    float def_grad[DIM * DIM] = {}; // column-major
+    float affine[DIM * DIM] = {};
+    Cdf<DIM> cdf;
+    float init_volume = 0.0f, init_radius = 0.0f, mass = 0.0f;
+    static ParticleDynamics with_density(float radius, float density) {
+        ParticleDynamics d;
+        float v = radius * 2.0f, vol = 1.0f;
+        for (int i = 0; i < DIM; ++i) vol *= v; // powi(exponent): the particles are square-ish
+        for (int i = 0; i < DIM; ++i) d.def_grad[i * DIM + i] = 1.0f;
+        d.init_volume = vol;
+        d.init_radius = radius;
+        d.mass = vol * density;
+        return d;
+    }
+};
+
+template <int DIM>
+struct Particle { // src/solver/particle3d.rs:53-60
+    float position[DIM] = {};
+    ParticleDynamics<DIM> dynamics;
+    models::ElasticCoefficients model;
+    std::optional<models::DruckerPrager> plasticity;
+    std::optional<ParticlePhase> phase;
+    uint32_t model_kind = B200MPM_MODEL_COROTATED; // additive selector (b200mpm.h)
+
+    // GpuParticles::from_particles + GpuModels::from_particles (particle3d.rs:192-210, models/mod.rs:20-49)
+    b200mpm_particle to_abi() const {
+        b200mpm_particle o;
+        std::memset(&o, 0, sizeof(o));
+        for (int i = 0; i < DIM; ++i) {
+            o.position[i] = position[i];
+            o.velocity[i] = dynamics.velocity[i];
+            o.cdf_normal[i] = dynamics.cdf.normal[i];
+            o.cdf_rigid_vel[i] = dynamics.cdf.rigid_vel[i];
+        }
+        for (int i = 0; i < DIM * DIM; ++i) {
+            o.def_grad[i] = dynamics.def_grad[i];
+            o.affine[i] = dynamics.affine[i];
+        }
+        o.cdf_signed_distance = dynamics.cdf.signed_distance;
+        o.cdf_affinity = dynamics.cdf.affinity;
+        o.init_volume = dynamics.init_volume;
+        o.init_radius = dynamics.init_radius;
+        o.mass = dynamics.mass;
+        o.lambda = model.lambda;
+        o.mu = model.mu;
+        const models::DruckerPrager dp = plasticity.value_or(models::DruckerPrager::new_(-1.0f, -1.0f));
+        o.dp_h0 = dp.h0, o.dp_h1 = dp.h1, o.dp_h2 = dp.h2, o.dp_h3 = dp.h3, o.dp_lambda = dp.lambda, o.dp_mu = dp.mu;
+        const models::DruckerPragerPlasticState st;
+        o.plastic_det = st.plastic_deformation_gradient_det;
+        o.plastic_hardening = st.plastic_hardening;
+        o.plastic_log_vol_gain = st.log_vol_gain;
+        const ParticlePhase ph = phase.value_or(ParticlePhase{0.0f, -1.0f});
+        o.phase = ph.phase;
+        o.max_stretch = ph.max_stretch;
+        o.model = model_kind;
+        return o;
+    }
+};
+
+} // namespace solver
+
+namespace pipeline {
+
+template <int DIM>
+class MpmData;
+
+// MpmPipeline (src/pipeline.rs:24-39). `new_` can fail (the reference returns Result<_, ComposerError>).
+template <int DIM>
+class MpmPipeline {
+public:
+    static MpmPipeline new_(int cuda_device = 0) {
+        MpmPipeline p;
+        check(b200mpm_pipeline_create(cuda_device, DIM, &p.h_));
+        return p;
+    }
+    MpmPipeline(MpmPipeline&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    MpmPipeline& operator=(MpmPipeline&& o) noexcept {
+        std::swap(h_, o.h_);
+        return *this;
+    }
+    MpmPipeline(const MpmPipeline&) = delete;
+    ~MpmPipeline() { b200mpm_pipeline_destroy(h_); }
+
+    // queue_step(&self, &mut MpmData, &mut KernelInvocationQueue, add_timestamps) followed by
+    // `for _ in 0..num_substeps { queue.encode(..) }` and `submit` (pipeline.rs:195-281, step.rs:122-128,169).
+    void queue_step(MpmData<DIM>& data, uint32_t num_substeps, bool add_timestamps = false);
+    void sync() { check(b200mpm_sync(h_)); }
+    void set_stream(void* cuda_stream) { check(b200mpm_pipeline_set_stream(h_, cuda_stream)); }
+    std::vector<double> timings_ms() {
+        std::vector<double> ms(B200MPM_NUM_PASSES);
+        check(b200mpm_get_timings(h_, ms.data()));
+        return ms;
+    }
+    b200mpm_pipeline* raw() { return h_; }
+
+private:
+    MpmPipeline() = default;
+    b200mpm_pipeline* h_ = nullptr;
+};
+
+// MpmData (src/pipeline.rs:84-172).
+template <int DIM>
+class MpmData {
+public:
+    // MpmData::with_select_coupling: `bodies` is what GpuBodySet::from_rapier extracts per BodyCouplingEntry.
+    static MpmData with_select_coupling(MpmPipeline<DIM>& pipeline, const solver::SimulationParamsT<DIM>& params,
+                                        const std::vector<solver::Particle<DIM>>& particles,
+                                        const std::vector<b200mpm_body>& bodies, float cell_width, uint32_t grid_capacity) {
+        std::vector<b200mpm_particle> flat;
+        flat.reserve(particles.size());
+        for (const auto& p : particles) flat.push_back(p.to_abi());
+        MpmData d;
+        const b200mpm_sim_params sp = params.to_abi();
+        check(b200mpm_data_create(pipeline.raw(), &sp, flat.data(), flat.size(), bodies.data(), bodies.size(), cell_width,
+                                  grid_capacity, &d.h_));
+        return d;
+    }
+    MpmData(MpmData&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    MpmData(const MpmData&) = delete;
+    ~MpmData() { b200mpm_data_destroy(h_); }
+
+    size_t num_particles() const { return b200mpm_data_num_particles(h_); }
+    void write_sim_params(const solver::SimulationParamsT<DIM>& p) { // ui.rs:98-103
+        const b200mpm_sim_params sp = p.to_abi();
+        check(b200mpm_write_sim_params(h_, &sp));
+    }
+    void write_body_poses(const std::vector<b200mpm_pose>& poses) { check(b200mpm_write_body_poses(h_, poses.data(), poses.size())); }
+    void write_body_vels(const std::vector<b200mpm_velocity>& vels) { check(b200mpm_write_body_vels(h_, vels.data(), vels.size())); }
+    std::vector<b200mpm_pose> read_body_poses() { // poses_staging.read (step.rs:175-176)
+        std::vector<b200mpm_pose> out(b200mpm_data_num_bodies(h_));
+        check(b200mpm_read_body_poses(h_, out.data(), out.size()));
+        return out;
+    }
+    std::vector<b200mpm_particle> read_particles() {
+        std::vector<b200mpm_particle> out(num_particles());
+        check(b200mpm_read_particles(h_, out.data()));
+        return out;
+    }
+    b200mpm_data* raw() { return h_; }
+
+private:
+    MpmData() = default;
+    b200mpm_data* h_ = nullptr;
+};
+
+template <int DIM>
+inline void MpmPipeline<DIM>::queue_step(MpmData<DIM>& data, uint32_t num_substeps, bool add_timestamps) {
+    check(b200mpm_set_timestamps(h_, add_timestamps ? 1 : 0));
+    check(b200mpm_step(h_, data.raw(), num_substeps));
+}
+
+} // namespace pipeline
+} // namespace wgsparkl

@@ -1,0 +1,115 @@
+//! Raw FFI declarations for libb200mpm.so (include/b200mpm.h). `-sys` style: no logic.
+//! NOT compiled in this repository's image (no rustc); kept as the binding a wgsparkl maintainer adds.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const B200MPM_MAX_BODIES: usize = 16;
+pub const B200MPM_NUM_PASSES: usize = 10;
+
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default)]
+pub struct b200mpm_sim_params {
+    pub gravity: [f32; 3],
+    pub dt: f32,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Debug)]
+pub struct b200mpm_particle {
+    pub position: [f32; 3],
+    pub velocity: [f32; 3],
+    pub def_grad: [f32; 9],
+    pub affine: [f32; 9],
+    pub cdf_normal: [f32; 3],
+    pub cdf_rigid_vel: [f32; 3],
+    pub cdf_signed_distance: f32,
+    pub cdf_affinity: u32,
+    pub init_volume: f32,
+    pub init_radius: f32,
+    pub mass: f32,
+    pub lambda: f32,
+    pub mu: f32,
+    pub dp_h0: f32,
+    pub dp_h1: f32,
+    pub dp_h2: f32,
+    pub dp_h3: f32,
+    pub dp_lambda: f32,
+    pub dp_mu: f32,
+    pub plastic_det: f32,
+    pub plastic_hardening: f32,
+    pub plastic_log_vol_gain: f32,
+    pub phase: f32,
+    pub max_stretch: f32,
+    pub model: u32,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Debug)]
+pub struct b200mpm_body {
+    pub shape_type: u32,
+    pub shape_a: [f32; 3],
+    pub shape_b: [f32; 3],
+    pub radius: f32,
+    pub translation: [f32; 3],
+    pub rotation: [f32; 4],
+    pub linvel: [f32; 3],
+    pub angvel: [f32; 3],
+    pub inv_mass: [f32; 3],
+    pub inv_inertia: [f32; 9],
+    pub local_com: [f32; 3],
+    pub two_ways: u32,
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default)]
+pub struct b200mpm_pose {
+    pub translation: [f32; 3],
+    pub rotation: [f32; 4],
+}
+
+#[repr(C)]
+#[derive(Copy, Clone, Debug, Default)]
+pub struct b200mpm_velocity {
+    pub linear: [f32; 3],
+    pub angular: [f32; 3],
+}
+
+pub enum b200mpm_pipeline {}
+pub enum b200mpm_data {}
+
+#[link(name = "b200mpm")]
+extern "C" {
+    pub fn b200mpm_last_error() -> *const c_char;
+    pub fn b200mpm_pipeline_create(device: c_int, dim: c_int, out: *mut *mut b200mpm_pipeline) -> c_int;
+    pub fn b200mpm_pipeline_destroy(p: *mut b200mpm_pipeline);
+    pub fn b200mpm_pipeline_set_stream(p: *mut b200mpm_pipeline, cuda_stream: *mut c_void) -> c_int;
+    pub fn b200mpm_pipeline_launch_count(p: *const b200mpm_pipeline) -> u64;
+    pub fn b200mpm_data_create(
+        p: *mut b200mpm_pipeline,
+        params: *const b200mpm_sim_params,
+        particles: *const b200mpm_particle,
+        num_particles: usize,
+        bodies: *const b200mpm_body,
+        num_bodies: usize,
+        cell_width: f32,
+        grid_capacity: u32,
+        out: *mut *mut b200mpm_data,
+    ) -> c_int;
+    pub fn b200mpm_data_destroy(d: *mut b200mpm_data);
+    pub fn b200mpm_data_num_particles(d: *const b200mpm_data) -> usize;
+    pub fn b200mpm_data_num_bodies(d: *const b200mpm_data) -> usize;
+    pub fn b200mpm_step(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, num_substeps: u32) -> c_int;
+    pub fn b200mpm_sync(p: *mut b200mpm_pipeline) -> c_int;
+    pub fn b200mpm_set_timestamps(p: *mut b200mpm_pipeline, enabled: c_int) -> c_int;
+    pub fn b200mpm_get_timings(p: *mut b200mpm_pipeline, ms: *mut f64) -> c_int;
+    pub fn b200mpm_write_sim_params(d: *mut b200mpm_data, params: *const b200mpm_sim_params) -> c_int;
+    pub fn b200mpm_write_body_poses(d: *mut b200mpm_data, poses: *const b200mpm_pose, n: usize) -> c_int;
+    pub fn b200mpm_write_body_vels(d: *mut b200mpm_data, vels: *const b200mpm_velocity, n: usize) -> c_int;
+    pub fn b200mpm_read_body_poses(d: *mut b200mpm_data, poses: *mut b200mpm_pose, n: usize) -> c_int;
+    pub fn b200mpm_read_body_vels(d: *mut b200mpm_data, vels: *mut b200mpm_velocity, n: usize) -> c_int;
+    pub fn b200mpm_read_positions(d: *mut b200mpm_data, out: *mut f32) -> c_int;
+    pub fn b200mpm_read_particles(d: *mut b200mpm_data, out: *mut b200mpm_particle) -> c_int;
+    pub fn b200mpm_data_status(d: *mut b200mpm_data, num_active_blocks: *mut u32) -> c_int;
+    pub fn b200mpm_sort_only(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;
+    pub fn b200mpm_prefix_sum_u32(p: *mut b200mpm_pipeline, data: *mut u32, len: usize) -> c_int;
+}

@@ -1,0 +1,175 @@
+"""CPU tests of the oracle (oracle/): the reference's only known-answer test (prefix sum), the restated
+un-vendored arithmetic against numpy in float64, physical invariants, and the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from wgsparkl_b200 import abi, scenes
+from wgsparkl_b200.models import ElasticCoefficients
+from wgsparkl_b200.solver import SimulationParams, make_particles
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_prefix_sum_known_answer(oracle_mod):
+    """src/grid/prefix_sum.rs:180-230: LEN 15071, ones / iota / random % 10000; expected = eval_cpu
+    (prefix_sum.rs:71-83: inclusive scan shifted right by one, v[0] = 0)."""
+    LEN = 15071
+    rng = np.random.default_rng(0)
+    for v in (np.ones(LEN, np.uint32), np.arange(LEN, dtype=np.uint32),
+              (rng.integers(0, 2**32, LEN, dtype=np.uint64) % 10_000).astype(np.uint32)):
+        ref = v.copy()
+        for i in range(LEN - 1):  # literal eval_cpu
+            ref[i + 1] += ref[i]
+        ref[1:] = ref[:-1].copy()
+        ref[0] = 0
+        assert np.array_equal(oracle_mod.prefix_sum(v), ref)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_svd_against_numpy(oracle_mod, dim):
+    rng = np.random.default_rng(1)
+    for k in range(200):
+        scale = [1.0, 0.3, 1e-3][k % 3]
+        F = (np.eye(dim) + scale * rng.uniform(-1, 1, (dim, dim))).astype(np.float32)
+        if k % 7 == 0:
+            F[:, 0] *= -1.0  # det < 0: sign carried by the last singular value
+        U, S, Vt = oracle_mod.svd(F)
+        assert np.allclose(U @ np.diag(S) @ Vt, F, atol=2e-6 * max(1.0, np.abs(F).max()))
+        assert np.allclose(U @ U.T, np.eye(dim), atol=1e-6) and np.allclose(Vt @ Vt.T, np.eye(dim), atol=1e-6)
+        assert np.linalg.det(U.astype(np.float64)) > 0 and np.linalg.det(Vt.astype(np.float64)) > 0
+        ref = np.linalg.svd(F.astype(np.float64), compute_uv=False)
+        assert np.allclose(np.sort(np.abs(S))[::-1], ref, rtol=2e-7, atol=1e-7)
+        assert np.sign(np.prod(S)) == np.sign(np.linalg.det(F.astype(np.float64)))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_kirchhoff_stress_against_float64(oracle_mod, dim):
+    """linear_elasticity.wgsl:14-41 and neo_hookean_elasticity.wgsl:11-26 restated in numpy float64."""
+    rng = np.random.default_rng(2)
+    lam, mu = 2.0e5, 3.0e5
+    for _ in range(50):
+        F = (np.eye(dim) + 0.2 * rng.uniform(-1, 1, (dim, dim))).astype(np.float32)
+        F64 = F.astype(np.float64)
+        U, S, Vt = np.linalg.svd(F64)
+        J = np.prod(S)
+        tau = 2 * mu * (U @ np.diag(S - 1) @ Vt) @ F64.T + lam * (J - 1) * J * np.eye(dim)
+        got = oracle_mod.kirchoff_stress(F, lam, mu, abi.MODEL_COROTATED)
+        assert np.allclose(got, tau, rtol=2e-4, atol=2e-4 * mu * 1e-2)
+        Jd = max(np.linalg.det(F64), 1e-10)
+        tau_nh = mu * F64 @ F64.T + (lam * np.log(Jd) - mu) * np.eye(dim)
+        got = oracle_mod.kirchoff_stress(F, lam, mu, abi.MODEL_NEO_HOOKEAN)
+        assert np.allclose(got, tau_nh, rtol=1e-5, atol=1e-5 * mu)
+
+
+def test_drucker_prager_invariants(oracle_mod):
+    """drucker_prager.wgsl:112-158: lambda == 0 disables; tensile states snap to the identity stretch;
+    compressed states are projected onto the cone (volume preserved in log space, deviator shrunk)."""
+    from wgsparkl_b200.models import DruckerPrager
+
+    dp = DruckerPrager.new(2.0e9, 0.2)
+    pl = [dp.h0, dp.h1, dp.h2, dp.h3, dp.lambda_, dp.mu]
+    F = np.diag([1.1, 1.05, 1.2]).astype(np.float32)  # expansion: trace(strain) > 0
+    Fp, st = oracle_mod.dp_project(F, pl, [1.0, 1.0, 0.0])
+    assert np.allclose(np.linalg.svd(Fp.astype(np.float64), compute_uv=False), 1.0, atol=1e-6)
+    assert st[1] > 1.0 and np.isclose(st[2], np.log(np.linalg.det(F.astype(np.float64))), atol=1e-5)
+    F = np.diag([0.9, 0.99, 0.97]).astype(np.float32)  # compression with shear
+    Fp, st = oracle_mod.dp_project(F, pl, [1.0, 1.0, 0.0])
+    e0, e1 = np.log(np.diag(F.astype(np.float64))), np.log(np.diag(Fp.astype(np.float64)))
+    assert np.isclose(e0.sum(), e1.sum(), atol=1e-5)  # return mapping is deviatoric
+    assert np.linalg.norm(e1 - e1.mean()) <= np.linalg.norm(e0 - e0.mean()) + 1e-7
+    pl0 = list(pl)
+    pl0[4] = 0.0
+    Fp, st = oracle_mod.dp_project(F, pl0, [1.0, 1.0, 0.0])
+    assert np.array_equal(Fp, F) and np.array_equal(st, np.float32([1.0, 1.0, 0.0]))
+
+
+def _body(shape_type, a=(0, 0, 0), b=(0, 0, 0), radius=0.0, t=(0, 0, 0), rot=(0, 0, 0, 1)):
+    o = np.zeros((), dtype=abi.body_dtype)
+    o["shape_type"], o["shape_a"], o["shape_b"], o["radius"], o["translation"], o["rotation"] = shape_type, a, b, radius, t, rot
+    return o
+
+
+def test_shape_projection(oracle_mod):
+    """wgparry Shape::projectPointOnBoundary contract for cuboid / ball / capsule."""
+    cub = _body(abi.SHAPE_CUBOID, a=(2, 1, 3), t=(1, 0, 0))
+    p, inside = oracle_mod.project_point(3, cub, (1.0 + 5.0, 0.5, 0.0))
+    assert not inside and np.allclose(p, (3.0, 0.5, 0.0))
+    p, inside = oracle_mod.project_point(3, cub, (1.0 + 0.5, 0.8, 0.0))  # inside: nearest face is +y
+    assert inside and np.allclose(p, (1.5, 1.0, 0.0))
+    ball = _body(abi.SHAPE_BALL, radius=2.0)
+    p, inside = oracle_mod.project_point(3, ball, (0.0, 0.5, 0.0))
+    assert inside and np.allclose(p, (0, 2, 0))
+    p, inside = oracle_mod.project_point(3, ball, (3.0, 4.0, 0.0))
+    assert not inside and np.allclose(p, (1.2, 1.6, 0.0), atol=1e-6)
+    cap = _body(abi.SHAPE_CAPSULE, a=(0, -1, 0), b=(0, 1, 0), radius=0.5)
+    p, inside = oracle_mod.project_point(3, cap, (2.0, 0.3, 0.0))
+    assert not inside and np.allclose(p, (0.5, 0.3, 0.0), atol=1e-6)
+    p, inside = oracle_mod.project_point(3, cap, (0.0, 3.0, 0.0))
+    assert not inside and np.allclose(p, (0.0, 1.5, 0.0), atol=1e-6)
+    # rotated cuboid, 2D: rotation by 90 degrees swaps the half extents
+    c2 = _body(abi.SHAPE_CUBOID, a=(2, 1, 0), rot=(0, 1, 0, 0))
+    p, inside = oracle_mod.project_point(2, c2, (0.0, 5.0))
+    assert not inside and np.allclose(p, (0.0, 2.0), atol=1e-6)
+
+
+def test_mass_and_momentum_conservation(oracle_mod):
+    """P2G weights are a partition of unity: grid mass == particle mass and, with no forces, grid momentum ==
+    particle momentum (p2g.wgsl:188-230 with APIC affine = 0)."""
+    rng = np.random.default_rng(3)
+    pos = rng.uniform(-3, 3, (500, 3)).astype(np.float32)
+    vel = rng.uniform(-1, 1, (500, 3)).astype(np.float32)
+    parts = make_particles(pos, 3, 0.25, 3.0, ElasticCoefficients.from_young_modulus(1e5, 0.3), velocity=vel)
+    sim = oracle_mod.OracleSim(3, SimulationParams([0, 0, 0], 1e-3), parts, None, 1.0, 4096)
+    for stage in (0, 1, 2, 4, 5):
+        sim.stage(stage)
+    _, nodes = sim.read_grid()
+    mvm = nodes["momentum_velocity_mass"].astype(np.float64)
+    assert np.isclose(mvm[..., 3].sum(), parts["mass"].astype(np.float64).sum(), rtol=1e-6)
+    mom = (parts["mass"][:, None] * vel).astype(np.float64).sum(0)
+    assert np.allclose(mvm[..., :3].sum((0, 1)), mom, rtol=1e-5, atol=1e-5)
+
+
+def test_free_fall_matches_gravity(oracle_mod):
+    scene = scenes.elastic_cube_3d(6, y_offset=30.0, ground=False, jitter=False)
+    sim = oracle_mod.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], 1.0, 4096)
+    sim.step(10)
+    out = sim.read_particles()
+    g, dt = scene["params"].gravity[1], scene["params"].dt
+    assert np.allclose(out["velocity"][:, 1], g * dt * 10, rtol=1e-4)
+    assert np.allclose(out["velocity"][:, [0, 2]], 0.0, atol=1e-5)
+
+
+def test_block_activation_includes_empty_neighbours(oracle_mod):
+    """touch_particle_blocks activates the particle's block and its {0,1}^3 neighbours (grid.wgsl:300-320)."""
+    parts = make_particles(np.float32([[0.4, 0.4, 0.4]]), 3, 0.25, 1.0, ElasticCoefficients.from_young_modulus(1e5, 0.3))
+    sim = oracle_mod.OracleSim(3, SimulationParams([0, 0, 0], 1e-3), parts, None, 1.0, 64)
+    sim.sort_only()
+    blocks, _ = sim.read_grid()
+    assert len(blocks) == 8 and blocks["num_particles"].sum() == 1
+    vids = {tuple(v) for v in blocks["vid"]}
+    assert vids == {(-1 + a, -1 + b, -1 + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)}
+
+
+def test_capacity_overflow_drops_blocks_silently(oracle_mod):
+    scene = scenes.elastic_cube_3d(12, y_offset=3.0)
+    sim = oracle_mod.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], 1.0, 8)
+    sim.sort_only()
+    assert sim.overflowed() and sim.num_active_blocks() == 8
+
+
+@pytest.mark.parametrize("name", ["elastic3d", "sand3d", "elastic2d", "coupled3d"])
+def test_golden_fixtures(oracle_mod, name):
+    """The oracle reproduces its committed outputs (tests/golden/make_golden.py): pins it against drift."""
+    from golden.make_golden import CASES, run_case
+
+    path = os.path.join(GOLDEN, name + ".npz")
+    ref = np.load(path)
+    got = run_case(oracle_mod, *CASES[name])
+    for key in ref.files:
+        a, b = got[key], ref[key]
+        if a.dtype.kind in "iu":
+            assert np.array_equal(a, b), key
+        else:
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-6 * max(1.0, np.abs(b).max())), key

@@ -149,7 +149,6 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
     LaunchCfg c = p->cfg();
     {
         PassTimer t(p, B200MPM_PASS_GRID_SORT);
-        launch_clear(c, d->dev);
         launch_touch(c, d->dev, d->cur);
         launch_count(c, d->dev);
         launch_scan_cells(c, d->dev);
@@ -171,7 +170,6 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
     LaunchCfg cs{p->dim, p->num_sms, side ? side : main, counter};
     const DeviceData& dev = d->dev;
     launch_begin_substep(c, dev);
-    launch_clear(c, dev);
     launch_touch(c, dev, d->cur);
     if (side) {
         cudaEventRecord(d->ev[0], main);

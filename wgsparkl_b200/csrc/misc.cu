@@ -7,12 +7,26 @@ namespace b2 {
 // ---- update_world_mass_properties (rigid_impulses.wgsl:139-150) + counter reset ----------------------
 // wgrapier Body::updateMprops: com = pose * local_com,
 // inv_inertia_world = R I^-1 R^T.
+// + reset_hmap (grid.wgsl:186-203) and the clearing of last substep's per-cell bins / scan descriptors, spread
+// over the whole grid of this kernel; the rigid-body part runs on the first warp of CTA 0.
 template <int D>
-__global__ void k_begin_substep(DeviceData d) {
+__global__ void __launch_bounds__(256) k_begin_substep(DeviceData d) {
+    {
+        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t i = tid; i < d.capacity; i += stride) d.hkeys[i] = NONE;
+        // prev_active_blocks was published by the last k_scatter (0 before the first substep: the arrays are
+        // zero-initialised at creation)
+        const uint32_t prev = min(d.counters->prev_active_blocks, d.capacity);
+        const uint32_t nbins = prev * CELLS_PER_BLOCK + 1;
+        for (uint32_t i = tid; i < nbins; i += stride) d.cell_start[i] = 0;
+        const uint32_t ntiles = (nbins + 2047u) / 2048u;
+        for (uint32_t i = tid; i < ntiles + 1; i += stride) d.scan_state[i] = 0ull;
+    }
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const uint32_t id = threadIdx.x;
     if (id == 0) {
         Counters* c = d.counters;
-        c->prev_active_blocks = c->num_active_blocks;
         c->num_active_blocks = 0;
         c->scan_ticket = 0;
         c->work_p2g = 0;
@@ -366,8 +380,8 @@ __global__ void k_gather_grid(DeviceData d, b200mpm_block_info* blocks, b200mpm_
 static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
 
 void launch_begin_substep(const LaunchCfg& c, const DeviceData& d) {
-    if (c.dim == 2) k_begin_substep<2><<<1, 32, 0, c.stream>>>(d);
-    else k_begin_substep<3><<<1, 32, 0, c.stream>>>(d);
+    if (c.dim == 2) k_begin_substep<2><<<c.num_sms * 2, 256, 0, c.stream>>>(d);
+    else k_begin_substep<3><<<c.num_sms * 2, 256, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
 void launch_integrate_bodies(const LaunchCfg& c, const DeviceData& d) {

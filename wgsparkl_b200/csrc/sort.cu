@@ -90,16 +90,22 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
     const bool leader = active && (lane == 0 || prev_key != key);
-    uint32_t slot = NONE;
-    if (leader) {
-        slot = insert_block<D>(d, bx, by, bz); // offset (0,..,0) first: its slot identifies the particle's block
-#pragma unroll
-        for (int o = 1; o < Dim<D>::NASSOC; ++o) { // blocks_associated_to_block (grid.wgsl:300-320)
-            int ox = o & 1, oy = (o >> 1) & 1, oz = (D == 3) ? (o >> 2) & 1 : 0;
-            insert_block<D>(d, bx + ox, by + oy, bz + oz);
-        }
-    }
     const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
+    // For every run leader (usually one per warp) the 2^D insertions of blocks_associated_to_block
+    // (grid.wgsl:300-320) are spread over 2^D lanes: one probe latency instead of 2^D in a row.
+    uint32_t slot = NONE;
+    for (uint32_t rem = leaders; rem; rem &= rem - 1) {
+        const int L = __ffs(rem) - 1;
+        const int lbx = __shfl_sync(0xffffffffu, bx, L), lby = __shfl_sync(0xffffffffu, by, L),
+                  lbz = __shfl_sync(0xffffffffu, bz, L);
+        uint32_t s = NONE;
+        if (lane < (uint32_t)Dim<D>::NASSOC) {
+            const int ox = lane & 1, oy = (lane >> 1) & 1, oz = (D == 3) ? (lane >> 2) & 1 : 0;
+            s = insert_block<D>(d, lbx + ox, lby + oy, lbz + oz);
+        }
+        s = __shfl_sync(0xffffffffu, s, 0); // offset (0,..,0): the slot that identifies the particle's block
+        if ((int)lane == L) slot = s;
+    }
     const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
     const int src = below ? (31 - __clz(below)) : 0;
     slot = __shfl_sync(0xffffffffu, slot, src);
@@ -109,18 +115,31 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
 // ---- update_block_particle_count (sort.wgsl:89-99), one bin per cell ---------------------------------
 __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
-    uint32_t pk = d.pkey[i];
-    uint32_t ck = NONE, r = 0;
-    if (pk != NONE) {
-        uint32_t hid = d.hvals[pk >> 6];
-        if (hid < d.capacity) {
-            ck = hid * CELLS_PER_BLOCK + (pk & 63u);
-            r = atomicAdd(d.cell_start + ck, 1u);
+    const bool active = i < d.n;
+    uint32_t ck = NONE;
+    if (active) {
+        const uint32_t pk = d.pkey[i];
+        if (pk != NONE) {
+            const uint32_t hid = d.hvals[pk >> 6];
+            if (hid < d.capacity) ck = hid * CELLS_PER_BLOCK + (pk & 63u);
         }
     }
-    d.pkey[i] = ck;
-    d.rank[i] = r;
+    // Runs of consecutive lanes in the same cell (the buffers are nearly sorted already) share one atomic.
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, ck, 1);
+    const bool leader = (lane == 0) || (prev != ck);
+    const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
+    const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
+    const int L = 31 - __clz(below);
+    const uint32_t above = (L == 31) ? 0u : (leaders >> (L + 1));
+    const int run = above ? __ffs(above) : (32 - L);
+    uint32_t base = 0;
+    if (leader && ck != NONE) base = atomicAdd(d.cell_start + ck, (uint32_t)run);
+    base = __shfl_sync(0xffffffffu, base, L);
+    if (active) {
+        d.pkey[i] = ck;
+        d.rank[i] = base + (lane - (uint32_t)L);
+    }
 }
 
 // ---- exclusive scan, single pass with decoupled look-back (replaces prefix_sum.wgsl) -----------------
@@ -132,6 +151,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_prefix;
     const uint32_t len = counters ? (min(counters->num_active_blocks, capacity) * CELLS_PER_BLOCK + 1) : len_value;
+    // The grid is sized for the worst case (capacity); CTAs beyond the live tiles leave without a ticket, so
+    // the tickets handed out are exactly 0 .. ntiles-1 and the same-address atomic stays cheap.
+    if (blockIdx.x * SCAN_TILE >= len) return;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -162,25 +184,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
         if (w < warp) warp_off += x;
         total += x;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) { // decoupled look-back, 32 predecessors per round
         const uint64_t FLAG_A = 1ull << 62, FLAG_P = 2ull << 62;
         uint32_t running = 0;
         if (tile == 0) {
-            atomicExch((unsigned long long*)(state + 0), FLAG_P | (uint64_t)total);
+            if (lane == 0) atomicExch((unsigned long long*)(state + 0), FLAG_P | (uint64_t)total);
         } else {
-            atomicExch((unsigned long long*)(state + tile), FLAG_A | (uint64_t)total);
-            int j = (int)tile - 1;
+            if (lane == 0) atomicExch((unsigned long long*)(state + tile), FLAG_A | (uint64_t)total);
+            int j0 = (int)tile - 1; // lane l looks at tile j0 - l
             while (true) {
-                uint64_t s = *((volatile uint64_t*)(state + j));
+                const int j = j0 - (int)lane;
+                uint64_t s = (j >= 0) ? *((volatile uint64_t*)(state + j)) : FLAG_P; // virtual tile -1: prefix 0
                 uint64_t flag = s >> 62;
-                if (flag == 0) continue;
-                running += (uint32_t)s;
-                if (flag == 2) break;
-                --j;
+                // wait until every inspected tile has published something
+                if (__any_sync(0xffffffffu, flag == 0)) continue;
+                const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2);
+                const int stop = pmask ? (__ffs(pmask) - 1) : 32; // nearest tile with an inclusive prefix
+                uint32_t v = ((int)lane <= stop) ? (uint32_t)s : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                running += v;
+                if (pmask) break;
+                j0 -= 32;
             }
-            atomicExch((unsigned long long*)(state + tile), FLAG_P | (uint64_t)(running + total));
+            if (lane == 0) atomicExch((unsigned long long*)(state + tile), FLAG_P | (uint64_t)(running + total));
         }
-        s_prefix = running;
+        if (lane == 0) s_prefix = running;
     }
     __syncthreads();
     uint32_t excl = s_prefix + warp_off + (inc - sum);
@@ -227,6 +256,7 @@ __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_block_prepare(DeviceData d)
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) d.counters->prev_active_blocks = min(d.counters->num_active_blocks, d.capacity); // for the next clear
     if (d.has_bodies) {
         // CPIC work list: a block runs the collider-aware paths iff one of the 2^D blocks its tile overlaps
         // has a node near / inside a collider. (i doubles as a block index here.)
