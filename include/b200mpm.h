@@ -223,13 +223,52 @@ int b200mpm_sort_only(b200mpm_pipeline* p, b200mpm_data* d);
  * ("as if a 0 was prepended", prefix_sum.rs:7-8) computed on the device. */
 int b200mpm_prefix_sum_u32(b200mpm_pipeline* p, uint32_t* data, size_t len);
 
-/* ---- multi-GPU slab sharding (new) ----------------------------------- */
+/* ---- multi-GPU slab sharding (new: the reference is single-device) ------------------------
+ *
+ * One process per GPU; rank r owns the particles whose block x-index lies in [x_lo, x_hi). The library packs
+ * and unpacks DEVICE buffers; the caller moves them between ranks (NCCL send/recv and all-reduce — through
+ * torch.distributed in wgsparkl_b200/sharded.py, directly in a Rust host). Per substep:
+ *
+ *   b200mpm_shard_emigrate   -> exchange records with the -x / +x neighbours -> b200mpm_shard_immigrate
+ *   b200mpm_shard_step_begin    (sort ... P2G on the rank's own particles)
+ *   b200mpm_shard_halo_pack  -> exchange the shared block columns             -> b200mpm_shard_halo_add
+ *   b200mpm_shard_impulses(read) -> all-reduce(sum, int32[16*6])              -> b200mpm_shard_impulses(write)
+ *   b200mpm_shard_step_end      (G2P + particle update, body integration)
+ */
+#define B200MPM_PARTICLE_RECORD_BYTES 128u /* one migrating particle */
+#define B200MPM_HALO_BLOCK_BYTES 1040u /* one halo block: virtual id + 64 x (momentum xyz, mass) */
+#define B200MPM_SHARD_HEADER_BYTES 16u
 
-/* Attach this rank's data to a slab decomposition along block-x. The data owns particles whose
- * block x-index lies in [x_lo, x_hi). Exchange buffers are plain host-visible staging areas:
- * the caller (torch.distributed / NCCL in the Python host, NCCL in a Rust host) moves them
- * between ranks. See INTEGRATION.md. */
-int b200mpm_slab_configure(b200mpm_data* d, int rank, int world, int32_t x_lo, int32_t x_hi);
+/* b200mpm_data_create with room for `particle_capacity` >= num_particles particles (immigrants) and
+ * caller-chosen particle ids (NULL = 0..n-1; a sharded run passes global ids so that migrated particles stay
+ * identifiable). */
+int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params, const b200mpm_particle* particles,
+                           size_t num_particles, const uint32_t* particle_ids, size_t particle_capacity,
+                           const b200mpm_body* bodies, size_t num_bodies, float cell_width, uint32_t grid_capacity,
+                           b200mpm_data** out);
+int b200mpm_slab_configure(b200mpm_data* d, int32_t x_lo, int32_t x_hi);
+/* Particles currently held by this data (== num_particles unless sharded). Synchronises. */
+int b200mpm_data_num_live(b200mpm_data* d, size_t* num_live);
+/* Exchange buffers are DEVICE memory: a 16-byte header (uint32 record count + padding, written and read on the
+ * device: no host round trip) followed by `cap` records. Fixed-size buffers travel between the ranks.
+ *
+ * Packs the particles that left the slab into the -x / +x buffers and flags them dead (they are dropped at the
+ * end of the substep). Buffer size: 16 + cap_records * B200MPM_PARTICLE_RECORD_BYTES. Asynchronous. */
+int b200mpm_shard_emigrate(b200mpm_pipeline* p, b200mpm_data* d, void* dev_left, void* dev_right, uint32_t cap_records);
+/* Appends the records of a received migration buffer to the live particles. Asynchronous. */
+int b200mpm_shard_immigrate(b200mpm_pipeline* p, b200mpm_data* d, const void* dev_buffer, uint32_t cap_records);
+int b200mpm_shard_step_begin(b200mpm_pipeline* p, b200mpm_data* d);
+/* Packs the node momenta of the shared block columns (x == x_lo -> dev_left, x == x_hi -> dev_right).
+ * Buffer size: 16 + cap_blocks * B200MPM_HALO_BLOCK_BYTES. Asynchronous. */
+int b200mpm_shard_halo_pack(b200mpm_pipeline* p, b200mpm_data* d, void* dev_left, void* dev_right, uint32_t cap_blocks);
+/* Adds a received halo buffer to the blocks this rank also holds. Asynchronous. */
+int b200mpm_shard_halo_add(b200mpm_pipeline* p, b200mpm_data* d, const void* dev_buffer, uint32_t cap_blocks);
+/* write == 0: body impulses -> dev_buf (int32[16*6]); write != 0: dev_buf -> body impulses. */
+int b200mpm_shard_impulses(b200mpm_pipeline* p, b200mpm_data* d, int32_t* dev_buf, int write);
+int b200mpm_shard_step_end(b200mpm_pipeline* p, b200mpm_data* d);
+/* Live particles in device order with their ids (no un-permutation). */
+int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uint32_t* ids, size_t capacity,
+                                     size_t* count);
 
 #ifdef __cplusplus
 }

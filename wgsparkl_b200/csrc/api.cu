@@ -67,8 +67,10 @@ struct b200mpm_data {
     // One captured CUDA graph per ping-pong parity: the substep is recorded once and replayed, like the
     // reference's KernelInvocationQueue (src_testbed/step.rs:122-128). Independent kernels sit on parallel
     // branches of the graph.
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-    uint64_t graph_launches[2] = {0, 0};
+    cudaGraphExec_t graph_exec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}; // [parity][phase]
+    uint64_t graph_launches[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    uint32_t n_live_host = 0; // host mirror of counters->n_live (sharded runs track it)
+    bool sharded = false;
     cudaStream_t side = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -165,10 +167,21 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
 
 // Enqueues one substep. With `side` the independent kernels are forked onto a second stream:
 //   touch -> { block_prepare  ||  count -> scan } -> scatter -> { g2p_cdf -> p2g(cpic)  ||  p2g } -> g2p
-void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cudaStream_t side, uint64_t* counter) {
+// phase: PHASE_ALL = the whole substep; PHASE_BEGIN = up to and including P2G; PHASE_END = from G2P on
+// (sharded runs exchange the node halo and the body impulses between the two).
+enum { PHASE_ALL = 0, PHASE_BEGIN = 1, PHASE_END = 2 };
+
+void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cudaStream_t side, uint64_t* counter,
+                     int phase) {
     LaunchCfg c{p->dim, p->num_sms, main, counter};
     LaunchCfg cs{p->dim, p->num_sms, side ? side : main, counter};
     const DeviceData& dev = d->dev;
+    if (phase == PHASE_END) {
+        launch_g2p_update(c, dev, d->cur);
+        launch_integrate_bodies(c, dev);
+        launch_drop_dead_tail(c, dev);
+        return;
+    }
     launch_begin_substep(c, dev);
     launch_touch(c, dev, d->cur);
     if (side) {
@@ -190,14 +203,15 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
     if (side && dev.has_bodies) cudaEventRecord(d->ev[3], side);
     launch_p2g(c, dev, d->cur);
     if (side && dev.has_bodies) cudaStreamWaitEvent(main, d->ev[3], 0);
+    if (phase == PHASE_BEGIN) return;
     launch_g2p_update(c, dev, d->cur);
     launch_integrate_bodies(c, dev);
 }
 
 // Captures the substep for the current parity into a graph (once), then replays it.
-bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d) {
+bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
     const int par = d->cur;
-    if (!d->graph_exec[par]) {
+    if (!d->graph_exec[par][phase]) {
         if (!d->side) {
             if (cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking) != cudaSuccess) return false;
             for (auto& e : d->ev)
@@ -209,29 +223,41 @@ bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d) {
             cudaGetLastError();
             return false;
         }
-        enqueue_substep(p, d, p->stream, d->side, &count);
+        enqueue_substep(p, d, p->stream, d->side, &count, phase);
         if (cudaStreamEndCapture(p->stream, &graph) != cudaSuccess || !graph) {
             cudaGetLastError();
             return false;
         }
-        cudaError_t e = cudaGraphInstantiate(&d->graph_exec[par], graph, 0);
+        cudaError_t e = cudaGraphInstantiate(&d->graph_exec[par][phase], graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            d->graph_exec[par] = nullptr;
+            d->graph_exec[par][phase] = nullptr;
             return false;
         }
-        d->graph_launches[par] = count;
+        d->graph_launches[par][phase] = count;
     }
-    if (cudaGraphLaunch(d->graph_exec[par], p->stream) != cudaSuccess) return false;
-    p->launches += d->graph_launches[par];
-    d->cur ^= 1;
-    d->sorted_indirect = false;
+    if (cudaGraphLaunch(d->graph_exec[par][phase], p->stream) != cudaSuccess) return false;
+    p->launches += d->graph_launches[par][phase];
+    if (phase != PHASE_BEGIN) {
+        d->cur ^= 1;
+        d->sorted_indirect = false;
+    }
     return true;
 }
 
+// One phase of a substep without timestamps: graph replay, or plain launches when graphs are disabled.
+void run_phase(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
+    if (p->use_graphs && run_substep_graph(p, d, phase)) return;
+    enqueue_substep(p, d, p->stream, nullptr, &p->launches, phase);
+    if (phase != PHASE_BEGIN) {
+        d->cur ^= 1;
+        d->sorted_indirect = false;
+    }
+}
+
 void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
-    if (!p->timestamps && p->use_graphs && run_substep_graph(p, d)) return;
+    if (!p->timestamps && p->use_graphs && run_substep_graph(p, d, PHASE_ALL)) return;
     LaunchCfg c = p->cfg();
     {
         PassTimer t(p, B200MPM_PASS_UPDATE_RIGID_PARTICLES);
@@ -325,7 +351,17 @@ uint64_t b200mpm_pipeline_launch_count(const b200mpm_pipeline* p) { return p ? p
 int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, const b200mpm_particle* particles,
                         size_t num_particles, const b200mpm_body* bodies, size_t num_bodies, float cell_width,
                         uint32_t grid_capacity, b200mpm_data** out) {
+    return b200mpm_data_create_ex(p, params, particles, num_particles, nullptr, num_particles, bodies, num_bodies, cell_width,
+                                  grid_capacity, out);
+}
+
+int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params, const b200mpm_particle* particles,
+                           size_t num_particles, const uint32_t* particle_ids, size_t particle_capacity,
+                           const b200mpm_body* bodies, size_t num_bodies, float cell_width, uint32_t grid_capacity,
+                           b200mpm_data** out) {
     if (!p || !params || !out) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (particle_capacity < num_particles) return fail(B200MPM_ERR_INVALID_ARGUMENT, "particle_capacity < num_particles");
+    if (particle_capacity >= (1ull << 31)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "too many particles");
     *out = nullptr;
     if (num_particles && !particles) return fail(B200MPM_ERR_INVALID_ARGUMENT, "particles is null");
     if (num_bodies && !bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "bodies is null");
@@ -343,14 +379,16 @@ int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, c
     uint32_t capacity = 1;
     while (capacity < grid_capacity) capacity <<= 1; // grid.rs:283
     const int D = p->dim;
-    const uint32_t n = (uint32_t)num_particles;
+    const uint32_t n = (uint32_t)num_particles; // particles uploaded now
+    const uint32_t ncap = (uint32_t)particle_capacity; // room for immigrants (sharded runs)
 
     auto* d = new b200mpm_data();
     d->pipe = p;
     d->num_bodies = (uint32_t)num_bodies;
     DeviceData& dev = d->dev;
-    dev.n = n;
+    dev.n = ncap;
     dev.capacity = capacity;
+    d->n_live_host = n;
     dev.has_bodies = num_bodies > 0;
 
     // ---- material table (dedup of the per-particle model buffers) + SoA staging on the host
@@ -408,7 +446,7 @@ int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, c
             float f;
         } mb, ob;
         mb.u = mid;
-        ob.u = i;
+        ob.u = particle_ids ? particle_ids[i] : i;
         pos4[i] = make_float4(q.position[0], q.position[1], D == 3 ? q.position[2] : 0.0f, mb.f);
         vel4[i] = make_float4(q.velocity[0], q.velocity[1], D == 3 ? q.velocity[2] : 0.0f, ob.f);
         Fa[i] = make_float4(q.def_grad[0], q.def_grad[1], q.def_grad[2], q.def_grad[3]);
@@ -449,29 +487,29 @@ int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, c
     } while (0)
 
     for (int s = 0; s < 2; ++s) {
-        ALLOC(dev.pos4[s], n);
-        ALLOC(dev.vel4[s], n);
-        ALLOC(dev.Fa[s], n);
-        ALLOC(dev.Ca[s], n);
+        ALLOC(dev.pos4[s], ncap);
+        ALLOC(dev.vel4[s], ncap);
+        ALLOC(dev.Fa[s], ncap);
+        ALLOC(dev.Ca[s], ncap);
         if (D == 3) {
-            ALLOC(dev.Fb[s], n);
-            ALLOC(dev.Fc[s], n);
-            ALLOC(dev.Cb[s], n);
-            ALLOC(dev.Cc[s], n);
+            ALLOC(dev.Fb[s], ncap);
+            ALLOC(dev.Fc[s], ncap);
+            ALLOC(dev.Cb[s], ncap);
+            ALLOC(dev.Cc[s], ncap);
         }
-        if (has_plastic) ALLOC(dev.plastic[s], n);
-        if (dev.has_bodies) ALLOC(dev.cdf_aff[s], n);
+        if (has_plastic) ALLOC(dev.plastic[s], ncap);
+        if (dev.has_bodies) ALLOC(dev.cdf_aff[s], ncap);
     }
     if (dev.has_bodies) {
-        ALLOC(dev.cdf_nd, n);
-        ALLOC(dev.cdf_rv, n);
+        ALLOC(dev.cdf_nd, ncap);
+        ALLOC(dev.cdf_rv, ncap);
     }
     Material* dmat = nullptr;
     ALLOC(dmat, materials.size());
     dev.materials = dmat;
-    ALLOC(dev.pkey, n);
-    ALLOC(dev.rank, n);
-    ALLOC(dev.sorted_ids, n);
+    ALLOC(dev.pkey, ncap);
+    ALLOC(dev.rank, ncap);
+    ALLOC(dev.sorted_ids, ncap);
     ALLOC(dev.hkeys, capacity);
     ALLOC(dev.hvals, capacity);
     ALLOC(dev.block_vid, capacity);
@@ -547,7 +585,13 @@ int b200mpm_data_create(b200mpm_pipeline* p, const b200mpm_sim_params* params, c
     hs[0].dt = params->dt;
     hs[0].cell_width = cell_width;
     hs[0].num_bodies = (uint32_t)num_bodies;
+    hs[0].slab_lo = -2147483647 - 1;
+    hs[0].slab_hi = 2147483647;
     UPLOAD(dev.sim, hs);
+    std::vector<Counters> hc(1);
+    std::memset(hc.data(), 0, sizeof(Counters));
+    hc[0].n_live = n;
+    UPLOAD(dev.counters, hc);
 #undef ALLOC
 #undef UPLOAD
     cudaError_t e = cudaStreamSynchronize(p->stream); // host vectors go out of scope
@@ -563,8 +607,9 @@ void b200mpm_data_destroy(b200mpm_data* d) {
     if (!d) return;
     cudaSetDevice(d->pipe->device);
     cudaStreamSynchronize(d->pipe->stream);
-    for (auto& g : d->graph_exec)
-        if (g) cudaGraphExecDestroy(g);
+    for (auto& gp : d->graph_exec)
+        for (auto& g : gp)
+            if (g) cudaGraphExecDestroy(g);
     for (auto& e : d->ev)
         if (e) cudaEventDestroy(e);
     if (d->side) cudaStreamDestroy(d->side);
@@ -574,7 +619,7 @@ void b200mpm_data_destroy(b200mpm_data* d) {
     delete d;
 }
 
-size_t b200mpm_data_num_particles(const b200mpm_data* d) { return d ? d->dev.n : 0; }
+size_t b200mpm_data_num_particles(const b200mpm_data* d) { return d ? d->n_live_host : 0; }
 size_t b200mpm_data_num_bodies(const b200mpm_data* d) { return d ? d->num_bodies : 0; }
 
 int b200mpm_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps) {
@@ -709,6 +754,7 @@ int b200mpm_read_positions(b200mpm_data* d, float* out) {
     size_t bytes = (size_t)d->dev.n * sizeof(float4);
     int r = ensure_staging(d, bytes);
     if (r) return r;
+    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_particles_unordered");
     launch_gather_positions(p->cfg(), d->dev, d->cur, (float4*)d->staging);
     CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
@@ -723,7 +769,8 @@ int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out) {
     size_t bytes = (size_t)d->dev.n * sizeof(b200mpm_particle);
     int r = ensure_staging(d, bytes);
     if (r) return r;
-    launch_gather_particles(p->cfg(), d->dev, d->cur, (b200mpm_particle*)d->staging);
+    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_particles_unordered");
+    launch_gather_particles(p->cfg(), d->dev, d->cur, (b200mpm_particle*)d->staging, nullptr);
     CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
     return B200MPM_OK;
@@ -737,7 +784,9 @@ int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks) {
     CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
     if (num_active_blocks) *num_active_blocks = std::min(c.num_active_blocks, d->dev.capacity);
-    if (c.overflow) return fail(B200MPM_ERR_GRID_OVERFLOW, "grid block capacity exceeded: blocks were dropped");
+    if (c.overflow == 1) return fail(B200MPM_ERR_GRID_OVERFLOW, "grid block capacity exceeded: blocks were dropped");
+    if (c.overflow == 2) return fail(B200MPM_ERR_GRID_OVERFLOW, "a shard exchange buffer was too small");
+    if (c.overflow == 3) return fail(B200MPM_ERR_GRID_OVERFLOW, "particle_capacity exceeded by immigrants: particles were lost");
     return B200MPM_OK;
 }
 
@@ -808,13 +857,111 @@ int b200mpm_prefix_sum_u32(b200mpm_pipeline* p, uint32_t* data, size_t len) {
     return rc;
 }
 
-int b200mpm_slab_configure(b200mpm_data* d, int rank, int world, int32_t x_lo, int32_t x_hi) {
-    (void)d;
-    (void)rank;
-    (void)world;
-    (void)x_lo;
-    (void)x_hi;
-    return fail(B200MPM_ERR_INVALID_ARGUMENT, "slab sharding is not implemented yet");
+int b200mpm_slab_configure(b200mpm_data* d, int32_t x_lo, int32_t x_hi) {
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (x_lo >= x_hi) return fail(B200MPM_ERR_INVALID_ARGUMENT, "empty slab");
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    int r = ensure_pinned(d, 4096);
+    if (r) return r;
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    int* h = (int*)d->pinned;
+    h[0] = x_lo;
+    h[1] = x_hi;
+    CU_TRY(cudaMemcpyAsync(&d->dev.sim->slab_lo, h, 2 * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    d->sharded = true;
+    return B200MPM_OK;
+}
+
+int b200mpm_data_num_live(b200mpm_data* d, size_t* num_live) {
+    if (!d || !num_live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    b200mpm_pipeline* p = d->pipe;
+    CU_TRY(cudaSetDevice(p->device));
+    Counters c;
+    CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    d->n_live_host = c.n_live;
+    *num_live = c.n_live;
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_emigrate(b200mpm_pipeline* p, b200mpm_data* d, void* dev_left, void* dev_right, uint32_t cap_records) {
+    if (!p || !d || d->pipe != p || !dev_left || !dev_right) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    launch_emigrate(p->cfg(), d->dev, d->cur, dev_left, dev_right, cap_records);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_immigrate(b200mpm_pipeline* p, b200mpm_data* d, const void* dev_buffer, uint32_t cap_records) {
+    if (!p || !d || d->pipe != p || !dev_buffer) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    launch_immigrate(p->cfg(), d->dev, d->cur, dev_buffer, cap_records);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_step_begin(b200mpm_pipeline* p, b200mpm_data* d) {
+    if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
+    CU_TRY(cudaSetDevice(p->device));
+    run_phase(p, d, PHASE_BEGIN);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_step_end(b200mpm_pipeline* p, b200mpm_data* d) {
+    if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
+    CU_TRY(cudaSetDevice(p->device));
+    run_phase(p, d, PHASE_END);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_halo_pack(b200mpm_pipeline* p, b200mpm_data* d, void* dev_left, void* dev_right, uint32_t cap_blocks) {
+    if (!p || !d || d->pipe != p || !dev_left || !dev_right) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    launch_halo_pack(p->cfg(), d->dev, dev_left, dev_right, cap_blocks);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_halo_add(b200mpm_pipeline* p, b200mpm_data* d, const void* dev_buffer, uint32_t cap_blocks) {
+    if (!p || !d || d->pipe != p || !dev_buffer) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    launch_halo_add(p->cfg(), d->dev, dev_buffer, cap_blocks);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_impulses(b200mpm_pipeline* p, b200mpm_data* d, int32_t* dev_buf, int write) {
+    if (!p || !d || d->pipe != p || !dev_buf) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    launch_impulses_io(p->cfg(), d->dev, dev_buf, write);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uint32_t* ids, size_t capacity,
+                                     size_t* count) {
+    if (!d || !count) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    size_t live = 0;
+    int r = b200mpm_data_num_live(d, &live);
+    if (r) return r;
+    *count = live;
+    if (live == 0) return B200MPM_OK;
+    if (!out || !ids || capacity < live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "output too small");
+    b200mpm_pipeline* p = d->pipe;
+    size_t pbytes = live * sizeof(b200mpm_particle);
+    size_t poff = ((size_t)d->dev.n * sizeof(b200mpm_particle) + 255) & ~(size_t)255;
+    r = ensure_staging(d, poff + (size_t)d->dev.n * sizeof(uint32_t));
+    if (r) return r;
+    uint32_t* dids = (uint32_t*)((char*)d->staging + poff);
+    launch_gather_particles(p->cfg(), d->dev, d->cur, (b200mpm_particle*)d->staging, dids);
+    CU_TRY(cudaMemcpyAsync(out, d->staging, pbytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaMemcpyAsync(ids, dids, live * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
 }
 
 } // extern "C"

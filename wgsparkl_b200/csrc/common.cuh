@@ -12,6 +12,7 @@ namespace b2 {
 constexpr uint32_t NONE = 0xffffffffu; // grid.wgsl:80
 constexpr int CELLS_PER_BLOCK = 64; // grid.wgsl:43
 constexpr uint32_t MAT_ID_MASK = 0x0fffffffu;
+constexpr uint32_t FLAG_DEAD = 0x40000000u; // the particle emigrated to a neighbour slab; dropped at the end of the substep
 constexpr uint32_t FLAG_PHASE_BROKEN = 0x80000000u; // phases[i].phase was set to 0 (particle_update.wgsl:106,112)
 
 template <int D>
@@ -78,6 +79,7 @@ struct SimState {
     float dt;
     float cell_width;
     uint32_t num_bodies;
+    int slab_lo, slab_hi; // this rank owns particles whose block x-index is in [slab_lo, slab_hi) (sharded runs)
 };
 
 // ---- device-resident counters --------------------------------------------------------------
@@ -91,7 +93,10 @@ struct Counters {
     uint32_t work_g2p;
     uint32_t work_cdf;
     uint32_t num_cpic_blocks; // blocks (with particles) whose tile holds a collider this substep
-    uint32_t dropped_particles; // particles whose block was dropped (overflow)
+    uint32_t dropped_particles; // particles whose block was dropped (overflow) or that left the slab
+    uint32_t n_live; // particles currently held (== n unless the data is a slab of a sharded run)
+    uint32_t send_count[2]; // emigrants packed for the -x / +x neighbour (sharded runs)
+    uint32_t halo_count[2]; // blocks packed for the -x / +x neighbour (sharded runs)
 };
 
 // ---- all device pointers of one MpmData --------------------------------------------------

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 6) k_g2p(DeviceData d, int cur) {
     const uint32_t dropped = d.counters->dropped_particles;
     if (dropped) {
         const uint32_t total = d.cell_start[nb * CELLS_PER_BLOCK];
-        for (uint32_t k = total + blockIdx.x * blockDim.x + t; k < total + dropped && k < d.n; k += gridDim.x * blockDim.x) {
+        for (uint32_t k = total + blockIdx.x * blockDim.x + t; k < total + dropped && k < d.counters->n_live; k += gridDim.x * blockDim.x) {
             const uint32_t id = d.sorted_ids[k];
             d.pos4[nxt][k] = d.pos4[cur][id];
             d.vel4[nxt][k] = d.vel4[cur][id];

@@ -38,7 +38,15 @@ uint32_t scan_num_tiles(uint64_t len);
 
 // Readback helpers (device -> staging in caller order).
 void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out);
-void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out);
+void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out, uint32_t* ids);
+
+// Slab sharding (shard.cu)
+void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap);
+void launch_immigrate(const LaunchCfg& c, const DeviceData& d, int cur, const void* in, uint32_t cap);
+void launch_drop_dead_tail(const LaunchCfg& c, const DeviceData& d);
+void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap);
+void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap);
+void launch_impulses_io(const LaunchCfg& c, const DeviceData& d, int* buf, int write);
 void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_info* blocks, b200mpm_node* nodes,
                         uint32_t max_blocks);
 void launch_gather_sorted_ids(const LaunchCfg& c, const DeviceData& d, int cur, int indirect, uint32_t* out);

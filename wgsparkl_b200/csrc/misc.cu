@@ -262,16 +262,16 @@ __global__ void k_read_poses(DeviceData d, b200mpm_pose* poses, b200mpm_velocity
 // ---- particle / grid readback in the caller's layout ---------------------------------------------------------
 __global__ void k_gather_positions(DeviceData d, int cur, float4* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
+    if (i >= d.counters->n_live) return;
     float4 p = d.pos4[cur][i];
     uint32_t orig = __float_as_uint(d.vel4[cur][i].w);
     out[orig] = make_float4(p.x, p.y, p.z, 0.0f);
 }
 
 template <int D>
-__global__ void k_gather_particles(DeviceData d, int cur, b200mpm_particle* out) {
+__global__ void k_gather_particles(DeviceData d, int cur, b200mpm_particle* out, uint32_t* ids) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.n) return;
+    if (i >= d.counters->n_live) return;
     float4 p = d.pos4[cur][i];
     float4 v = d.vel4[cur][i];
     uint32_t orig = __float_as_uint(v.w);
@@ -324,12 +324,17 @@ __global__ void k_gather_particles(DeviceData d, int cur, b200mpm_particle* out)
     o.phase = (mbits & FLAG_PHASE_BROKEN) ? 0.0f : m.phase;
     o.max_stretch = m.max_stretch;
     o.model = m.model;
-    out[orig] = o;
+    if (ids) { // device order + ids (sharded runs)
+        out[i] = o;
+        ids[i] = (mbits & FLAG_DEAD) ? NONE : orig;
+    } else {
+        out[orig] = o;
+    }
 }
 
 __global__ void k_gather_sorted_ids(DeviceData d, int cur, int indirect, uint32_t* out) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= d.n) return;
+    if (k >= d.counters->n_live) return;
     // After a full substep the particle buffers ARE in sorted order; after a sort-only pass the
     // order is given by sorted_ids.
     uint32_t id = indirect ? d.sorted_ids[k] : k;
@@ -395,10 +400,10 @@ void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, f
     k_gather_positions<<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, out);
     ++*c.launch_counter;
 }
-void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out) {
+void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out, uint32_t* ids) {
     if (d.n == 0) return;
-    if (c.dim == 2) k_gather_particles<2><<<div_up(d.n, 128), 128, 0, c.stream>>>(d, cur, out);
-    else k_gather_particles<3><<<div_up(d.n, 128), 128, 0, c.stream>>>(d, cur, out);
+    if (c.dim == 2) k_gather_particles<2><<<div_up(d.n, 128), 128, 0, c.stream>>>(d, cur, out, ids);
+    else k_gather_particles<3><<<div_up(d.n, 128), 128, 0, c.stream>>>(d, cur, out, ids);
     ++*c.launch_counter;
 }
 void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_info* blocks, b200mpm_node* nodes,

@@ -1,0 +1,224 @@
+// Multi-GPU slab sharding (no counterpart in the reference, which is single-device).
+//
+// The domain is cut into slabs of grid-block columns along x; rank r owns the particles whose block
+// x-index lies in [slab_lo, slab_hi). Per substep:
+//   1. migration   — particles whose block left the slab are packed for the -x / +x neighbour and flagged
+//                    dead; immigrants are appended to the live range;
+//   2. P2G         — on the rank's own particles only; the block column `slab_hi` (written by the last owned
+//                    column, owned by the +x neighbour) and the column `slab_lo` hold PARTIAL node sums;
+//   3. node halo   — both neighbours exchange their partial sums of the shared column (keyed by the block's
+//                    virtual id) and add them: a + b on one side, b + a on the other, bitwise the same;
+//   4. impulses    — the 16 x 6 fixed-point body impulses are summed over ranks (exact, integers);
+//   5. G2P + update, body integration (replicated, deterministic).
+// The kernels here only pack / unpack device buffers; the transport (NCCL send/recv, all-reduce) belongs to the
+// host (wgsparkl_b200/sharded.py with torch.distributed; a Rust host would call NCCL directly).
+#include "launch.h"
+
+namespace b2 {
+
+// One migrating particle: 8 x 16 bytes.
+struct __align__(16) ParticleRecord {
+    float4 pos4, vel4, Fa, Fb, Ca, Cb;
+    float Fc, Cc;
+    uint32_t cdf_aff, pad;
+    float4 plastic;
+};
+static_assert(sizeof(ParticleRecord) == 128, "ParticleRecord must be 128 bytes");
+
+// One halo block: virtual id + 64 nodes (momentum xyz + mass).
+struct __align__(16) HaloBlock {
+    int4 vid;
+    float4 node[CELLS_PER_BLOCK];
+};
+static_assert(sizeof(HaloBlock) == 16 + 1024, "HaloBlock must be 1040 bytes");
+
+// Every exchange buffer starts with a 16-byte header holding the record count, so that neither side needs a
+// host round trip: fixed-size buffers travel, the receiver reads the count on the device.
+struct __align__(16) ShardHeader {
+    uint32_t count, pad0, pad1, pad2;
+};
+template <class T>
+__device__ __forceinline__ T* shard_records(void* buf) { return (T*)((char*)buf + sizeof(ShardHeader)); }
+template <class T>
+__device__ __forceinline__ const T* shard_records(const void* buf) { return (const T*)((const char*)buf + sizeof(ShardHeader)); }
+
+template <int D>
+__global__ void __launch_bounds__(256) k_emigrate(DeviceData d, int cur, void* left_buf, void* right_buf, uint32_t cap) {
+    ParticleRecord* left = shard_records<ParticleRecord>(left_buf);
+    ParticleRecord* right = shard_records<ParticleRecord>(right_buf);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.counters->n_live) return;
+    float4 p = d.pos4[cur][i];
+    if (__float_as_uint(p.w) & FLAG_DEAD) return;
+    const int bx = assoc_cell(p.x, d.sim->cell_width) >> Dim<D>::LOG_BLOCK;
+    const int dir = (bx < d.sim->slab_lo) ? 0 : (bx >= d.sim->slab_hi) ? 1 : -1;
+    if (dir < 0) return;
+    const uint32_t slot = atomicAdd(&d.counters->send_count[dir], 1u);
+    if (slot >= cap) { // buffer too small: the particle stays (and is retried next substep); reported via status
+        d.counters->overflow = 2u;
+        return;
+    }
+    ParticleRecord r;
+    r.pos4 = p;
+    r.vel4 = d.vel4[cur][i];
+    r.Fa = d.Fa[cur][i];
+    r.Ca = d.Ca[cur][i];
+    r.Fb = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.Cb = r.Fb;
+    r.Fc = r.Cc = 0.0f;
+    if (D == 3) {
+        r.Fb = d.Fb[cur][i];
+        r.Cb = d.Cb[cur][i];
+        r.Fc = d.Fc[cur][i];
+        r.Cc = d.Cc[cur][i];
+    }
+    r.cdf_aff = d.has_bodies ? d.cdf_aff[cur][i] : 0u;
+    r.pad = 0u;
+    r.plastic = d.has_plastic ? d.plastic[cur][i] : make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+    (dir == 0 ? left : right)[slot] = r;
+    d.pos4[cur][i].w = __uint_as_float(__float_as_uint(p.w) | FLAG_DEAD);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_immigrate(DeviceData d, int cur, const void* buf, uint32_t cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = min(((const ShardHeader*)buf)->count, cap);
+    if (i >= count) return;
+    const uint32_t dst = d.counters->n_live + i; // n_live is bumped by k_immigrate_commit afterwards
+    if (dst >= d.n) {
+        d.counters->overflow = 3u; // particle_capacity exceeded: the immigrant is lost
+        return;
+    }
+    const ParticleRecord r = shard_records<ParticleRecord>(buf)[i];
+    d.pos4[cur][dst] = r.pos4;
+    d.vel4[cur][dst] = r.vel4;
+    d.Fa[cur][dst] = r.Fa;
+    d.Ca[cur][dst] = r.Ca;
+    if (D == 3) {
+        d.Fb[cur][dst] = r.Fb;
+        d.Cb[cur][dst] = r.Cb;
+        d.Fc[cur][dst] = r.Fc;
+        d.Cc[cur][dst] = r.Cc;
+    }
+    if (d.has_bodies) d.cdf_aff[cur][dst] = r.cdf_aff;
+    if (d.has_plastic) d.plastic[cur][dst] = r.plastic;
+}
+
+__global__ void k_immigrate_commit(DeviceData d, const void* buf, uint32_t cap) {
+    const uint32_t count = min(((const ShardHeader*)buf)->count, cap);
+    d.counters->n_live = min(d.counters->n_live + count, d.n);
+}
+__global__ void k_zero_shard_counters(Counters* c) {
+    c->send_count[0] = c->send_count[1] = 0;
+    c->halo_count[0] = c->halo_count[1] = 0;
+}
+// Publishes the record counts in the buffer headers (which = 0: migration, 1: halo).
+__global__ void k_write_headers(Counters* c, void* left, void* right, uint32_t cap, int which) {
+    const uint32_t* cnt = which ? c->halo_count : c->send_count;
+    ((ShardHeader*)left)->count = min(cnt[0], cap);
+    ((ShardHeader*)right)->count = min(cnt[1], cap);
+    if (cnt[0] > cap || cnt[1] > cap) c->overflow = 2u;
+}
+// After a substep the next buffer holds the sorted live particles in [0, total) and the parked (dead) ones after:
+// dropping the tail removes the emigrants.
+__global__ void k_drop_dead_tail(DeviceData d) {
+    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+    d.counters->n_live = d.cell_start[nb * CELLS_PER_BLOCK];
+}
+
+// Packs the node momenta of the active blocks of the shared columns (x == slab_lo -> buffer 0, x == slab_hi ->
+// buffer 1). One CTA of 64 threads per block, grid-stride.
+__global__ void __launch_bounds__(CELLS_PER_BLOCK) k_halo_pack(DeviceData d, void* left_buf, void* right_buf, uint32_t cap) {
+    __shared__ uint32_t s_slot;
+    HaloBlock* left = shard_records<HaloBlock>(left_buf);
+    HaloBlock* right = shard_records<HaloBlock>(right_buf);
+    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+    const int lo = d.sim->slab_lo, hi = d.sim->slab_hi;
+    for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+        const int4 vid = d.block_vid[b];
+        const int dir = (vid.x == lo) ? 0 : (vid.x == hi) ? 1 : -1;
+        if (dir < 0) continue; // (uniform per CTA)
+        __syncthreads();
+        if (threadIdx.x == 0) s_slot = atomicAdd(&d.counters->halo_count[dir], 1u);
+        __syncthreads();
+        const uint32_t slot = s_slot;
+        if (slot >= cap) continue;
+        HaloBlock* out = (dir == 0 ? left : right) + slot;
+        if (threadIdx.x == 0) out->vid = vid;
+        out->node[threadIdx.x] = d.node_mv[b * CELLS_PER_BLOCK + threadIdx.x];
+    }
+}
+
+// Adds the neighbour's partial sums to the blocks this rank also holds.
+template <int D>
+__global__ void __launch_bounds__(CELLS_PER_BLOCK) k_halo_add(DeviceData d, const void* buf, uint32_t cap) {
+    const uint32_t count = min(((const ShardHeader*)buf)->count, cap);
+    const HaloBlock* in = shard_records<HaloBlock>(buf);
+    for (uint32_t k = blockIdx.x; k < count; k += gridDim.x) {
+        const int4 vid = in[k].vid;
+        const uint32_t hid = find_block(d.hkeys, d.hvals, d.capacity - 1, pack_key<D>(vid.x, vid.y, vid.z));
+        if (hid == NONE || hid >= d.capacity) continue; // no particle of this rank reads that block
+        float4 a = d.node_mv[hid * CELLS_PER_BLOCK + threadIdx.x];
+        const float4 b = in[k].node[threadIdx.x];
+        a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+        d.node_mv[hid * CELLS_PER_BLOCK + threadIdx.x] = a;
+    }
+}
+
+// Body impulses <-> dense int32[16][6] (lin xyz, ang xyz) for the all-reduce.
+__global__ void k_impulses_io(DeviceData d, int* buf, int write) {
+    const uint32_t id = threadIdx.x;
+    if (id >= B200MPM_MAX_BODIES) return;
+    BodyDev& b = d.bodies[id];
+    for (int k = 0; k < 3; ++k) {
+        if (write) {
+            b.imp_lin[k] = buf[id * 6 + k];
+            b.imp_ang[k] = buf[id * 6 + 3 + k];
+        } else {
+            buf[id * 6 + k] = (id < d.sim->num_bodies) ? b.imp_lin[k] : 0;
+            buf[id * 6 + 3 + k] = (id < d.sim->num_bodies) ? b.imp_ang[k] : 0;
+        }
+    }
+}
+
+static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
+
+void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap) {
+    k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
+    if (d.n) {
+        if (c.dim == 2) k_emigrate<2><<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, left, right, cap);
+        else k_emigrate<3><<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, left, right, cap);
+    }
+    k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 0);
+    *c.launch_counter += 3;
+}
+void launch_immigrate(const LaunchCfg& c, const DeviceData& d, int cur, const void* in, uint32_t cap) {
+    if (cap == 0) return;
+    if (c.dim == 2) k_immigrate<2><<<div_up(cap, 256), 256, 0, c.stream>>>(d, cur, in, cap);
+    else k_immigrate<3><<<div_up(cap, 256), 256, 0, c.stream>>>(d, cur, in, cap);
+    k_immigrate_commit<<<1, 1, 0, c.stream>>>(d, in, cap);
+    *c.launch_counter += 2;
+}
+void launch_drop_dead_tail(const LaunchCfg& c, const DeviceData& d) {
+    k_drop_dead_tail<<<1, 1, 0, c.stream>>>(d);
+    ++*c.launch_counter;
+}
+void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap) {
+    k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
+    k_halo_pack<<<c.num_sms * 8, CELLS_PER_BLOCK, 0, c.stream>>>(d, left, right, cap);
+    k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 1);
+    *c.launch_counter += 3;
+}
+void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap) {
+    if (cap == 0) return;
+    int grid = (int)(cap < (uint32_t)(c.num_sms * 8) ? cap : (uint32_t)(c.num_sms * 8));
+    if (c.dim == 2) k_halo_add<2><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d, in, cap);
+    else k_halo_add<3><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d, in, cap);
+    ++*c.launch_counter;
+}
+void launch_impulses_io(const LaunchCfg& c, const DeviceData& d, int* buf, int write) {
+    k_impulses_io<<<1, 32, 0, c.stream>>>(d, buf, write);
+    ++*c.launch_counter;
+}
+
+} // namespace b2

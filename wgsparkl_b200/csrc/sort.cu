@@ -69,13 +69,15 @@ __device__ __forceinline__ uint32_t insert_block(const DeviceData& d, int bx, in
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < d.n;
+    const bool active = i < d.counters->n_live;
     const float h = d.sim->cell_width;
     int bx = 0, by = 0, bz = 0;
     uint32_t cell = 0;
     uint32_t key = NONE;
+    bool dead = false;
     if (active) {
         float4 p = d.pos4[cur][i];
+        dead = (__float_as_uint(p.w) & FLAG_DEAD) != 0u; // emigrated (k_emigrate): parked, then dropped
         int cx = assoc_cell(p.x, h), cy = assoc_cell(p.y, h);
         bx = cx >> Dim<D>::LOG_BLOCK; // floor(c / BLOCK), grid.wgsl:286
         by = cy >> Dim<D>::LOG_BLOCK;
@@ -85,11 +87,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
             bz = cz >> Dim<D>::LOG_BLOCK;
             cell += (cz & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK * Dim<D>::BLOCK;
         }
-        key = pack_key<D>(bx, by, bz);
+        key = dead ? NONE : pack_key<D>(bx, by, bz);
     }
     const uint32_t lane = threadIdx.x & 31;
     uint32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool leader = active && (lane == 0 || prev_key != key);
+    const bool leader = active && !dead && (lane == 0 || prev_key != key);
     const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
     // For every run leader (usually one per warp) the 2^D insertions of blocks_associated_to_block
     // (grid.wgsl:300-320) are spread over 2^D lanes: one probe latency instead of 2^D in a row.
@@ -109,13 +111,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
     const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
     const int src = below ? (31 - __clz(below)) : 0;
     slot = __shfl_sync(0xffffffffu, slot, src);
-    if (active) d.pkey[i] = (slot == NONE) ? NONE : (slot * CELLS_PER_BLOCK + cell);
+    if (active) d.pkey[i] = (slot == NONE || dead) ? NONE : (slot * CELLS_PER_BLOCK + cell);
 }
 
 // ---- update_block_particle_count (sort.wgsl:89-99), one bin per cell ---------------------------------
 __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < d.n;
+    const bool active = i < d.counters->n_live;
     uint32_t ck = NONE;
     if (active) {
         const uint32_t pk = d.pkey[i];
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
                 d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
         }
     }
-    if (i >= d.n) return;
+    if (i >= d.counters->n_live) return;
     uint32_t ck = d.pkey[i];
     if (ck != NONE) {
         const uint32_t dest = d.cell_start[ck] + d.rank[i];

@@ -59,7 +59,21 @@ EXPORTS = (
     "b200mpm_sort_only",
     "b200mpm_prefix_sum_u32",
     "b200mpm_slab_configure",
+    "b200mpm_data_create_ex",
+    "b200mpm_data_num_live",
+    "b200mpm_shard_emigrate",
+    "b200mpm_shard_immigrate",
+    "b200mpm_shard_step_begin",
+    "b200mpm_shard_halo_pack",
+    "b200mpm_shard_halo_add",
+    "b200mpm_shard_impulses",
+    "b200mpm_shard_step_end",
+    "b200mpm_read_particles_unordered",
 )
+
+PARTICLE_RECORD_BYTES = 128  # B200MPM_PARTICLE_RECORD_BYTES
+HALO_BLOCK_BYTES = 1040  # B200MPM_HALO_BLOCK_BYTES
+SHARD_HEADER_BYTES = 16  # B200MPM_SHARD_HEADER_BYTES
 
 
 def load_library():
@@ -103,7 +117,17 @@ def load_library():
     L.b200mpm_data_status.argtypes = [vp, ctypes.POINTER(u32)]
     L.b200mpm_sort_only.argtypes = [vp, vp]
     L.b200mpm_prefix_sum_u32.argtypes = [vp, vp, sz]
-    L.b200mpm_slab_configure.argtypes = [vp, i32, i32, ctypes.c_int32, ctypes.c_int32]
+    L.b200mpm_slab_configure.argtypes = [vp, ctypes.c_int32, ctypes.c_int32]
+    L.b200mpm_data_create_ex.argtypes = [vp, vp, vp, sz, vp, sz, vp, sz, ctypes.c_float, u32, ctypes.POINTER(vp)]
+    L.b200mpm_data_num_live.argtypes = [vp, ctypes.POINTER(sz)]
+    L.b200mpm_shard_emigrate.argtypes = [vp, vp, vp, vp, u32]
+    L.b200mpm_shard_immigrate.argtypes = [vp, vp, vp, u32]
+    L.b200mpm_shard_step_begin.argtypes = [vp, vp]
+    L.b200mpm_shard_halo_pack.argtypes = [vp, vp, vp, vp, u32]
+    L.b200mpm_shard_halo_add.argtypes = [vp, vp, vp, u32]
+    L.b200mpm_shard_impulses.argtypes = [vp, vp, vp, i32]
+    L.b200mpm_shard_step_end.argtypes = [vp, vp]
+    L.b200mpm_read_particles_unordered.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
     _lib = L
     return L
 
@@ -184,7 +208,7 @@ class MpmData:
     """MpmData (src/pipeline.rs:84-172): owns every device buffer of one simulation."""
 
     def __init__(self, pipeline: MpmPipeline, params: SimulationParams, particles, bodies=None,
-                 cell_width: float = 1.0, grid_capacity: int = 60_000):
+                 cell_width: float = 1.0, grid_capacity: int = 60_000, particle_ids=None, particle_capacity=None):
         L = load_library()
         self.pipeline = pipeline
         self.dim = pipeline.dim
@@ -201,9 +225,17 @@ class MpmData:
         while self.capacity < grid_capacity:
             self.capacity <<= 1
         h = ctypes.c_void_p()
-        _check(L.b200mpm_data_create(pipeline._h, abi.ptr(p), abi.ptr(particles), self.num_particles,
-                                     abi.ptr(bodies), self.num_bodies, ctypes.c_float(cell_width),
-                                     int(grid_capacity), ctypes.byref(h)))
+        if particle_ids is None and particle_capacity is None:
+            _check(L.b200mpm_data_create(pipeline._h, abi.ptr(p), abi.ptr(particles), self.num_particles,
+                                         abi.ptr(bodies), self.num_bodies, ctypes.c_float(cell_width),
+                                         int(grid_capacity), ctypes.byref(h)))
+            self.particle_capacity = self.num_particles
+        else:
+            ids = None if particle_ids is None else np.ascontiguousarray(particle_ids, dtype=np.uint32)
+            self.particle_capacity = int(particle_capacity or self.num_particles)
+            _check(L.b200mpm_data_create_ex(pipeline._h, abi.ptr(p), abi.ptr(particles), self.num_particles, abi.ptr(ids),
+                                            self.particle_capacity, abi.ptr(bodies), self.num_bodies,
+                                            ctypes.c_float(cell_width), int(grid_capacity), ctypes.byref(h)))
         self._h = h
 
     @staticmethod
@@ -276,6 +308,48 @@ class MpmData:
         got = ctypes.c_size_t(0)
         _check(load_library().b200mpm_read_grid(self._h, abi.ptr(blocks), abi.ptr(nodes), nb, ctypes.byref(got)))
         return blocks[: got.value], nodes.reshape(-1, 64)[: got.value]
+
+    # ---- slab sharding (include/b200mpm.h "multi-GPU slab sharding"); buffers are raw device pointers (ints)
+    def slab_configure(self, x_lo: int, x_hi: int):
+        _check(load_library().b200mpm_slab_configure(self._h, int(x_lo), int(x_hi)))
+
+    def num_live(self) -> int:
+        n = ctypes.c_size_t(0)
+        _check(load_library().b200mpm_data_num_live(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def shard_emigrate(self, dev_left: int, dev_right: int, cap_records: int):
+        _check(load_library().b200mpm_shard_emigrate(self.pipeline._h, self._h, ctypes.c_void_p(dev_left),
+                                                     ctypes.c_void_p(dev_right), cap_records))
+
+    def shard_immigrate(self, dev_buffer: int, cap_records: int):
+        _check(load_library().b200mpm_shard_immigrate(self.pipeline._h, self._h, ctypes.c_void_p(dev_buffer), cap_records))
+
+    def shard_step_begin(self):
+        _check(load_library().b200mpm_shard_step_begin(self.pipeline._h, self._h))
+
+    def shard_halo_pack(self, dev_left: int, dev_right: int, cap_blocks: int):
+        _check(load_library().b200mpm_shard_halo_pack(self.pipeline._h, self._h, ctypes.c_void_p(dev_left),
+                                                      ctypes.c_void_p(dev_right), cap_blocks))
+
+    def shard_halo_add(self, dev_buffer: int, cap_blocks: int):
+        _check(load_library().b200mpm_shard_halo_add(self.pipeline._h, self._h, ctypes.c_void_p(dev_buffer), cap_blocks))
+
+    def shard_impulses(self, dev_buf: int, write: bool):
+        _check(load_library().b200mpm_shard_impulses(self.pipeline._h, self._h, ctypes.c_void_p(dev_buf), 1 if write else 0))
+
+    def shard_step_end(self):
+        _check(load_library().b200mpm_shard_step_end(self.pipeline._h, self._h))
+
+    def read_particles_unordered(self):
+        """(particles, ids) of the live particles in device order."""
+        out = np.zeros(self.particle_capacity, dtype=abi.particle_dtype)
+        ids = np.zeros(self.particle_capacity, dtype=np.uint32)
+        n = ctypes.c_size_t(0)
+        _check(load_library().b200mpm_read_particles_unordered(self._h, abi.ptr(out), abi.ptr(ids), self.particle_capacity,
+                                                               ctypes.byref(n)))
+        keep = ids[: n.value] != abi.NONE
+        return out[: n.value][keep], ids[: n.value][keep]
 
     def read_sorted_ids(self):
         out = np.zeros(self.num_particles, dtype=np.uint32)
