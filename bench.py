@@ -36,6 +36,9 @@ UNIT = "particle-substeps/s"
 BYTES_P2G = 66.0
 BYTES_G2P_ELASTIC = 162.0
 BYTES_G2P_SAND = 218.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_g2p launch at 1M particles, from the committed
+# `ncu --set full` capture (profiles/); None until a capture of the current kernel is committed.
+G2P_NCU_TRAFFIC_BYTES = None
 
 
 def load_peaks():
@@ -99,12 +102,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_scene(n_side, contact=True):
+def build_scene(n_side, contact=True, nx=None):
     from wgsparkl_b200 import scenes
 
     # configs[1]: 3D elastic cube drop, n_side^3 particles. The cube starts just above the ground cuboid
     # so that the timed region covers the contact phase (CPIC active), the more expensive regime.
-    return scenes.elastic_cube_3d(n_side, y_offset=-5.0 if contact else 60.0, grid_capacity=60_000)
+    return scenes.elastic_cube_3d(n_side, y_offset=-5.0 if contact else 60.0, grid_capacity=60_000, nx=nx)
 
 
 def frame_io_arrays(scene):
@@ -134,15 +137,25 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     hbm_peak, peak_kind = load_peaks()
 
-    scene = build_scene(args.n_side)
-    n = len(scene["particles"])
+    # N = 1: BASELINE configs[1] (1M-particle elastic cube). N > 1: the same block stretched along x to N x 1M
+    # particles and slab-sharded over the N GPUs (weak scaling; migration + node halo over NCCL every substep).
+    scene = build_scene(args.n_side, nx=args.n_side * world)
+    n_total = len(scene["particles"])
     spf = scene["substeps_per_frame"]
-    pipe = MpmPipeline(local_rank, 3)  # raises without the CUDA library / an sm_100 device: no fallback
     stream = torch.cuda.Stream(device=local_rank)
-    pipe.set_stream(stream.cuda_stream)
-    data = MpmData(pipe, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    sharded = None
+    if world == 1:
+        pipe = MpmPipeline(local_rank, 3)  # raises without the CUDA library / an sm_100 device: no fallback
+        pipe.set_stream(stream.cuda_stream)
+        data = MpmData(pipe, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    else:
+        from wgsparkl_b200.sharded import ShardedMpm
+
+        sharded = ShardedMpm(scene, rank, world, local_rank, stream=stream)
+        pipe, data = sharded.pipe, sharded.data
     poses, vels = frame_io_arrays(scene)
-    host_pos = torch.empty((n, 4), dtype=torch.float32).pin_memory().numpy()
+    n_local = data.num_particles
+    host_pos = torch.empty((max(n_local, 1), 4), dtype=torch.float32).pin_memory().numpy()
 
     def barrier():
         if world > 1:
@@ -164,14 +177,20 @@ def run_ours(args):
         return float(ms.item())
 
     def frame_device():
-        pipe.queue_step(data, spf)
+        if sharded is None:
+            pipe.queue_step(data, spf)
+        else:
+            sharded.step(spf)
 
     def frame_e2e():
         data.write_body_poses(poses)  # H2D (src_testbed/step.rs:92-96)
         data.write_body_vels(vels)  # H2D (step.rs:98-119)
-        pipe.queue_step(data, spf)
+        frame_device()
         data.read_body_poses()  # D2H (step.rs:175-176)
-        data.read_positions(host_pos)  # D2H: the step's result, into pinned host memory
+        if sharded is None:
+            data.read_positions(host_pos)  # D2H: the step's result, into pinned host memory
+        else:
+            data.read_particles_unordered()  # D2H: this rank's slab
 
     for _ in range(args.warmup):
         frame_device()
@@ -182,56 +201,66 @@ def run_ours(args):
     ms = timed(frame_device, args.steps)
     launches = pipe.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    value = n * spf * args.steps * world / (ms * 1e-3)
+    value = n_total * spf * args.steps / (ms * 1e-3)
 
     # end-to-end through the C ABI with host buffers
     frame_e2e()
     ms_e2e = timed(frame_e2e, args.steps)
-    e2e_value = n * spf * args.steps * world / (ms_e2e * 1e-3)
+    e2e_value = n_total * spf * args.steps / (ms_e2e * 1e-3)
     nb = len(scene["bodies"])
     h2d = nb * (poses.dtype.itemsize + vels.dtype.itemsize)
-    d2h = nb * poses.dtype.itemsize + n * 16
+    d2h = nb * poses.dtype.itemsize + (n_local * 16 if sharded is None else n_local * 200)
 
-    # per-kernel durations (CUDA events around each pass, on the launching stream) for the roofline
-    pipe.set_timestamps(True)
-    frames_prof = max(1, min(args.steps, 3))
-    for _ in range(frames_prof):
-        frame_device()
-    t = pipe.timings_ms()
-    pipe.set_timestamps(False)
-    launches_per_kernel = frames_prof * spf
-    g2p_ms = t["g2p"] / launches_per_kernel
-    p2g_ms = t["p2g"] / launches_per_kernel
-    g2p_gbs = BYTES_G2P_ELASTIC * n / (g2p_ms * 1e-3) / 1e9
-    p2g_gbs = BYTES_P2G * n / (p2g_ms * 1e-3) / 1e9
+    roof = None
     nblocks, overflow = data.status()
+    if sharded is None:
+        # per-kernel durations (CUDA events around each pass, on the launching stream) for the roofline
+        pipe.set_timestamps(True)
+        frames_prof = max(1, min(args.steps, 3))
+        for _ in range(frames_prof):
+            frame_device()
+        t = pipe.timings_ms()
+        pipe.set_timestamps(False)
+        launches_per_kernel = frames_prof * spf
+        g2p_ms = t["g2p"] / launches_per_kernel
+        p2g_ms = t["p2g"] / launches_per_kernel
+        g2p_gbs = BYTES_G2P_ELASTIC * n_total / (g2p_ms * 1e-3) / 1e9
+        p2g_gbs = BYTES_P2G * n_total / (p2g_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_g2p (grid_update + g2p + particles_update)",
+                "achieved": g2p_gbs, "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s",
+                "frac": g2p_gbs / hbm_peak, "traffic": G2P_NCU_TRAFFIC_BYTES,
+                "bytes_per_particle": BYTES_G2P_ELASTIC, "ms_per_launch": g2p_ms,
+                "p2g": {"achieved": p2g_gbs, "frac": p2g_gbs / hbm_peak, "bytes_per_particle": BYTES_P2G,
+                        "ms_per_launch": p2g_ms, "note": "both P2G instantiations, serialised (timestamps mode)"},
+                "pass_ms_per_substep": {k: v / launches_per_kernel for k, v in t.items()}}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])",
-                   "particles_per_gpu": n, "substeps_per_step": spf, "cell_width": scene["cell_width"],
-                   "active_blocks": nblocks, "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world,
-                   "l2": "inputs larger than L2 (%.0f MB of particle state per GPU)" % (n * 220 / 1e6)},
+        "config": {"workload": "3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])"
+                   + ("" if world == 1 else ", stretched to %d x 1M particles along x" % world),
+                   "particles_total": n_total, "particles_per_gpu": n_total // world, "substeps_per_step": spf,
+                   "cell_width": scene["cell_width"], "active_blocks_rank0": nblocks,
+                   "parallelism": "1 GPU" if world == 1 else
+                   "%d slabs along x (particle migration + node-halo exchange over NCCL every substep)" % world,
+                   "l2": "inputs larger than L2 (%.0f MB of particle state per GPU)" % (n_total // world * 220 / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_g2p (grid_update + g2p + particles_update)",
-                     "achieved": g2p_gbs, "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s",
-                     "frac": g2p_gbs / hbm_peak, "traffic": None,
-                     "bytes_per_particle": BYTES_G2P_ELASTIC, "ms_per_launch": g2p_ms,
-                     "p2g": {"achieved": p2g_gbs, "frac": p2g_gbs / hbm_peak, "bytes_per_particle": BYTES_P2G,
-                             "ms_per_launch": p2g_ms},
-                     "pass_ms_per_substep": {k: v / launches_per_kernel for k, v in t.items()}},
     }
+    if roof is not None:
+        out["roofline"] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, scene)
     if rank == 0:
         print(json.dumps(out))
-    data.close()
-    pipe.close()
+    if sharded is not None:
+        sharded.close()
+    else:
+        data.close()
+        pipe.close()
     if world > 1:
         dist.destroy_process_group()
 

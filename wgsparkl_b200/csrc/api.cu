@@ -49,12 +49,14 @@ struct b200mpm_pipeline {
     std::vector<EventPair> events;
     std::vector<cudaEvent_t> event_pool;
     double pass_ms[B200MPM_NUM_PASSES] = {0};
+    std::vector<b200mpm_data*> children; // data objects created on this pipeline (orphaned, not freed, on destroy)
     // scratch for b200mpm_prefix_sum_u32
     LaunchCfg cfg() { return LaunchCfg{dim, num_sms, stream, &launches}; }
 };
 
 struct b200mpm_data {
-    b200mpm_pipeline* pipe = nullptr;
+    b200mpm_pipeline* pipe = nullptr; // null once the pipeline has been destroyed (only destroy is legal then)
+    int device = 0;
     DeviceData dev{};
     int cur = 0;
     bool sorted_indirect = true; // sorted_ids is an indirection into `cur` (no full substep since the last sort)
@@ -76,6 +78,8 @@ struct b200mpm_data {
 };
 
 namespace {
+
+void orphan_data(b200mpm_data* d) { d->pipe = nullptr; }
 
 template <class T>
 int dev_alloc(b200mpm_data* d, T** out, size_t count, bool zero = true) {
@@ -333,6 +337,8 @@ void b200mpm_pipeline_destroy(b200mpm_pipeline* p) {
         cudaEventDestroy(e.b);
     }
     for (auto e : p->event_pool) cudaEventDestroy(e);
+    // Data objects that outlive their pipeline stay valid for b200mpm_data_destroy only.
+    for (b200mpm_data* d : p->children) orphan_data(d);
     cudaStreamDestroy(p->own_stream);
     delete p;
 }
@@ -384,6 +390,7 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
 
     auto* d = new b200mpm_data();
     d->pipe = p;
+    d->device = p->device;
     d->num_bodies = (uint32_t)num_bodies;
     DeviceData& dev = d->dev;
     dev.n = ncap;
@@ -599,14 +606,26 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
         b200mpm_data_destroy(d);
         return fail(B200MPM_ERR_CUDA, cudaGetErrorString(e));
     }
+    p->children.push_back(d);
     *out = d;
     return B200MPM_OK;
 }
 
 void b200mpm_data_destroy(b200mpm_data* d) {
     if (!d) return;
-    cudaSetDevice(d->pipe->device);
-    cudaStreamSynchronize(d->pipe->stream);
+    if (d->pipe) {
+        cudaSetDevice(d->pipe->device);
+        cudaStreamSynchronize(d->pipe->stream);
+        auto& ch = d->pipe->children;
+        for (size_t i = 0; i < ch.size(); ++i)
+            if (ch[i] == d) {
+                ch.erase(ch.begin() + i);
+                break;
+            }
+    } else {
+        cudaSetDevice(d->device);
+        cudaDeviceSynchronize();
+    }
     for (auto& gp : d->graph_exec)
         for (auto& g : gp)
             if (g) cudaGraphExecDestroy(g);
@@ -667,8 +686,9 @@ int b200mpm_get_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_PASSES]) {
 }
 
 int b200mpm_write_sim_params(b200mpm_data* d, const b200mpm_sim_params* params) {
-    if (!d || !params) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!d || !params || !d->pipe) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument / destroyed pipeline");
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     int r = ensure_pinned(d, 4096);
     if (r) return r;
@@ -687,6 +707,7 @@ int b200mpm_write_body_poses(b200mpm_data* d, const b200mpm_pose* poses, size_t 
     if (n > d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "more poses than bodies");
     if (n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     int r = ensure_pinned(d, 4096);
     if (r) return r;
@@ -705,6 +726,7 @@ int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_
     if (n > d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "more velocities than bodies");
     if (n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     int r = ensure_pinned(d, 4096);
     if (r) return r;
@@ -723,6 +745,7 @@ static int read_body_state(b200mpm_data* d, b200mpm_pose* poses, b200mpm_velocit
     if (n > d->num_bodies) n = d->num_bodies;
     if (n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     int r = ensure_pinned(d, 4096);
     if (r) return r;
@@ -750,6 +773,7 @@ int b200mpm_read_positions(b200mpm_data* d, float* out) {
     if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (d->dev.n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     size_t bytes = (size_t)d->dev.n * sizeof(float4);
     int r = ensure_staging(d, bytes);
@@ -765,6 +789,7 @@ int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out) {
     if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (d->dev.n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     size_t bytes = (size_t)d->dev.n * sizeof(b200mpm_particle);
     int r = ensure_staging(d, bytes);
@@ -779,6 +804,7 @@ int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out) {
 int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks) {
     if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     Counters c;
     CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
@@ -801,6 +827,7 @@ int b200mpm_read_grid(b200mpm_data* d, b200mpm_block_info* blocks, b200mpm_node*
     if (take == 0) return B200MPM_OK;
     if (!blocks || !nodes) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null output");
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     size_t bbytes = take * sizeof(b200mpm_block_info);
     size_t boff = (bbytes + 255) & ~(size_t)255;
     size_t nbytes = take * CELLS_PER_BLOCK * sizeof(b200mpm_node);
@@ -819,6 +846,7 @@ int b200mpm_read_sorted_ids(b200mpm_data* d, uint32_t* out) {
     if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (d->dev.n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     size_t bytes = (size_t)d->dev.n * sizeof(uint32_t);
     int r = ensure_staging(d, bytes);
@@ -861,6 +889,7 @@ int b200mpm_slab_configure(b200mpm_data* d, int32_t x_lo, int32_t x_hi) {
     if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (x_lo >= x_hi) return fail(B200MPM_ERR_INVALID_ARGUMENT, "empty slab");
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     int r = ensure_pinned(d, 4096);
     if (r) return r;
@@ -877,6 +906,7 @@ int b200mpm_slab_configure(b200mpm_data* d, int32_t x_lo, int32_t x_hi) {
 int b200mpm_data_num_live(b200mpm_data* d, size_t* num_live) {
     if (!d || !num_live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
     Counters c;
     CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
@@ -952,6 +982,7 @@ int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uin
     if (live == 0) return B200MPM_OK;
     if (!out || !ids || capacity < live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "output too small");
     b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     size_t pbytes = live * sizeof(b200mpm_particle);
     size_t poff = ((size_t)d->dev.n * sizeof(b200mpm_particle) + 255) & ~(size_t)255;
     r = ensure_staging(d, poff + (size_t)d->dev.n * sizeof(uint32_t));

@@ -57,19 +57,20 @@ def elastic_block_2d(n_side=100, jitter=True, seed=SEED):
                 substeps_per_frame=15)
 
 
-def elastic_cube_3d(n_side=100, y_offset=60.0, jitter=True, seed=SEED, grid_capacity=60_000, ground=True):
+def elastic_cube_3d(n_side=100, y_offset=60.0, jitter=True, seed=SEED, grid_capacity=60_000, ground=True, nx=None):
     """Config 2: 3D corotated-elastic cube dropped on a static ground cuboid (elastic_cut3.rs:28-71
-    scaled, trimeshes removed)."""
+    scaled, trimeshes removed). `nx` (default n_side) stretches the block along x for weak-scaling runs."""
     h = 1.0
-    pos = _lattice3(n_side, n_side, n_side, (-n_side / 2.0, y_offset, -n_side / 2.0), h)
+    nx = nx or n_side
+    pos = _lattice3(nx, n_side, n_side, (-nx / 2.0, y_offset, -n_side / 2.0), h)
     pos = _jitter(pos, h, jitter, seed)
     parts = make_particles(pos, 3, h / 4.0, 2700.0, ElasticCoefficients.from_young_modulus(10_000_000.0, 0.2),
                            phase=ParticlePhase(1.0, F32_MAX))
     bodies, colliders = RigidBodySet(), ColliderSet()
     if ground:
         rb = bodies.insert(RigidBodyBuilder.fixed().translation([0.0, -4.0, 0.0]))
-        colliders.insert_with_parent(ColliderBuilder.cuboid(max(100.0, n_side * 1.0), 1.0, max(100.0, n_side * 1.0)), rb, bodies)
-    return dict(name="3d_elastic_cube_%d" % (n_side**3), dim=3,
+        colliders.insert_with_parent(ColliderBuilder.cuboid(max(100.0, nx * 1.0), 1.0, max(100.0, n_side * 1.0)), rb, bodies)
+    return dict(name="3d_elastic_cube_%d" % (nx * n_side * n_side), dim=3,
                 params=SimulationParams([0.0, -9.81 * 4.0, 0.0], (1.0 / 60.0) / 20.0), particles=parts,
                 bodies=bodies_to_abi(bodies, colliders, 3), cell_width=h, grid_capacity=grid_capacity,
                 substeps_per_frame=20)

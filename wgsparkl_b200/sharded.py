@@ -75,7 +75,8 @@ class ShardedMpm:
     are cheap to rebuild); each rank keeps the particles of its slab."""
 
     def __init__(self, scene: dict, rank: int, world: int, device: int, migration_cap: int = 16384,
-                 halo_cap: Optional[int] = None, slack: float = 1.6, slabs: Optional[List[Tuple[int, int]]] = None):
+                 halo_cap: Optional[int] = None, slack: float = 1.6, slabs: Optional[List[Tuple[int, int]]] = None,
+                 stream=None):
         import torch
         import torch.distributed as dist
 
@@ -89,7 +90,9 @@ class ShardedMpm:
         ids = np.nonzero(mine)[0].astype(np.uint32)
         n_mine = int(mine.sum())
         self.pipe = MpmPipeline(device, self.dim)
-        self.stream = torch.cuda.current_stream(device)
+        # One explicit torch stream carries the kernels of this rank AND its NCCL exchanges (the legacy default
+        # stream has handle 0, which the C ABI reads as "use the pipeline's own stream").
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
         self.pipe.set_stream(self.stream.cuda_stream)
         cap = int(n_mine * slack) + 4 * migration_cap
         self.data = MpmData(self.pipe, scene["params"], parts[mine], scene["bodies"], scene["cell_width"], scene["grid_capacity"],
@@ -119,6 +122,10 @@ class ShardedMpm:
             np.any(b["inv_mass"] != 0) or np.any(b["inv_inertia"] != 0) or np.any(b["linvel"] != 0) or np.any(b["angvel"] != 0))
 
     def substep(self):
+        with self.torch.cuda.stream(self.stream):
+            self._substep()
+
+    def _substep(self):
         d, dist = self.data, self.dist
         left, right = neighbours(self.rank, self.world)
         if self.world > 1:
@@ -193,10 +200,15 @@ class LocalSlabs:
         self.world = world
         bx = particle_block_x(scene["particles"]["position"][:, 0], scene["cell_width"], scene["dim"])
         slabs = kw.pop("slabs", None) or partition_slabs(bx, world)
-        self.ranks = [ShardedMpm(scene, r, world, device, slabs=slabs, **kw) for r in range(world)]
+        self.stream = torch.cuda.Stream(device=device)  # all slabs share one stream: program order = data order
+        self.ranks = [ShardedMpm(scene, r, world, device, slabs=slabs, stream=self.stream, **kw) for r in range(world)]
         self.n_global = len(scene["particles"])
 
     def substep(self):
+        with self.torch.cuda.stream(self.stream):
+            self._substep()
+
+    def _substep(self):
         R, W = self.ranks, self.world
         for r in R:
             r.data.shard_emigrate(r.mig_send[0].data_ptr(), r.mig_send[1].data_ptr(), r.migration_cap)
