@@ -266,6 +266,16 @@ int b200mpm_shard_halo_add(b200mpm_pipeline* p, b200mpm_data* d, const void* dev
 /* write == 0: body impulses -> dev_buf (int32[16*6]); write != 0: dev_buf -> body impulses. */
 int b200mpm_shard_impulses(b200mpm_pipeline* p, b200mpm_data* d, int32_t* dev_buf, int write);
 int b200mpm_shard_step_end(b200mpm_pipeline* p, b200mpm_data* d);
+/* Native transport: the library owns an NCCL communicator (libnccl.so.2 is resolved with dlopen, i.e. the copy
+ * the host process already uses) and the exchange buffers, and b200mpm_shard_step enqueues WHOLE sharded substeps
+ * — kernels, the two neighbour send/recv groups and the impulse all-reduce — on the pipeline's stream, replayed
+ * from one captured CUDA graph per substep. rank 0 calls b200mpm_nccl_unique_id and distributes the 128 bytes
+ * (any out-of-band channel: torch.distributed in the Python host), then every rank calls
+ * b200mpm_shard_comm_init after b200mpm_slab_configure. */
+int b200mpm_nccl_unique_id(void* out, size_t bytes);
+int b200mpm_shard_comm_init(b200mpm_pipeline* p, b200mpm_data* d, int rank, int world, const void* unique_id,
+                            uint32_t migration_cap_records, uint32_t halo_cap_blocks);
+int b200mpm_shard_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps);
 /* Live particles in device order with their ids (no un-permutation). */
 int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uint32_t* ids, size_t capacity,
                                      size_t* count);

@@ -25,16 +25,17 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ok = True
-    for name, scene, n in (
-        ("elastic, sliding in +x", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80),
-        ("sand + solids + moving bodies", scenes.mixed_coupled_3d(12 * world, 12, 12, n_dynamic=2), 40),
+    for name, scene, n, native in (
+        ("elastic, sliding in +x [native nccl]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, True),
+        ("sand + solids + bodies  [native nccl]", scenes.mixed_coupled_3d(12 * world, 12, 12, n_dynamic=2), 40, True),
+        ("elastic, sliding in +x [torch.dist ]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, False),
     ):
         if name.startswith("elastic"):
             scene["particles"]["velocity"][:, 0] = 6.0
             scene["particles"]["velocity"][:, 1] = -2.0
         else:
             scene["bodies"]["translation"][2:, 1] = 12.0
-        sh = ShardedMpm(scene, rank, world, local)
+        sh = ShardedMpm(scene, rank, world, local, native=native)
         n0 = sh.num_live()
         sh.step(n)
         sh.sync()
@@ -53,7 +54,7 @@ def main():
             good = errs["position"] <= (1e-5 if sand else 2e-6) and errs["velocity"] <= (5e-3 if sand else 1e-4) \
                 and errs["def_grad"] <= 1e-5 and np.array_equal(got["cdf_affinity"], ref["cdf_affinity"])
             good = good and sum(c[0] for c in counts) == sum(c[1] for c in counts) == len(ref)
-            print("%-32s world=%d live before/after %s  errors %s  -> %s" % (
+            print("%-38s world=%d live before/after %s  errors %s  -> %s" % (
                 name, world, counts, {k: "%.2e" % v for k, v in errs.items()}, "PASS" if good else "FAIL"), flush=True)
             ok = ok and good
             data.close()

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "launch.h"
+#include "nccl_dyn.h"
 
 using namespace b2;
 
@@ -69,8 +70,18 @@ struct b200mpm_data {
     // One captured CUDA graph per ping-pong parity: the substep is recorded once and replayed, like the
     // reference's KernelInvocationQueue (src_testbed/step.rs:122-128). Independent kernels sit on parallel
     // branches of the graph.
-    cudaGraphExec_t graph_exec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}; // [parity][phase]
-    uint64_t graph_launches[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    cudaGraphExec_t graph_exec[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}}; // [parity][phase]
+    uint64_t graph_launches[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    // Native slab exchange (b200mpm_shard_comm_init): NCCL communicator + device exchange buffers.
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    void* mig_send[2] = {nullptr, nullptr};
+    void* mig_recv[2] = {nullptr, nullptr};
+    void* halo_send[2] = {nullptr, nullptr};
+    void* halo_recv[2] = {nullptr, nullptr};
+    int* imp_buf = nullptr;
+    uint32_t mig_cap = 0, halo_cap = 0;
+    bool bodies_react = false; // some body can react to an impulse (mass or motion): the impulse all-reduce is needed
     uint32_t n_live_host = 0; // host mirror of counters->n_live (sharded runs track it)
     bool sharded = false;
     cudaStream_t side = nullptr;
@@ -173,13 +184,49 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
 //   touch -> { block_prepare  ||  count -> scan } -> scatter -> { g2p_cdf -> p2g(cpic)  ||  p2g } -> g2p
 // phase: PHASE_ALL = the whole substep; PHASE_BEGIN = up to and including P2G; PHASE_END = from G2P on
 // (sharded runs exchange the node halo and the body impulses between the two).
-enum { PHASE_ALL = 0, PHASE_BEGIN = 1, PHASE_END = 2 };
+enum { PHASE_ALL = 0, PHASE_BEGIN = 1, PHASE_END = 2, PHASE_SHARDED = 3 };
 
 void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cudaStream_t side, uint64_t* counter,
                      int phase) {
     LaunchCfg c{p->dim, p->num_sms, main, counter};
     LaunchCfg cs{p->dim, p->num_sms, side ? side : main, counter};
     const DeviceData& dev = d->dev;
+    if (phase == PHASE_SHARDED) {
+        // One whole substep of a slab: migration and node-halo exchanges are NCCL send/recv groups on the same
+        // stream (and inside the same captured graph) as the kernels.
+        const NcclApi& nc = nccl_api();
+        const int left = d->rank > 0 ? d->rank - 1 : -1, right = d->rank < d->world - 1 ? d->rank + 1 : -1;
+        const size_t mig_bytes = B200MPM_SHARD_HEADER_BYTES + (size_t)d->mig_cap * B200MPM_PARTICLE_RECORD_BYTES;
+        const size_t halo_bytes = B200MPM_SHARD_HEADER_BYTES + (size_t)d->halo_cap * B200MPM_HALO_BLOCK_BYTES;
+        auto exchange = [&](void** send, void** recv, size_t bytes) {
+            nc.GroupStart();
+            if (left >= 0) {
+                nc.Send(send[0], bytes, ncclUint8, left, d->comm, main);
+                nc.Recv(recv[0], bytes, ncclUint8, left, d->comm, main);
+            }
+            if (right >= 0) {
+                nc.Send(send[1], bytes, ncclUint8, right, d->comm, main);
+                nc.Recv(recv[1], bytes, ncclUint8, right, d->comm, main);
+            }
+            nc.GroupEnd();
+        };
+        launch_emigrate(c, dev, d->cur, d->mig_send[0], d->mig_send[1], d->mig_cap);
+        exchange(d->mig_send, d->mig_recv, mig_bytes);
+        if (left >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[0], d->mig_cap);
+        if (right >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[1], d->mig_cap);
+        enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
+        launch_halo_pack(c, dev, d->halo_send[0], d->halo_send[1], d->halo_cap);
+        exchange(d->halo_send, d->halo_recv, halo_bytes);
+        if (left >= 0) launch_halo_add(c, dev, d->halo_recv[0], d->halo_cap);
+        if (right >= 0) launch_halo_add(c, dev, d->halo_recv[1], d->halo_cap);
+        if (d->bodies_react) {
+            launch_impulses_io(c, dev, d->imp_buf, 0);
+            nc.AllReduce(d->imp_buf, d->imp_buf, B200MPM_MAX_BODIES * 6, ncclInt32, ncclSum, d->comm, main); // exact
+            launch_impulses_io(c, dev, d->imp_buf, 1);
+        }
+        enqueue_substep(p, d, main, side, counter, PHASE_END);
+        return;
+    }
     if (phase == PHASE_END) {
         launch_g2p_update(c, dev, d->cur);
         launch_integrate_bodies(c, dev);
@@ -550,6 +597,13 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
     }
     UPLOAD(dmat, materials);
 
+    for (size_t i = 0; i < num_bodies; ++i) {
+        const b200mpm_body& s = bodies[i];
+        for (int k = 0; k < 3; ++k)
+            if (s.linvel[k] != 0.0f || s.angvel[k] != 0.0f || (s.two_ways && s.inv_mass[k] != 0.0f)) d->bodies_react = true;
+        for (int k = 0; k < 9; ++k)
+            if (s.two_ways && s.inv_inertia[k] != 0.0f) d->bodies_react = true;
+    }
     std::vector<BodyDev> hb(B200MPM_MAX_BODIES);
     std::memset(hb.data(), 0, hb.size() * sizeof(BodyDev));
     for (size_t i = 0; i < num_bodies; ++i) {
@@ -631,6 +685,14 @@ void b200mpm_data_destroy(b200mpm_data* d) {
             if (g) cudaGraphExecDestroy(g);
     for (auto& e : d->ev)
         if (e) cudaEventDestroy(e);
+    if (d->comm && nccl_api().ok) nccl_api().CommDestroy(d->comm);
+    for (int k = 0; k < 2; ++k) {
+        if (d->mig_send[k]) cudaFree(d->mig_send[k]);
+        if (d->mig_recv[k]) cudaFree(d->mig_recv[k]);
+        if (d->halo_send[k]) cudaFree(d->halo_send[k]);
+        if (d->halo_recv[k]) cudaFree(d->halo_recv[k]);
+    }
+    if (d->imp_buf) cudaFree(d->imp_buf);
     if (d->side) cudaStreamDestroy(d->side);
     for (void* p : d->allocs) cudaFree(p);
     if (d->staging) cudaFree(d->staging);
@@ -734,6 +796,17 @@ int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_
     if (r) return r;
     CU_TRY(cudaStreamSynchronize(p->stream));
     std::memcpy(d->pinned, vels, n * sizeof(b200mpm_velocity));
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k)
+            if (vels[i].linear[k] != 0.0f || vels[i].angular[k] != 0.0f) {
+                if (!d->bodies_react)
+                    for (auto& gp : d->graph_exec) // the captured sharded substep has no impulse all-reduce yet
+                        if (gp[PHASE_SHARDED]) {
+                            cudaGraphExecDestroy(gp[PHASE_SHARDED]);
+                            gp[PHASE_SHARDED] = nullptr;
+                        }
+                d->bodies_react = true;
+            }
     CU_TRY(cudaMemcpyAsync(d->staging, d->pinned, n * sizeof(b200mpm_velocity), cudaMemcpyHostToDevice, p->stream));
     launch_write_vels(p->cfg(), d->dev, (const b200mpm_velocity*)d->staging, (uint32_t)n);
     CU_TRY(cudaStreamSynchronize(p->stream));
@@ -968,6 +1041,61 @@ int b200mpm_shard_impulses(b200mpm_pipeline* p, b200mpm_data* d, int32_t* dev_bu
     if (!p || !d || d->pipe != p || !dev_buf) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     CU_TRY(cudaSetDevice(p->device));
     launch_impulses_io(p->cfg(), d->dev, dev_buf, write);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
+int b200mpm_nccl_unique_id(void* out, size_t bytes) {
+    if (!out || bytes < sizeof(ncclUniqueId)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "need a 128-byte buffer");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(B200MPM_ERR_COMM, nc.error);
+    ncclUniqueId id;
+    ncclResult_t r = nc.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(B200MPM_ERR_COMM, nc.GetErrorString(r));
+    std::memcpy(out, &id, sizeof(id));
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_comm_init(b200mpm_pipeline* p, b200mpm_data* d, int rank, int world, const void* unique_id,
+                            uint32_t migration_cap, uint32_t halo_cap) {
+    if (!p || !d || d->pipe != p || !unique_id) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (world < 1 || rank < 0 || rank >= world || !migration_cap || !halo_cap)
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "bad rank / world / capacities");
+    if (d->comm) return fail(B200MPM_ERR_INVALID_ARGUMENT, "communicator already initialised");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(B200MPM_ERR_COMM, nc.error);
+    CU_TRY(cudaSetDevice(p->device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    ncclResult_t r = nc.CommInitRank(&d->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(B200MPM_ERR_COMM, nc.GetErrorString(r));
+    d->rank = rank;
+    d->world = world;
+    d->mig_cap = migration_cap;
+    d->halo_cap = halo_cap;
+    const size_t mig_bytes = B200MPM_SHARD_HEADER_BYTES + (size_t)migration_cap * B200MPM_PARTICLE_RECORD_BYTES;
+    const size_t halo_bytes = B200MPM_SHARD_HEADER_BYTES + (size_t)halo_cap * B200MPM_HALO_BLOCK_BYTES;
+    for (int k = 0; k < 2; ++k) {
+        CU_TRY(cudaMalloc(&d->mig_send[k], mig_bytes));
+        CU_TRY(cudaMalloc(&d->mig_recv[k], mig_bytes));
+        CU_TRY(cudaMalloc(&d->halo_send[k], halo_bytes));
+        CU_TRY(cudaMalloc(&d->halo_recv[k], halo_bytes));
+        CU_TRY(cudaMemsetAsync(d->mig_send[k], 0, mig_bytes, p->stream));
+        CU_TRY(cudaMemsetAsync(d->mig_recv[k], 0, mig_bytes, p->stream));
+        CU_TRY(cudaMemsetAsync(d->halo_send[k], 0, halo_bytes, p->stream));
+        CU_TRY(cudaMemsetAsync(d->halo_recv[k], 0, halo_bytes, p->stream));
+    }
+    CU_TRY(cudaMalloc(&d->imp_buf, B200MPM_MAX_BODIES * 6 * sizeof(int)));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    d->sharded = true;
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps) {
+    if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
+    if (!d->comm) return fail(B200MPM_ERR_INVALID_ARGUMENT, "b200mpm_shard_comm_init has not been called");
+    CU_TRY(cudaSetDevice(p->device));
+    for (uint32_t s = 0; s < num_substeps; ++s) run_phase(p, d, PHASE_SHARDED);
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;
 }

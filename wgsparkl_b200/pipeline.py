@@ -69,6 +69,9 @@ EXPORTS = (
     "b200mpm_shard_impulses",
     "b200mpm_shard_step_end",
     "b200mpm_read_particles_unordered",
+    "b200mpm_nccl_unique_id",
+    "b200mpm_shard_comm_init",
+    "b200mpm_shard_step",
 )
 
 PARTICLE_RECORD_BYTES = 128  # B200MPM_PARTICLE_RECORD_BYTES
@@ -128,6 +131,9 @@ def load_library():
     L.b200mpm_shard_impulses.argtypes = [vp, vp, vp, i32]
     L.b200mpm_shard_step_end.argtypes = [vp, vp]
     L.b200mpm_read_particles_unordered.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
+    L.b200mpm_nccl_unique_id.argtypes = [vp, sz]
+    L.b200mpm_shard_comm_init.argtypes = [vp, vp, i32, i32, vp, u32, u32]
+    L.b200mpm_shard_step.argtypes = [vp, vp, u32]
     _lib = L
     return L
 
@@ -135,6 +141,12 @@ def load_library():
 def _check(code):
     if code != OK:
         raise B200MpmError(code, load_library().b200mpm_last_error().decode("utf-8", "replace"))
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check(load_library().b200mpm_nccl_unique_id(buf, 128))
+    return buf.raw
 
 
 class MpmPipeline:
@@ -340,6 +352,14 @@ class MpmData:
 
     def shard_step_end(self):
         _check(load_library().b200mpm_shard_step_end(self.pipeline._h, self._h))
+
+    def shard_comm_init(self, rank: int, world: int, unique_id: bytes, migration_cap: int, halo_cap: int):
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        _check(load_library().b200mpm_shard_comm_init(self.pipeline._h, self._h, rank, world, buf, migration_cap, halo_cap))
+
+    def shard_step(self, num_substeps: int):
+        """Whole sharded substeps (kernels + NCCL exchanges) from the native library, asynchronous."""
+        _check(load_library().b200mpm_shard_step(self.pipeline._h, self._h, int(num_substeps)))
 
     def read_particles_unordered(self):
         """(particles, ids) of the live particles in device order."""

@@ -76,7 +76,7 @@ class ShardedMpm:
 
     def __init__(self, scene: dict, rank: int, world: int, device: int, migration_cap: int = 16384,
                  halo_cap: Optional[int] = None, slack: float = 1.6, slabs: Optional[List[Tuple[int, int]]] = None,
-                 stream=None):
+                 stream=None, native: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -120,6 +120,15 @@ class ShardedMpm:
         # the impulse all-reduce is only needed if some body can react to an impulse
         self.needs_impulses = bool(len(b)) and bool(
             np.any(b["inv_mass"] != 0) or np.any(b["inv_inertia"] != 0) or np.any(b["linvel"] != 0) or np.any(b["angvel"] != 0))
+        # Native transport: the library owns an NCCL communicator and replays whole sharded substeps (kernels +
+        # send/recv groups + impulse all-reduce) from one CUDA graph; torch.distributed only ships the unique id.
+        self.native = bool(native and world > 1 and dist.is_available() and dist.is_initialized())
+        if self.native:
+            from .pipeline import nccl_unique_id
+
+            box = [nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.data.shard_comm_init(rank, world, box[0], migration_cap, halo_cap)
 
     def substep(self):
         with self.torch.cuda.stream(self.stream):
@@ -152,6 +161,9 @@ class ShardedMpm:
         d.shard_step_end()
 
     def step(self, substeps: int):
+        if self.native:
+            self.data.shard_step(substeps)
+            return
         for _ in range(substeps):
             self.substep()
 
@@ -201,7 +213,8 @@ class LocalSlabs:
         bx = particle_block_x(scene["particles"]["position"][:, 0], scene["cell_width"], scene["dim"])
         slabs = kw.pop("slabs", None) or partition_slabs(bx, world)
         self.stream = torch.cuda.Stream(device=device)  # all slabs share one stream: program order = data order
-        self.ranks = [ShardedMpm(scene, r, world, device, slabs=slabs, stream=self.stream, **kw) for r in range(world)]
+        self.ranks = [ShardedMpm(scene, r, world, device, slabs=slabs, stream=self.stream, native=False, **kw)
+                      for r in range(world)]
         self.n_global = len(scene["particles"])
 
     def substep(self):
