@@ -276,6 +276,13 @@ int b200mpm_nccl_unique_id(void* out, size_t bytes);
 int b200mpm_shard_comm_init(b200mpm_pipeline* p, b200mpm_data* d, int rank, int world, const void* unique_id,
                             uint32_t migration_cap_records, uint32_t halo_cap_blocks);
 int b200mpm_shard_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps);
+/* Optional, after b200mpm_shard_comm_init: replace the two NCCL send/recv groups of every substep by direct
+ * NVLink stores. Each rank exports a CUDA-IPC handle (64 bytes) of its receive arena, the handles of ALL ranks are
+ * gathered out of band, and each rank maps its two neighbours. The pack kernels then write the migration records
+ * and the halo blocks straight into the neighbour's memory and raise a sequence flag there; the unpack side spins
+ * on its local flag. (The impulse all-reduce stays on NCCL.) */
+int b200mpm_shard_p2p_export(b200mpm_pipeline* p, b200mpm_data* d, void* handle_out, size_t bytes);
+int b200mpm_shard_p2p_connect(b200mpm_pipeline* p, b200mpm_data* d, const void* handles, size_t num_handles);
 /* Live particles in device order with their ids (no un-permutation). */
 int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uint32_t* ids, size_t capacity,
                                      size_t* count);

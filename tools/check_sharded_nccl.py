@@ -25,17 +25,20 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ok = True
-    for name, scene, n, native in (
-        ("elastic, sliding in +x [native nccl]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, True),
-        ("sand + solids + bodies  [native nccl]", scenes.mixed_coupled_3d(12 * world, 12, 12, n_dynamic=2), 40, True),
-        ("elastic, sliding in +x [torch.dist ]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, False),
+    for name, scene, n, native, p2p in (
+        ("elastic, sliding in +x [nvlink p2p ]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, True, True),
+        ("sand + solids + bodies  [nvlink p2p ]", scenes.mixed_coupled_3d(12 * world, 12, 12, n_dynamic=2), 40, True, True),
+        ("elastic, sliding in +x [native nccl]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, True, False),
+        ("elastic, sliding in +x [torch.dist ]", scenes.elastic_cube_3d(16, y_offset=-5.0, nx=16 * world), 80, False, False),
     ):
         if name.startswith("elastic"):
             scene["particles"]["velocity"][:, 0] = 6.0
             scene["particles"]["velocity"][:, 1] = -2.0
         else:
             scene["bodies"]["translation"][2:, 1] = 12.0
-        sh = ShardedMpm(scene, rank, world, local, native=native)
+        sh = ShardedMpm(scene, rank, world, local, native=native, p2p=p2p)
+        if rank == 0 and p2p:
+            print('   p2p active:', getattr(sh, 'p2p', False), flush=True)
         n0 = sh.num_live()
         sh.step(n)
         sh.sync()

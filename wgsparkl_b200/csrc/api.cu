@@ -81,6 +81,12 @@ struct b200mpm_data {
     void* halo_recv[2] = {nullptr, nullptr};
     int* imp_buf = nullptr;
     uint32_t mig_cap = 0, halo_cap = 0;
+    // Peer-to-peer exchange (b200mpm_shard_p2p_export / _connect): one arena per rank, mapped by both neighbours.
+    //   arena = [flags: 4 x u32 (+pad to 256 B)] [mig from-left x2 parity] [mig from-right x2] [halo from-left x2] [halo from-right x2]
+    bool p2p_ready = false;
+    char* arena = nullptr;
+    char* peer_arena[2] = {nullptr, nullptr}; // -x / +x neighbour's arena (IPC mapping)
+    size_t arena_mig_bytes = 0, arena_halo_bytes = 0;
     bool bodies_react = false; // some body can react to an impulse (mass or motion): the impulse all-reduce is needed
     uint32_t n_live_host = 0; // host mirror of counters->n_live (sharded runs track it)
     bool sharded = false;
@@ -210,15 +216,42 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
             }
             nc.GroupEnd();
         };
-        launch_emigrate(c, dev, d->cur, d->mig_send[0], d->mig_send[1], d->mig_cap);
-        exchange(d->mig_send, d->mig_recv, mig_bytes);
-        if (left >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[0], d->mig_cap);
-        if (right >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[1], d->mig_cap);
-        enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
-        launch_halo_pack(c, dev, d->halo_send[0], d->halo_send[1], d->halo_cap);
-        exchange(d->halo_send, d->halo_recv, halo_bytes);
-        if (left >= 0) launch_halo_add(c, dev, d->halo_recv[0], d->halo_cap);
-        if (right >= 0) launch_halo_add(c, dev, d->halo_recv[1], d->halo_cap);
+        if (d->p2p_ready) {
+            // Peer-to-peer: the pack kernels store straight into the neighbour's receive buffers over NVLink.
+            const int par = d->cur; // double buffering by substep parity
+            auto mig_buf = [&](char* arena, int from_dir) { return arena + 256 + (size_t)(from_dir * 2 + par) * d->arena_mig_bytes; };
+            auto halo_buf = [&](char* arena, int from_dir) {
+                return arena + 256 + 4 * d->arena_mig_bytes + (size_t)(from_dir * 2 + par) * d->arena_halo_bytes;
+            };
+            auto flag = [&](char* arena, int from_dir, int kind) { return (uint32_t*)arena + from_dir * 2 + kind; };
+            char* pl = d->peer_arena[0];
+            char* pr = d->peer_arena[1];
+            // I am the +x neighbour of `left` (its from-right buffers) and the -x neighbour of `right`.
+            void* ml = pl ? (void*)mig_buf(pl, 1) : d->mig_send[0];
+            void* mr = pr ? (void*)mig_buf(pr, 0) : d->mig_send[1];
+            void* hl = pl ? (void*)halo_buf(pl, 1) : d->halo_send[0];
+            void* hr = pr ? (void*)halo_buf(pr, 0) : d->halo_send[1];
+            launch_shard_tick(c, dev);
+            launch_emigrate(c, dev, d->cur, ml, mr, d->mig_cap, pl ? flag(pl, 1, 0) : nullptr, pr ? flag(pr, 0, 0) : nullptr, true);
+            launch_shard_wait(c, dev, pl ? flag(d->arena, 0, 0) : nullptr, pr ? flag(d->arena, 1, 0) : nullptr);
+            if (left >= 0) launch_immigrate(c, dev, d->cur, mig_buf(d->arena, 0), d->mig_cap);
+            if (right >= 0) launch_immigrate(c, dev, d->cur, mig_buf(d->arena, 1), d->mig_cap);
+            enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
+            launch_halo_pack(c, dev, hl, hr, d->halo_cap, pl ? flag(pl, 1, 1) : nullptr, pr ? flag(pr, 0, 1) : nullptr, true);
+            launch_shard_wait(c, dev, pl ? flag(d->arena, 0, 1) : nullptr, pr ? flag(d->arena, 1, 1) : nullptr);
+            if (left >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 0), d->halo_cap);
+            if (right >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 1), d->halo_cap);
+        } else {
+            launch_emigrate(c, dev, d->cur, d->mig_send[0], d->mig_send[1], d->mig_cap);
+            exchange(d->mig_send, d->mig_recv, mig_bytes);
+            if (left >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[0], d->mig_cap);
+            if (right >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[1], d->mig_cap);
+            enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
+            launch_halo_pack(c, dev, d->halo_send[0], d->halo_send[1], d->halo_cap);
+            exchange(d->halo_send, d->halo_recv, halo_bytes);
+            if (left >= 0) launch_halo_add(c, dev, d->halo_recv[0], d->halo_cap);
+            if (right >= 0) launch_halo_add(c, dev, d->halo_recv[1], d->halo_cap);
+        }
         if (d->bodies_react) {
             launch_impulses_io(c, dev, d->imp_buf, 0);
             nc.AllReduce(d->imp_buf, d->imp_buf, B200MPM_MAX_BODIES * 6, ncclInt32, ncclSum, d->comm, main); // exact
@@ -693,6 +726,9 @@ void b200mpm_data_destroy(b200mpm_data* d) {
         if (d->halo_recv[k]) cudaFree(d->halo_recv[k]);
     }
     if (d->imp_buf) cudaFree(d->imp_buf);
+    for (int k = 0; k < 2; ++k)
+        if (d->peer_arena[k]) cudaIpcCloseMemHandle(d->peer_arena[k]);
+    if (d->arena) cudaFree(d->arena);
     if (d->side) cudaStreamDestroy(d->side);
     for (void* p : d->allocs) cudaFree(p);
     if (d->staging) cudaFree(d->staging);
@@ -1088,6 +1124,55 @@ int b200mpm_shard_comm_init(b200mpm_pipeline* p, b200mpm_data* d, int rank, int 
     CU_TRY(cudaMalloc(&d->imp_buf, B200MPM_MAX_BODIES * 6 * sizeof(int)));
     CU_TRY(cudaStreamSynchronize(p->stream));
     d->sharded = true;
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_p2p_export(b200mpm_pipeline* p, b200mpm_data* d, void* handle_out, size_t bytes) {
+    if (!p || !d || d->pipe != p || !handle_out || bytes < sizeof(cudaIpcMemHandle_t))
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "need a 64-byte handle buffer");
+    if (!d->comm) return fail(B200MPM_ERR_INVALID_ARGUMENT, "b200mpm_shard_comm_init has not been called");
+    if (d->arena) return fail(B200MPM_ERR_INVALID_ARGUMENT, "arena already exported");
+    CU_TRY(cudaSetDevice(p->device));
+    d->arena_mig_bytes = (B200MPM_SHARD_HEADER_BYTES + (size_t)d->mig_cap * B200MPM_PARTICLE_RECORD_BYTES + 255) & ~(size_t)255;
+    d->arena_halo_bytes = (B200MPM_SHARD_HEADER_BYTES + (size_t)d->halo_cap * B200MPM_HALO_BLOCK_BYTES + 255) & ~(size_t)255;
+    const size_t total = 256 + 4 * d->arena_mig_bytes + 4 * d->arena_halo_bytes;
+    CU_TRY(cudaMalloc((void**)&d->arena, total));
+    CU_TRY(cudaMemset(d->arena, 0, total));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, d->arena));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return B200MPM_OK;
+}
+
+int b200mpm_shard_p2p_connect(b200mpm_pipeline* p, b200mpm_data* d, const void* handles, size_t num_handles) {
+    if (!p || !d || d->pipe != p || !handles) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!d->arena || (int)num_handles != d->world) return fail(B200MPM_ERR_INVALID_ARGUMENT, "export first; one handle per rank");
+    CU_TRY(cudaSetDevice(p->device));
+    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)handles;
+    const int nbr[2] = {d->rank - 1, d->rank + 1};
+    for (int k = 0; k < 2; ++k) {
+        if (nbr[k] < 0 || nbr[k] >= d->world) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, hs + nbr[k], sizeof(h));
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < k; ++j)
+                if (d->peer_arena[j]) {
+                    cudaIpcCloseMemHandle(d->peer_arena[j]);
+                    d->peer_arena[j] = nullptr;
+                }
+            return fail(B200MPM_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        }
+        d->peer_arena[k] = (char*)ptr;
+    }
+    for (auto& gp : d->graph_exec)
+        if (gp[PHASE_SHARDED]) {
+            cudaGraphExecDestroy(gp[PHASE_SHARDED]);
+            gp[PHASE_SHARDED] = nullptr;
+        }
+    d->p2p_ready = true;
     return B200MPM_OK;
 }
 

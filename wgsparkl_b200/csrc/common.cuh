@@ -97,6 +97,7 @@ struct Counters {
     uint32_t n_live; // particles currently held (== n unless the data is a slab of a sharded run)
     uint32_t send_count[2]; // emigrants packed for the -x / +x neighbour (sharded runs)
     uint32_t halo_count[2]; // blocks packed for the -x / +x neighbour (sharded runs)
+    uint32_t shard_seq; // substep sequence number of the peer-to-peer exchange flags
 };
 
 // ---- all device pointers of one MpmData --------------------------------------------------

@@ -119,6 +119,40 @@ __global__ void k_write_headers(Counters* c, void* left, void* right, uint32_t c
     ((ShardHeader*)right)->count = min(cnt[1], cap);
     if (cnt[0] > cap || cnt[1] > cap) c->overflow = 2u;
 }
+// ---- peer-to-peer exchange (NVLink stores into the neighbour's memory instead of NCCL send/recv) -------------
+// The pack kernels above are handed pointers INTO THE NEIGHBOUR'S receive buffers (CUDA IPC mappings), so the
+// records cross NVLink as plain stores while they are produced. k_publish then stores the record counts and,
+// after a system-scope fence, the substep sequence number into the neighbour's flag word; the neighbour's
+// k_wait spins on its local flag before its unpack kernels run. Buffers are double-buffered by substep parity
+// (a rank cannot get more than one exchange ahead of its neighbour).
+__global__ void k_shard_tick(Counters* c) { c->shard_seq += 1u; }
+
+__global__ void k_publish(Counters* c, void* left, void* right, uint32_t cap, int which, uint32_t* left_flag,
+                          uint32_t* right_flag) {
+    const uint32_t* cnt = which ? c->halo_count : c->send_count;
+    if (cnt[0] > cap || cnt[1] > cap) c->overflow = 2u;
+    const uint32_t seq = c->shard_seq;
+    if (left_flag) {
+        ((ShardHeader*)left)->count = min(cnt[0], cap);
+        __threadfence_system();
+        *((volatile uint32_t*)left_flag) = seq;
+    }
+    if (right_flag) {
+        ((ShardHeader*)right)->count = min(cnt[1], cap);
+        __threadfence_system();
+        *((volatile uint32_t*)right_flag) = seq;
+    }
+}
+
+__global__ void k_wait(const Counters* c, const uint32_t* from_left, const uint32_t* from_right) {
+    const uint32_t seq = c->shard_seq;
+    if (from_left)
+        while (*((volatile const uint32_t*)from_left) < seq) __nanosleep(200);
+    if (from_right)
+        while (*((volatile const uint32_t*)from_right) < seq) __nanosleep(200);
+    __threadfence_system();
+}
+
 // After a substep the next buffer holds the sorted live particles in [0, total) and the parked (dead) ones after:
 // dropping the tail removes the emigrants.
 __global__ void k_drop_dead_tail(DeviceData d) {
@@ -183,14 +217,24 @@ __global__ void k_impulses_io(DeviceData d, int* buf, int write) {
 
 static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
 
-void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap) {
+void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap,
+                     uint32_t* left_flag, uint32_t* right_flag, bool p2p) {
     k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
     if (d.n) {
         if (c.dim == 2) k_emigrate<2><<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, left, right, cap);
         else k_emigrate<3><<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, left, right, cap);
     }
-    k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 0);
+    if (p2p) k_publish<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 0, left_flag, right_flag);
+    else k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 0);
     *c.launch_counter += 3;
+}
+void launch_shard_tick(const LaunchCfg& c, const DeviceData& d) {
+    k_shard_tick<<<1, 1, 0, c.stream>>>(d.counters);
+    ++*c.launch_counter;
+}
+void launch_shard_wait(const LaunchCfg& c, const DeviceData& d, const uint32_t* from_left, const uint32_t* from_right) {
+    k_wait<<<1, 1, 0, c.stream>>>(d.counters, from_left, from_right);
+    ++*c.launch_counter;
 }
 void launch_immigrate(const LaunchCfg& c, const DeviceData& d, int cur, const void* in, uint32_t cap) {
     if (cap == 0) return;
@@ -203,10 +247,12 @@ void launch_drop_dead_tail(const LaunchCfg& c, const DeviceData& d) {
     k_drop_dead_tail<<<1, 1, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
-void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap) {
+void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap, uint32_t* left_flag,
+                      uint32_t* right_flag, bool p2p) {
     k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
     k_halo_pack<<<c.num_sms * 8, CELLS_PER_BLOCK, 0, c.stream>>>(d, left, right, cap);
-    k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 1);
+    if (p2p) k_publish<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 1, left_flag, right_flag);
+    else k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 1);
     *c.launch_counter += 3;
 }
 void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap) {

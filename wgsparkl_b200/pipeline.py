@@ -72,6 +72,8 @@ EXPORTS = (
     "b200mpm_nccl_unique_id",
     "b200mpm_shard_comm_init",
     "b200mpm_shard_step",
+    "b200mpm_shard_p2p_export",
+    "b200mpm_shard_p2p_connect",
 )
 
 PARTICLE_RECORD_BYTES = 128  # B200MPM_PARTICLE_RECORD_BYTES
@@ -134,6 +136,8 @@ def load_library():
     L.b200mpm_nccl_unique_id.argtypes = [vp, sz]
     L.b200mpm_shard_comm_init.argtypes = [vp, vp, i32, i32, vp, u32, u32]
     L.b200mpm_shard_step.argtypes = [vp, vp, u32]
+    L.b200mpm_shard_p2p_export.argtypes = [vp, vp, vp, sz]
+    L.b200mpm_shard_p2p_connect.argtypes = [vp, vp, vp, sz]
     _lib = L
     return L
 
@@ -356,6 +360,15 @@ class MpmData:
     def shard_comm_init(self, rank: int, world: int, unique_id: bytes, migration_cap: int, halo_cap: int):
         buf = ctypes.create_string_buffer(unique_id, 128)
         _check(load_library().b200mpm_shard_comm_init(self.pipeline._h, self._h, rank, world, buf, migration_cap, halo_cap))
+
+    def shard_p2p_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        _check(load_library().b200mpm_shard_p2p_export(self.pipeline._h, self._h, buf, 64))
+        return buf.raw
+
+    def shard_p2p_connect(self, handles):
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * len(handles))
+        _check(load_library().b200mpm_shard_p2p_connect(self.pipeline._h, self._h, blob, len(handles)))
 
     def shard_step(self, num_substeps: int):
         """Whole sharded substeps (kernels + NCCL exchanges) from the native library, asynchronous."""

@@ -76,7 +76,7 @@ class ShardedMpm:
 
     def __init__(self, scene: dict, rank: int, world: int, device: int, migration_cap: int = 16384,
                  halo_cap: Optional[int] = None, slack: float = 1.6, slabs: Optional[List[Tuple[int, int]]] = None,
-                 stream=None, native: bool = True):
+                 stream=None, native: bool = True, p2p: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -129,6 +129,21 @@ class ShardedMpm:
             box = [nccl_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             self.data.shard_comm_init(rank, world, box[0], migration_cap, halo_cap)
+            self.p2p = False
+            if p2p:
+                # NVLink peer-to-peer stores instead of NCCL send/recv: exchange CUDA-IPC handles of the arenas.
+                handles = [None] * world
+                dist.all_gather_object(handles, self.data.shard_p2p_export())
+                try:
+                    self.data.shard_p2p_connect(handles)
+                    ok = 1
+                except Exception:
+                    ok = 0
+                flag = torch.tensor([ok], device="cuda:%d" % device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
+                self.p2p = bool(flag.item())
+                if not self.p2p and ok:
+                    raise RuntimeError("peer-to-peer mapping succeeded on some ranks only")
 
     def substep(self):
         with self.torch.cuda.stream(self.stream):
