@@ -233,14 +233,21 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
             void* hr = pr ? (void*)halo_buf(pr, 0) : d->halo_send[1];
             launch_shard_tick(c, dev);
             launch_emigrate(c, dev, d->cur, ml, mr, d->mig_cap, pl ? flag(pl, 1, 0) : nullptr, pr ? flag(pr, 0, 0) : nullptr, true);
-            launch_shard_wait(c, dev, pl ? flag(d->arena, 0, 0) : nullptr, pr ? flag(d->arena, 1, 0) : nullptr);
-            if (left >= 0) launch_immigrate(c, dev, d->cur, mig_buf(d->arena, 0), d->mig_cap);
-            if (right >= 0) launch_immigrate(c, dev, d->cur, mig_buf(d->arena, 1), d->mig_cap);
+            launch_immigrate_p2p(c, dev, d->cur, pl ? mig_buf(d->arena, 0) : nullptr, pr ? mig_buf(d->arena, 1) : nullptr,
+                                 flag(d->arena, 0, 0), flag(d->arena, 1, 0), d->mig_cap);
             enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
             launch_halo_pack(c, dev, hl, hr, d->halo_cap, pl ? flag(pl, 1, 1) : nullptr, pr ? flag(pr, 0, 1) : nullptr, true);
-            launch_shard_wait(c, dev, pl ? flag(d->arena, 0, 1) : nullptr, pr ? flag(d->arena, 1, 1) : nullptr);
-            if (left >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 0), d->halo_cap);
-            if (right >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 1), d->halo_cap);
+            if (left >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 0), d->halo_cap, flag(d->arena, 0, 1));
+            if (right >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 1), d->halo_cap, flag(d->arena, 1, 1));
+            if (d->bodies_react) {
+                launch_impulses_io(c, dev, d->imp_buf, 0);
+                nc.AllReduce(d->imp_buf, d->imp_buf, B200MPM_MAX_BODIES * 6, ncclInt32, ncclSum, d->comm, main); // exact
+                launch_impulses_io(c, dev, d->imp_buf, 1);
+            }
+            // (the dead tail of this substep is dropped by the next k_shard_tick)
+            launch_g2p_update(c, dev, d->cur);
+            launch_integrate_bodies(c, dev);
+            return;
         } else {
             launch_emigrate(c, dev, d->cur, d->mig_send[0], d->mig_send[1], d->mig_cap);
             exchange(d->mig_send, d->mig_recv, mig_bytes);

@@ -98,6 +98,7 @@ struct Counters {
     uint32_t send_count[2]; // emigrants packed for the -x / +x neighbour (sharded runs)
     uint32_t halo_count[2]; // blocks packed for the -x / +x neighbour (sharded runs)
     uint32_t shard_seq; // substep sequence number of the peer-to-peer exchange flags
+    uint32_t n_base; // live count at the start of the substep: where the immigrants are appended
 };
 
 // ---- all device pointers of one MpmData --------------------------------------------------

@@ -44,12 +44,13 @@ void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b
 void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap,
                      uint32_t* left_flag = nullptr, uint32_t* right_flag = nullptr, bool p2p = false);
 void launch_shard_tick(const LaunchCfg& c, const DeviceData& d);
-void launch_shard_wait(const LaunchCfg& c, const DeviceData& d, const uint32_t* from_left, const uint32_t* from_right);
+void launch_immigrate_p2p(const LaunchCfg& c, const DeviceData& d, int cur, const void* from_left, const void* from_right,
+                          const uint32_t* flag_left, const uint32_t* flag_right, uint32_t cap);
 void launch_immigrate(const LaunchCfg& c, const DeviceData& d, int cur, const void* in, uint32_t cap);
 void launch_drop_dead_tail(const LaunchCfg& c, const DeviceData& d);
 void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap,
                       uint32_t* left_flag = nullptr, uint32_t* right_flag = nullptr, bool p2p = false);
-void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap);
+void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap, const uint32_t* flag = nullptr);
 void launch_impulses_io(const LaunchCfg& c, const DeviceData& d, int* buf, int write);
 void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_info* blocks, b200mpm_node* nodes,
                         uint32_t max_blocks);

@@ -125,7 +125,61 @@ __global__ void k_write_headers(Counters* c, void* left, void* right, uint32_t c
 // after a system-scope fence, the substep sequence number into the neighbour's flag word; the neighbour's
 // k_wait spins on its local flag before its unpack kernels run. Buffers are double-buffered by substep parity
 // (a rank cannot get more than one exchange ahead of its neighbour).
-__global__ void k_shard_tick(Counters* c) { c->shard_seq += 1u; }
+// First kernel of a peer-to-peer sharded substep: drops the dead (emigrated) tail left by the previous substep,
+// resets the pack counters, snapshots the live count (immigrants are appended there) and advances the sequence.
+__global__ void k_shard_tick(DeviceData d) {
+    Counters* c = d.counters;
+    if (c->shard_seq > 0u) {
+        const uint32_t nb = min(c->num_active_blocks, d.capacity);
+        c->n_live = d.cell_start[nb * CELLS_PER_BLOCK];
+    }
+    c->send_count[0] = c->send_count[1] = 0;
+    c->halo_count[0] = c->halo_count[1] = 0;
+    c->n_base = c->n_live;
+    c->shard_seq += 1u;
+}
+
+__device__ __forceinline__ void shard_wait_flag(const uint32_t* flag, uint32_t seq) {
+    if (threadIdx.x == 0) {
+        while (*((volatile const uint32_t*)flag) < seq) __nanosleep(100);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
+// Peer-to-peer immigration of BOTH neighbours' records in one kernel: waits for the neighbours' flags, appends the
+// -x records at n_base and the +x records right after, and publishes the new live count.
+template <int D>
+__global__ void __launch_bounds__(256) k_immigrate_p2p(DeviceData d, int cur, const void* from_left, const void* from_right,
+                                                       const uint32_t* flag_left, const uint32_t* flag_right, uint32_t cap) {
+    const uint32_t seq = d.counters->shard_seq;
+    if (from_left) shard_wait_flag(flag_left, seq);
+    if (from_right) shard_wait_flag(flag_right, seq);
+    const uint32_t cl = from_left ? min(((const ShardHeader*)from_left)->count, cap) : 0u;
+    const uint32_t cr = from_right ? min(((const ShardHeader*)from_right)->count, cap) : 0u;
+    const uint32_t n0 = d.counters->n_base;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) d.counters->n_live = min(n0 + cl + cr, d.n); // nobody reads n_live in this kernel
+    if (i >= cl + cr) return;
+    const uint32_t dst = n0 + i;
+    if (dst >= d.n) {
+        d.counters->overflow = 3u;
+        return;
+    }
+    const ParticleRecord r = (i < cl) ? shard_records<ParticleRecord>(from_left)[i] : shard_records<ParticleRecord>(from_right)[i - cl];
+    d.pos4[cur][dst] = r.pos4;
+    d.vel4[cur][dst] = r.vel4;
+    d.Fa[cur][dst] = r.Fa;
+    d.Ca[cur][dst] = r.Ca;
+    if (D == 3) {
+        d.Fb[cur][dst] = r.Fb;
+        d.Cb[cur][dst] = r.Cb;
+        d.Fc[cur][dst] = r.Fc;
+        d.Cc[cur][dst] = r.Cc;
+    }
+    if (d.has_bodies) d.cdf_aff[cur][dst] = r.cdf_aff;
+    if (d.has_plastic) d.plastic[cur][dst] = r.plastic;
+}
 
 __global__ void k_publish(Counters* c, void* left, void* right, uint32_t cap, int which, uint32_t* left_flag,
                           uint32_t* right_flag) {
@@ -185,7 +239,8 @@ __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_halo_pack(DeviceData d, voi
 
 // Adds the neighbour's partial sums to the blocks this rank also holds.
 template <int D>
-__global__ void __launch_bounds__(CELLS_PER_BLOCK) k_halo_add(DeviceData d, const void* buf, uint32_t cap) {
+__global__ void __launch_bounds__(CELLS_PER_BLOCK) k_halo_add(DeviceData d, const void* buf, uint32_t cap, const uint32_t* flag) {
+    if (flag) shard_wait_flag(flag, d.counters->shard_seq); // peer-to-peer: the neighbour raises it after its stores
     const uint32_t count = min(((const ShardHeader*)buf)->count, cap);
     const HaloBlock* in = shard_records<HaloBlock>(buf);
     for (uint32_t k = blockIdx.x; k < count; k += gridDim.x) {
@@ -219,7 +274,7 @@ static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b)
 
 void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap,
                      uint32_t* left_flag, uint32_t* right_flag, bool p2p) {
-    k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
+    if (!p2p) k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters); // (the p2p path resets them in k_shard_tick)
     if (d.n) {
         if (c.dim == 2) k_emigrate<2><<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, left, right, cap);
         else k_emigrate<3><<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, left, right, cap);
@@ -229,11 +284,15 @@ void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* lef
     *c.launch_counter += 3;
 }
 void launch_shard_tick(const LaunchCfg& c, const DeviceData& d) {
-    k_shard_tick<<<1, 1, 0, c.stream>>>(d.counters);
+    k_shard_tick<<<1, 1, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
-void launch_shard_wait(const LaunchCfg& c, const DeviceData& d, const uint32_t* from_left, const uint32_t* from_right) {
-    k_wait<<<1, 1, 0, c.stream>>>(d.counters, from_left, from_right);
+void launch_immigrate_p2p(const LaunchCfg& c, const DeviceData& d, int cur, const void* from_left, const void* from_right,
+                          const uint32_t* flag_left, const uint32_t* flag_right, uint32_t cap) {
+    if (!from_left && !from_right) return;
+    const uint32_t threads = cap * 2;
+    if (c.dim == 2) k_immigrate_p2p<2><<<div_up(threads, 256), 256, 0, c.stream>>>(d, cur, from_left, from_right, flag_left, flag_right, cap);
+    else k_immigrate_p2p<3><<<div_up(threads, 256), 256, 0, c.stream>>>(d, cur, from_left, from_right, flag_left, flag_right, cap);
     ++*c.launch_counter;
 }
 void launch_immigrate(const LaunchCfg& c, const DeviceData& d, int cur, const void* in, uint32_t cap) {
@@ -249,17 +308,17 @@ void launch_drop_dead_tail(const LaunchCfg& c, const DeviceData& d) {
 }
 void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap, uint32_t* left_flag,
                       uint32_t* right_flag, bool p2p) {
-    k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
+    if (!p2p) k_zero_shard_counters<<<1, 1, 0, c.stream>>>(d.counters);
     k_halo_pack<<<c.num_sms * 8, CELLS_PER_BLOCK, 0, c.stream>>>(d, left, right, cap);
     if (p2p) k_publish<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 1, left_flag, right_flag);
     else k_write_headers<<<1, 1, 0, c.stream>>>(d.counters, left, right, cap, 1);
     *c.launch_counter += 3;
 }
-void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap) {
+void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap, const uint32_t* flag) {
     if (cap == 0) return;
     int grid = (int)(cap < (uint32_t)(c.num_sms * 8) ? cap : (uint32_t)(c.num_sms * 8));
-    if (c.dim == 2) k_halo_add<2><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d, in, cap);
-    else k_halo_add<3><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d, in, cap);
+    if (c.dim == 2) k_halo_add<2><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d, in, cap, flag);
+    else k_halo_add<3><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d, in, cap, flag);
     ++*c.launch_counter;
 }
 void launch_impulses_io(const LaunchCfg& c, const DeviceData& d, int* buf, int write) {

@@ -186,6 +186,9 @@ class ShardedMpm:
         self.torch.cuda.synchronize()
 
     def num_live(self) -> int:
+        if getattr(self, "p2p", False):
+            # the peer-to-peer path drops the emigrated tail lazily (at the next substep): count the live ids
+            return int(len(self.data.read_particles_unordered()[1]))
         return self.data.num_live()
 
     def gather_particles(self):
