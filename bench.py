@@ -155,7 +155,7 @@ def run_ours(args):
         pipe, data = sharded.pipe, sharded.data
     poses, vels = frame_io_arrays(scene)
     n_local = data.num_particles
-    host_pos = torch.empty((max(n_local, 1), 4), dtype=torch.float32).pin_memory().numpy()
+    host_pos = torch.empty((max(data.particle_capacity, 1), 4), dtype=torch.float32).pin_memory().numpy()
 
     def barrier():
         if world > 1:
@@ -190,7 +190,7 @@ def run_ours(args):
         if sharded is None:
             data.read_positions(host_pos)  # D2H: the step's result, into pinned host memory
         else:
-            data.read_particles_unordered()  # D2H: this rank's slab
+            data.read_positions_unordered(host_pos)  # D2H: this rank's slab, into pinned host memory
 
     for _ in range(args.warmup):
         frame_device()
@@ -209,7 +209,7 @@ def run_ours(args):
     e2e_value = n_total * spf * args.steps / (ms_e2e * 1e-3)
     nb = len(scene["bodies"])
     h2d = nb * (poses.dtype.itemsize + vels.dtype.itemsize)
-    d2h = nb * poses.dtype.itemsize + (n_local * 16 if sharded is None else n_local * 200)
+    d2h = nb * poses.dtype.itemsize + n_local * 16
 
     roof = None
     nblocks, overflow = data.status()

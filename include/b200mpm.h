@@ -283,6 +283,9 @@ int b200mpm_shard_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_subste
  * on its local flag. (The impulse all-reduce stays on NCCL.) */
 int b200mpm_shard_p2p_export(b200mpm_pipeline* p, b200mpm_data* d, void* handle_out, size_t bytes);
 int b200mpm_shard_p2p_connect(b200mpm_pipeline* p, b200mpm_data* d, const void* handles, size_t num_handles);
+/* Positions of the live particles in device order: xyz + the particle id's bits in w (B200MPM_NONE for a
+ * particle that has emigrated). `out` holds 4 * capacity floats. */
+int b200mpm_read_positions_unordered(b200mpm_data* d, float* out, size_t capacity, size_t* count);
 /* Live particles in device order with their ids (no un-permutation). */
 int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uint32_t* ids, size_t capacity,
                                      size_t* count);

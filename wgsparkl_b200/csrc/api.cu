@@ -901,6 +901,25 @@ int b200mpm_read_positions(b200mpm_data* d, float* out) {
     return B200MPM_OK;
 }
 
+int b200mpm_read_positions_unordered(b200mpm_data* d, float* out, size_t capacity, size_t* count) {
+    if (!d || !count) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
+    CU_TRY(cudaSetDevice(p->device));
+    int r = ensure_staging(d, (size_t)d->dev.n * sizeof(float4) + 256);
+    if (r) return r;
+    launch_gather_positions(p->cfg(), d->dev, d->cur, (float4*)d->staging, 1);
+    Counters c;
+    CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    *count = c.n_live;
+    if (c.n_live == 0) return B200MPM_OK;
+    if (!out || capacity < c.n_live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "output too small");
+    CU_TRY(cudaMemcpyAsync(out, d->staging, (size_t)c.n_live * sizeof(float4), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
 int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out) {
     if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (d->dev.n == 0) return B200MPM_OK;

@@ -37,7 +37,7 @@ void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len,
 uint32_t scan_num_tiles(uint64_t len);
 
 // Readback helpers (device -> staging in caller order).
-void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out);
+void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out, int unordered = 0);
 void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out, uint32_t* ids);
 
 // Slab sharding (shard.cu)

@@ -260,12 +260,17 @@ __global__ void k_read_poses(DeviceData d, b200mpm_pose* poses, b200mpm_velocity
 }
 
 // ---- particle / grid readback in the caller's layout ---------------------------------------------------------
-__global__ void k_gather_positions(DeviceData d, int cur, float4* out) {
+__global__ void k_gather_positions(DeviceData d, int cur, float4* out, int unordered) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.counters->n_live) return;
     float4 p = d.pos4[cur][i];
     uint32_t orig = __float_as_uint(d.vel4[cur][i].w);
-    out[orig] = make_float4(p.x, p.y, p.z, 0.0f);
+    if (unordered) { // device order; w carries the particle id (NONE for an emigrated particle)
+        uint32_t id = (__float_as_uint(p.w) & FLAG_DEAD) ? NONE : orig;
+        out[i] = make_float4(p.x, p.y, p.z, __uint_as_float(id));
+    } else {
+        out[orig] = make_float4(p.x, p.y, p.z, 0.0f);
+    }
 }
 
 template <int D>
@@ -395,9 +400,9 @@ void launch_integrate_bodies(const LaunchCfg& c, const DeviceData& d) {
     else k_integrate_bodies<3><<<1, 32, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
-void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out) {
+void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out, int unordered) {
     if (d.n == 0) return;
-    k_gather_positions<<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, out);
+    k_gather_positions<<<div_up(d.n, 256), 256, 0, c.stream>>>(d, cur, out, unordered);
     ++*c.launch_counter;
 }
 void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out, uint32_t* ids) {

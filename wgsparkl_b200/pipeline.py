@@ -69,6 +69,7 @@ EXPORTS = (
     "b200mpm_shard_impulses",
     "b200mpm_shard_step_end",
     "b200mpm_read_particles_unordered",
+    "b200mpm_read_positions_unordered",
     "b200mpm_nccl_unique_id",
     "b200mpm_shard_comm_init",
     "b200mpm_shard_step",
@@ -133,6 +134,7 @@ def load_library():
     L.b200mpm_shard_impulses.argtypes = [vp, vp, vp, i32]
     L.b200mpm_shard_step_end.argtypes = [vp, vp]
     L.b200mpm_read_particles_unordered.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
+    L.b200mpm_read_positions_unordered.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
     L.b200mpm_nccl_unique_id.argtypes = [vp, sz]
     L.b200mpm_shard_comm_init.argtypes = [vp, vp, i32, i32, vp, u32, u32]
     L.b200mpm_shard_step.argtypes = [vp, vp, u32]
@@ -373,6 +375,14 @@ class MpmData:
     def shard_step(self, num_substeps: int):
         """Whole sharded substeps (kernels + NCCL exchanges) from the native library, asynchronous."""
         _check(load_library().b200mpm_shard_step(self.pipeline._h, self._h, int(num_substeps)))
+
+    def read_positions_unordered(self, out: Optional[np.ndarray] = None):
+        """(n_live, 4) float32: xyz + id bits in w (abi.NONE for emigrated particles), device order."""
+        if out is None:
+            out = np.zeros((self.particle_capacity, 4), dtype=np.float32)
+        n = ctypes.c_size_t(0)
+        _check(load_library().b200mpm_read_positions_unordered(self._h, abi.ptr(out), out.shape[0], ctypes.byref(n)))
+        return out[: n.value]
 
     def read_particles_unordered(self):
         """(particles, ids) of the live particles in device order."""
