@@ -11,7 +11,8 @@ from collections import defaultdict
 
 rep, kre, cubin, mangled = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre, "--launch-count", "1"],
+import os
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre, "--launch-skip", os.environ.get("NCU_SKIP", "0"), "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)

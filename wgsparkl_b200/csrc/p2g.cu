@@ -25,9 +25,7 @@
 
 namespace b2 {
 
-constexpr int P2G_THREADS = CELLS_PER_BLOCK;
-constexpr int P2G_CHUNK = 512; // particles staged per pass (8 per cell = the reference's seeding density)
-constexpr int P2G_CHUNK_CPIC = 384;
+constexpr int P2G_CHUNK = 256; // particles staged per pass and warp: 32 cells x 8 (the reference's seeding density)
 
 enum { P2G_FAST = 0, P2G_CPIC_MOMENTUM = 1, P2G_CPIC_IMPULSE = 2 };
 
@@ -168,17 +166,18 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
     return any_incompatible;
 }
 
-// CPIC = false: blocks whose tile holds no collider (block_flags == 0, or no bodies at all).
-// CPIC = true : the few blocks next to a collider (block_flags != 0).
+// One WARP owns half a block (32 cells, one lane per cell) and is an independent worker: its own staging
+// buffers, its own (BLOCK+2)^D tile, its own dynamic work queue position — there is no CTA-wide barrier anywhere
+// in the kernel (a CTA is a single warp), so some warps stage while others compute.
+//   CPIC = false: blocks whose tile holds no collider (block_flags == 0, or no bodies at all).
+//   CPIC = true : the few blocks next to a collider (compact list), further split into PARTS work items.
 template <int D, bool CPIC>
-__global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
+__global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, LB = Dim<D>::LOG_BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC, NBH = Dim<D>::NBH;
     constexpr int WI = (D == 3) ? 6 : 3; // impulse components per node
-    // 48 KB of static shared memory: the collider-side instantiation carries the cdf tile and the impulse
-    // tile, so it stages fewer particles per pass.
-    constexpr int CHUNK = CPIC ? P2G_CHUNK_CPIC : P2G_CHUNK;
-    constexpr int PER_THREAD = CHUNK / P2G_THREADS;
+    constexpr int CHUNK = P2G_CHUNK; // particles staged per pass = 8 per cell, the reference's seeding density
+    constexpr int HALF = CELLS_PER_BLOCK / 2;
     __shared__ float4 tile[TC];
     __shared__ float4 sp[CHUNK], sv[CHUNK], sa[CHUNK];
     __shared__ float4 sb[D == 3 ? CHUNK : 1];
@@ -186,17 +185,14 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
     __shared__ uint32_t s_ids[CHUNK];
     __shared__ uint32_t s_aff[CPIC ? CHUNK : 1]; // this substep's particle affinities (k_g2p_cdf, by sorted slot)
     __shared__ uint32_t s_nbr[NA];
-    __shared__ uint32_t s_next;
     __shared__ uint2 tcdf[CPIC ? TC : 1];
     __shared__ float timp[CPIC ? TC * WI : 1];
 
-    const int t = threadIdx.x;
-    const int lx = t & (B - 1), ly = (t >> LB) & (B - 1), lz = (D == 3) ? (t >> (2 * LB)) : 0;
-    const int tb = lx + T * ly + T * T * lz;
-    // A collider-side block is split into PARTS work items (each takes every cell's PARTS-th share of the
-    // run): these blocks are few, so their per-block latency — not throughput — is what shows up.
-    constexpr uint32_t PARTS = CPIC ? 4u : 1u;
-    const uint32_t nwork = CPIC ? d.counters->num_cpic_blocks * PARTS : min(d.counters->num_active_blocks, d.capacity);
+    const int lane = threadIdx.x;
+    // A collider-side half-block is split into PARTS work items (each takes every cell's PARTS-th share of the
+    // run): these blocks are few, so their latency — not throughput — is what shows up.
+    constexpr uint32_t PARTS = CPIC ? 2u : 1u;
+    const uint32_t nwork = (CPIC ? d.counters->num_cpic_blocks * PARTS : min(d.counters->num_active_blocks, d.capacity)) * 2u;
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
     uint32_t* work = CPIC ? &d.counters->work_p2g_cpic : &d.counters->work_p2g;
@@ -210,14 +206,14 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
     // near-identity permutation of the current buffers).
     auto stage = [&](uint32_t base, int cn) {
         // ids go through shared memory so that the request loop below stays rolled (few live registers
-        // next to the 108 accumulators); each thread only reads back the ids it wrote itself.
+        // next to the 108 accumulators); each lane only reads back the ids it wrote itself.
 #pragma unroll
-        for (int j = 0; j < PER_THREAD; ++j) {
-            const int i = t + j * P2G_THREADS;
+        for (int j = 0; j < CHUNK / 32; ++j) {
+            const int i = lane + j * 32;
             if (i < cn) s_ids[i] = __ldg(d.sorted_ids + base + i);
         }
 #pragma unroll 1
-        for (int i = t; i < cn; i += P2G_THREADS) {
+        for (int i = lane; i < cn; i += 32) {
             const uint32_t id = s_ids[i];
             const int s = p2g_swz(i);
             cp_async16(sp + s, pos4 + id);
@@ -232,36 +228,42 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
         cp_async_wait_all();
         // (x, y, z, material bits) -> (x, y, z, mass)
 #pragma unroll 1
-        for (int i = t; i < cn; i += P2G_THREADS) {
+        for (int i = lane; i < cn; i += 32) {
             const int s = p2g_swz(i);
             const uint32_t mbits = __float_as_uint(sp[s].w);
             sp[s].w = __ldg(&d.materials[mbits & MAT_ID_MASK].mass);
         }
+        __syncwarp();
     };
 
     while (true) {
-        __syncthreads();
-        if (t == 0) s_next = atomicAdd(work, 1u);
-        __syncthreads();
-        if (s_next >= nwork) break;
-        const uint32_t b = CPIC ? d.cpic_list[s_next / PARTS] : s_next;
-        const uint32_t part = s_next % PARTS;
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(work, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nwork) break;
+        const uint32_t half = w & 1u;
+        const uint32_t part = (w >> 1) % PARTS;
+        const uint32_t b = CPIC ? d.cpic_list[w / (2u * PARTS)] : (w >> 1);
         if (!CPIC && d.has_bodies && d.block_flags[b] != 0) continue; // handled by the CPIC instantiation
-        const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
-        const uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
-        if (first == last) continue; // halo block without particles: nothing to scatter
-        uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + t];
-        uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + t + 1];
+        const uint32_t cell = half * HALF + lane; // this lane's cell of the block
+        const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK + half * HALF];
+        const uint32_t last = d.cell_start[b * CELLS_PER_BLOCK + half * HALF + HALF];
+        if (first == last) continue; // nothing to scatter from this half
+        uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + cell];
+        uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + cell + 1];
         if (PARTS > 1) {
             const uint32_t len = end - start;
             end = start + (len * (part + 1)) / PARTS;
             start = start + (len * part) / PARTS;
         }
-        if (t < NA) s_nbr[t] = d.nbr[b * NA + t];
-        for (int n = t; n < TC; n += P2G_THREADS) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
+        const int lx = cell & (B - 1), ly = (cell >> LB) & (B - 1), lz = (D == 3) ? (cell >> (2 * LB)) : 0;
+        const int tb = lx + T * ly + T * T * lz;
+        __syncwarp(); // the previous work item's tile / s_nbr are no longer read
+        if (lane < NA) s_nbr[lane] = d.nbr[b * NA + lane];
+        for (int n = lane; n < TC; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
         if (CPIC) {
-            for (int n = t; n < TC; n += P2G_THREADS) {
+            for (int n = lane; n < TC; n += 32) {
                 int x = n % T, y = (n / T) % T, z = n / (T * T);
                 int ox = x >= B, oy = y >= B, oz = z >= B;
                 uint32_t hn = s_nbr[ox + 2 * oy + 4 * oz];
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
 #pragma unroll
                 for (int k = 0; k < WI; ++k) timp[n * WI + k] = 0.0f;
             }
+            __syncwarp();
         }
 
         const int4 vid = d.block_vid[b];
@@ -284,15 +287,15 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
             acc.clear();
             for (uint32_t base = first; base < last; base += CHUNK) {
                 const int cn = (int)min((uint32_t)CHUNK, last - base);
-                __syncthreads(); // the previous chunk is no longer in use; tcdf is complete
+                __syncwarp(); // the previous chunk is no longer in use
                 stage(base, cn);
-                __syncthreads();
                 const int lo = (int)(max(start, base) - base);
                 const int hi = (int)(min(end, base + (uint32_t)cn) - base);
                 incompatible |= p2g_accumulate<D, CPIC ? P2G_CPIC_MOMENTUM : P2G_FAST, D + 1>(
                     d, cur, base, lo, hi, sp, sv, sa, sb, sc, s_aff, cellpos, h, inv_h, tb, tcdf, acc);
             }
-            // Merge the per-cell stencils into the tile: 3^D conflict-free phases.
+            // Merge the per-cell stencils into the tile: 3^D conflict-free phases (within a phase the 32 lanes
+            // add to 32 distinct nodes).
 #pragma unroll
             for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz)
 #pragma unroll
@@ -307,22 +310,21 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
                         c.z += acc.a[n][2];
                         if (D == 3) c.w += acc.a[n][D];
                         tile[idx] = c;
-                        __syncthreads();
+                        __syncwarp();
                     }
         }
         if (CPIC) {
-            // Second pass, only if some particle/node pair of this block is CPIC-incompatible with a
-            // collider attached: per-node body impulses (p2g.wgsl:201-226).
-            if (__syncthreads_or(incompatible ? 1 : 0)) {
+            // Second pass, only if some particle/node pair of this work item is CPIC-incompatible with a collider
+            // that can react: per-node body impulses (p2g.wgsl:201-226).
+            if (__any_sync(0xffffffffu, incompatible)) {
                 P2GAcc<NBH, WI> imp;
                 imp.clear();
                 const bool single_chunk = (last - first) <= (uint32_t)CHUNK; // still staged
                 for (uint32_t base = first; base < last; base += CHUNK) {
                     const int cn = (int)min((uint32_t)CHUNK, last - base);
                     if (!single_chunk) {
-                        __syncthreads();
+                        __syncwarp();
                         stage(base, cn);
-                        __syncthreads();
                     }
                     const int lo = (int)(max(start, base) - base);
                     const int hi = (int)(min(end, base + (uint32_t)cn) - base);
@@ -338,13 +340,13 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
                             const int idx = tb + sx + T * sy + T * T * sz;
 #pragma unroll
                             for (int k = 0; k < WI; ++k) timp[idx * WI + k] += imp.a[n][k];
-                            __syncthreads();
+                            __syncwarp();
                         }
             }
         }
 
         // Flush the tile: one 16-byte reduction per touched node.
-        for (int n = t; n < TC; n += P2G_THREADS) {
+        for (int n = lane; n < TC; n += 32) {
             int x = n % T, y = (n / T) % T, z = n / (T * T);
             int ox = x >= B, oy = y >= B, oz = z >= B;
             uint32_t hn = s_nbr[ox + 2 * oy + 4 * oz];
@@ -375,9 +377,9 @@ __global__ void __launch_bounds__(P2G_THREADS) k_p2g(DeviceData d, int cur) {
 
 void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
-    const int grid = c.num_sms * 6;
-    if (c.dim == 2) k_p2g<2, false><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
-    else k_p2g<3, false><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
+    const int grid = c.num_sms * 10; // 10 single-warp CTAs per SM (shared memory: 22 KB each)
+    if (c.dim == 2) k_p2g<2, false><<<grid, 32, 0, c.stream>>>(d, cur);
+    else k_p2g<3, false><<<grid, 32, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 
@@ -385,9 +387,9 @@ void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
 // instantiations touch disjoint blocks and meet only in the commutative node reductions.
 void launch_p2g_cpic(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0 || !d.has_bodies) return;
-    const int grid = c.num_sms * 8;
-    if (c.dim == 2) k_p2g<2, true><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
-    else k_p2g<3, true><<<grid, P2G_THREADS, 0, c.stream>>>(d, cur);
+    const int grid = c.num_sms * 7;
+    if (c.dim == 2) k_p2g<2, true><<<grid, 32, 0, c.stream>>>(d, cur);
+    else k_p2g<3, true><<<grid, 32, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 
