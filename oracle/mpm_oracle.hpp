@@ -191,7 +191,19 @@ struct Svd {
     Mat<D> U;
     Vec<D> S;
     Mat<D> Vt;
+    double Sd[D]; // the same singular values before rounding to f32 (used by the exact-sigma mode only)
 };
+
+// Exact-sigma mode (test diagnostic, OFF by default = reference semantics). The WGSL rounds each singular
+// value to f32 and then forms sigma - 1, J - 1 and log(sigma) from the rounded value, which injects an absolute
+// error of ~6e-8 into strains that stiff materials multiply by 1e7..1e9. With the mode ON those three
+// quantities are formed from the unrounded (f64) singular values instead - the exact-arithmetic value of the
+// same formulas on the same f32 state. Tests use it to tell the reference's own rounding noise apart from
+// errors of the CUDA path (tests/test_gpu_step.py::test_sand_against_exact_sigma_oracle).
+inline bool& exact_sigma_mode() {
+    static bool on = false;
+    return on;
+}
 
 template <int D>
 inline Svd<D> svd(const Mat<D>& Ff) {
@@ -329,7 +341,10 @@ inline Svd<D> svd(const Mat<D>& Ff) {
             out.U.at(r, c) = (float)Ud[r][c];
             out.Vt.at(r, c) = (float)Vs[c][r];
         }
-    for (int i = 0; i < D; ++i) out.S[i] = (float)sig[i];
+    for (int i = 0; i < D; ++i) {
+        out.S[i] = (float)sig[i];
+        out.Sd[i] = sig[i];
+    }
     return out;
 }
 
@@ -1380,8 +1395,16 @@ struct Sim {
         Svd<D> s = svd(F);
         float j = s.S[0];
         for (int i = 1; i < D; ++i) j = j * s.S[i];
-        for (int i = 0; i < D; ++i) s.S[i] -= 1.0f;
-        float diag = model.lambda * (j - 1.0f) * j;
+        float jm1 = j - 1.0f;
+        if (exact_sigma_mode()) {
+            double jd = s.Sd[0];
+            for (int i = 1; i < D; ++i) jd *= s.Sd[i];
+            jm1 = (float)(jd - 1.0);
+            for (int i = 0; i < D; ++i) s.S[i] = (float)(s.Sd[i] - 1.0);
+        } else {
+            for (int i = 0; i < D; ++i) s.S[i] -= 1.0f;
+        }
+        float diag = model.lambda * jm1 * j;
         Mat<D> result = (recompose(s) * transpose(F)) * (2.0f * model.mu);
         for (int i = 0; i < D; ++i) result.at(i, i) += diag;
         return result;
@@ -1403,11 +1426,15 @@ struct Sim {
         float plastic_hardening;
         bool valid;
     };
-    static DpProjection project_deformation_gradient(const Plasticity& p, Vec<D> sv, float log_vol_gain, float alpha) {
+    static DpProjection project_deformation_gradient(const Plasticity& p, Vec<D> sv, float log_vol_gain, float alpha,
+                                                     const double* sv_exact = nullptr) {
         // drucker_prager.wgsl:43-64 (2D), 112-133 (3D)
         const float d = (float)D;
         Vec<D> strain;
-        for (int i = 0; i < D; ++i) strain[i] = std::log(sv[i]) + log_vol_gain / d;
+        for (int i = 0; i < D; ++i) {
+            float l = (sv_exact && exact_sigma_mode()) ? (float)std::log(sv_exact[i]) : std::log(sv[i]);
+            strain[i] = l + log_vol_gain / d;
+        }
         float strain_trace = strain[0];
         for (int i = 1; i < D; ++i) strain_trace = strain_trace + strain[i];
         Vec<D> dev;
@@ -1429,7 +1456,7 @@ struct Sim {
         if (p.lambda == 0.0f) return;
         Svd<D> s = svd(F);
         float alpha = dp_alpha(p, state.plastic_hardening);
-        DpProjection proj = project_deformation_gradient(p, s.S, state.log_vol_gain, alpha);
+        DpProjection proj = project_deformation_gradient(p, s.S, state.log_vol_gain, alpha, s.Sd);
         if (proj.valid) {
             float prev_det = s.S[0], new_det = proj.singular_values[0];
             for (int i = 1; i < D; ++i) {

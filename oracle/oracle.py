@@ -57,6 +57,7 @@ def lib():
         L.oracle_dp_project.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_project_point.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_set_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_exact_sigma.argtypes = [ctypes.c_int]
         L.oracle_max_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB

@@ -420,4 +420,7 @@ int oracle_project_point(int dim, const b200mpm_body* b, const float* pt, float*
     vec_to<3>(r.point, out);
     return r.is_inside;
 }
+// Test diagnostic: see exact_sigma_mode() in mpm_oracle.hpp. Process-wide.
+void oracle_set_exact_sigma(int on) { exact_sigma_mode() = (on != 0); }
+
 } // extern "C"

@@ -528,6 +528,7 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
                 return fail(B200MPM_ERR_INVALID_ARGUMENT, "too many distinct materials");
             }
             materials.push_back(m);
+            materials.back().dp_ratio = ((float)D * m.dp_lambda + 2.0f * m.dp_mu) / (2.0f * m.dp_mu);
             mat_index.emplace(std::move(key), mid);
         } else {
             mid = it->second;

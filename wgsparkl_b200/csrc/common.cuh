@@ -46,7 +46,8 @@ struct __align__(16) Material {
     float dp_h3, dp_lambda, dp_mu, phase;
     float max_stretch;
     uint32_t model;
-    uint32_t pad0, pad1;
+    float dp_ratio; // (d dp_lambda + 2 dp_mu) / (2 dp_mu) (drucker_prager.wgsl:56,125), filled by the host
+    uint32_t pad1;
 };
 
 // ---- rigid bodies (wgrapier GpuBodySet + rigid_impulses.wgsl state), <= 16 ---------------

@@ -22,7 +22,7 @@ namespace b2 {
 constexpr int G2P_THREADS = 128;
 
 template <int D, bool PLASTIC, bool CPIC>
-__global__ void __launch_bounds__(G2P_THREADS, 6) k_g2p(DeviceData d, int cur) {
+__global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? 5 : 6) k_g2p(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC;
     __shared__ float4 tile_v[TC];

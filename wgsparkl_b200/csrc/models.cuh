@@ -8,48 +8,95 @@
 
 namespace b2 {
 
-// DruckerPrager::alpha (drucker_prager.wgsl:25-29)
+// DruckerPrager::alpha (drucker_prager.wgsl:25-29). The friction angle is O(1) rad and -h2 q <= 0, so the
+// SFU approximations (abs. error ~2^-21) are well inside the f32 noise of the reference's own evaluation.
 __device__ __forceinline__ float dp_alpha(const Material& m, float q) {
-    float angle = m.dp_h0 + (m.dp_h1 * q - m.dp_h3) * expf(-m.dp_h2 * q);
-    float s = sinf(angle);
-    return sqrtf(2.0f / 3.0f) * (2.0f * s) / (3.0f - s);
+    float angle = m.dp_h0 + (m.dp_h1 * q - m.dp_h3) * __expf(-m.dp_h2 * q);
+    float s = __sinf(angle);
+    return 0.81649658092772603f * __fdividef(2.0f * s, 3.0f - s);
+}
+
+// log(1 + x) from an x that is accurate relative to itself (sigma - 1 out of the shifted SVD):
+// 2 atanh(x / (2 + x)), series to z^9 for |x| < 1/4 (remainder < 4e-10 relative), logf beyond.
+__device__ __forceinline__ float log1p_strain(float x, float one_plus_x) {
+    if (fabsf(x) < 0.25f) {
+        const float z = __fdividef(x, 2.0f + x), z2 = z * z;
+        float p = fmaf(z2, 1.0f / 9.0f, 1.0f / 7.0f);
+        p = fmaf(z2, p, 0.2f);
+        p = fmaf(z2, p, 1.0f / 3.0f);
+        p = fmaf(z2, p, 1.0f);
+        return 2.0f * z * p;
+    }
+    return logf(one_plus_x);
+}
+
+// exp(x) - 1, Taylor to x^7 for |x| < 1/4 (remainder < 2e-9 relative), expf beyond.
+__device__ __forceinline__ float expm1_strain(float x) {
+    if (fabsf(x) < 0.25f) {
+        float p = fmaf(x, 1.0f / 5040.0f, 1.0f / 720.0f);
+        p = fmaf(x, p, 1.0f / 120.0f);
+        p = fmaf(x, p, 1.0f / 24.0f);
+        p = fmaf(x, p, 1.0f / 6.0f);
+        p = fmaf(x, p, 0.5f);
+        p = fmaf(x, p, 1.0f);
+        return x * p;
+    }
+    return expf(x) - 1.0f;
 }
 
 // project_deformation_gradient (drucker_prager.wgsl:43-64 2D, 112-133 3D). Returns false when the
 // projection is invalid (gamma <= 0: state and F are left untouched by the caller).
+//   sv / svm1: singular values and (sigma - 1); outputs new_sv / new_svm1, the hardening increment, and
+//   log(prod sv) - log(prod new_sv) (the log-volume the projection removed, drucker_prager.wgsl:152).
 template <int D>
-__device__ __forceinline__ bool dp_project_sv(const Material& m, const float* sv, float log_vol_gain, float alpha,
-                                              float* new_sv, float& hardening) {
+__device__ __forceinline__ bool dp_project_sv(const Material& m, const float* sv, const float* svm1, float log_vol_gain,
+                                              float alpha, float* new_sv, float* new_svm1, float& hardening,
+                                              float& log_det_ratio) {
     const float d = (float)D;
     float strain[D], dev[D];
-    float trace = 0.0f;
+    float trace = 0.0f, log_det = 0.0f;
+    const float shift = log_vol_gain * (1.0f / d);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        strain[i] = logf(sv[i]) + log_vol_gain / d;
+        const float l = log1p_strain(svm1[i], sv[i]);
+        log_det = (i == 0) ? l : log_det + l;
+        strain[i] = l + shift;
         trace = (i == 0) ? strain[0] : trace + strain[i];
     }
     bool all_zero = true;
     float dev2 = 0.0f, strain2 = 0.0f;
+    const float mean = trace * (1.0f / d);
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        dev[i] = strain[i] - trace / d;
+        dev[i] = strain[i] - mean;
         all_zero = all_zero && (dev[i] == 0.0f);
         dev2 += dev[i] * dev[i];
         strain2 += strain[i] * strain[i];
     }
     if (trace > 0.0f || all_zero) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) new_sv[i] = 1.0f;
+        for (int i = 0; i < D; ++i) {
+            new_sv[i] = 1.0f;
+            new_svm1[i] = 0.0f;
+        }
         hardening = sqrtf(strain2);
+        log_det_ratio = log_det;
         return true;
     }
     float dev_norm = sqrtf(dev2);
-    float gamma = dev_norm + (d * m.dp_lambda + 2.0f * m.dp_mu) / (2.0f * m.dp_mu) * trace * alpha;
+    float gamma = dev_norm + m.dp_ratio * trace * alpha;
     if (gamma <= 0.0f) return false;
-    float k = gamma / dev_norm;
+    float k = __fdividef(gamma, dev_norm);
+    float new_log_det = 0.0f;
 #pragma unroll
-    for (int i = 0; i < D; ++i) new_sv[i] = expf(strain[i] - dev[i] * k);
+    for (int i = 0; i < D; ++i) {
+        const float e = strain[i] - dev[i] * k;
+        new_log_det += e;
+        new_svm1[i] = expm1_strain(e);
+        new_sv[i] = 1.0f + new_svm1[i];
+    }
     hardening = gamma;
+    log_det_ratio = log_det - new_log_det;
     return true;
 }
 
@@ -129,13 +176,19 @@ __device__ __forceinline__ void constitutive_update(const Material& m, uint32_t&
     if (D == 3 && !PLASTIC && !neo) {
         if (corotated_stress_small_strain3(m, F, tau)) return;
     }
-    float U[D * D], S[D], V[D * D];
+    float U[D * D], S[D], Sm1[D], V[D * D];
     float phase = (flags & FLAG_PHASE_BROKEN) ? 0.0f : m.phase;
     const bool may_stretch = PLASTIC && phase > 0.0f && m.max_stretch > 0.0f;
     const bool need_svd = !neo || (PLASTIC && (may_stretch || phase == 0.0f));
     if (need_svd) {
-        if (D == 2) svd2(F, U, S, V);
-        else svd3<4>(F, U, S, V);
+        bool have = false;
+        if (D == 3) have = svd3_fast(F, U, S, Sm1, V);
+        if (!have) {
+            if (D == 2) svd2(F, U, S, V);
+            else svd3<4>(F, U, S, V);
+#pragma unroll
+            for (int i = 0; i < D; ++i) Sm1[i] = S[i] - 1.0f;
+        }
     }
     if (PLASTIC) {
         if (may_stretch) { // particle_update.wgsl:101-115
@@ -149,27 +202,35 @@ __device__ __forceinline__ void constitutive_update(const Material& m, uint32_t&
         }
         if (phase == 0.0f && m.dp_lambda != 0.0f) { // particle_update.wgsl:118-122, drucker_prager.wgsl:134-158
             float alpha = dp_alpha(m, plastic.y);
-            float nsv[D], hard;
-            if (dp_project_sv<D>(m, S, plastic.z, alpha, nsv, hard)) {
+            float nsv[D], nsm1[D], hard, log_ratio;
+            if (dp_project_sv<D>(m, S, Sm1, plastic.z, alpha, nsv, nsm1, hard, log_ratio)) {
                 float prev_det = S[0], new_det = nsv[0];
 #pragma unroll
                 for (int i = 1; i < D; ++i) {
                     prev_det *= S[i];
                     new_det *= nsv[i];
                 }
-                plastic.x = plastic.x * prev_det / new_det;
-                plastic.z = plastic.z + logf(prev_det) - logf(new_det);
+                plastic.x = plastic.x * __fdividef(prev_det, new_det);
+                plastic.z = plastic.z + log_ratio;
                 plastic.y = plastic.y + hard;
+                // F <- U diag(S') V^T, written as F + U diag(S' - S) V^T: the plastic correction is small, so the
+                // rounding errors of U, V and S' only touch the correction and F keeps ~1 ulp accuracy.
+                float UdS[D * D];
 #pragma unroll
-                for (int i = 0; i < D; ++i) S[i] = nsv[i];
-                // F = U diag(S) V^T
+                for (int k = 0; k < D; ++k) {
+                    const float ds = nsm1[k] - Sm1[k];
+#pragma unroll
+                    for (int r = 0; r < D; ++r) UdS[k * D + r] = U[k * D + r] * ds;
+                    S[k] = nsv[k];
+                    Sm1[k] = nsm1[k];
+                }
 #pragma unroll
                 for (int c = 0; c < D; ++c)
 #pragma unroll
                     for (int r = 0; r < D; ++r) {
-                        float s = 0.0f;
+                        float s = F[c * D + r];
 #pragma unroll
-                        for (int k = 0; k < D; ++k) s += U[k * D + r] * S[k] * V[k * D + c];
+                        for (int k = 0; k < D; ++k) s += UdS[k * D + r] * V[k * D + c];
                         F[c * D + r] = s;
                     }
             }
@@ -194,21 +255,28 @@ __device__ __forceinline__ void constitutive_update(const Material& m, uint32_t&
     } else { // corotated: linear_elasticity.wgsl:14-41
         // 2 mu U (S - I) V^T F^T + lambda (J - 1) J I, with F^T = V S U^T:
         //   = U diag(2 mu (S - 1) S + lambda (J - 1) J) U^T
-        float j = S[0];
+        // J - 1 = prod(1 + (S_i - 1)) - 1 expanded, so it keeps the relative accuracy of (S_i - 1)
+        float jm1 = Sm1[0];
 #pragma unroll
-        for (int i = 1; i < D; ++i) j *= S[i];
-        float diag = m.lambda * (j - 1.0f) * j;
-        float e[D];
+        for (int i = 1; i < D; ++i) jm1 = fmaf(jm1, Sm1[i], jm1 + Sm1[i]);
+        float diag = m.lambda * jm1 * (1.0f + jm1);
+        float Ue[D * D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) e[i] = 2.0f * m.mu * (S[i] - 1.0f) * S[i] + diag;
+        for (int i = 0; i < D; ++i) {
+            const float e = 2.0f * m.mu * Sm1[i] * S[i] + diag;
+#pragma unroll
+            for (int r = 0; r < D; ++r) Ue[i * D + r] = U[i * D + r] * e;
+        }
 #pragma unroll
         for (int c = 0; c < D; ++c)
 #pragma unroll
             for (int r = 0; r < D; ++r) {
+                if (r > c) continue;
                 float s = 0.0f;
 #pragma unroll
-                for (int k = 0; k < D; ++k) s += U[k * D + r] * e[k] * U[k * D + c];
+                for (int k = 0; k < D; ++k) s += Ue[k * D + r] * U[k * D + c];
                 tau[c * D + r] = s;
+                tau[r * D + c] = s;
             }
     }
 }

@@ -194,4 +194,84 @@ __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* 
     }
 }
 
+#if defined(__CUDACC__)
+// ---- device fast path for the 3x3 SVD of a non-inverted, moderately strained F ---------------------------
+// Same mathematics as svd3 (Jacobi on the f64-formed M = F^T F - I), restructured for instruction count:
+//   * branch-free rotation  t = sign(d) 2 a_pq / (|d| + sqrt(d^2 + 4 a_pq^2)),  d = a_qq - a_pp  (one MUFU.RSQ,
+//     one MUFU.RCP; (c, s) renormalised, so the approximate intrinsics only steer convergence);
+//   * rolled sweep loop that stops once |off(M)| <= 1e-6 |diag(M)| (3 sweeps for almost every matrix, f32
+//     round-off floor is ~2e-7) - a rolled body also keeps the kernel inside the instruction cache;
+//   * no sorting (every use on the path is symmetric in the singular triplets) and no Gram-Schmidt:
+//     with det F > 0 and all sigma > 0.5,  u_i = F v_i / sigma_i  directly.
+// Also returns sigma_i - 1 (accurate relative to itself), which the strain / stress formulas consume.
+// Returns false - caller falls back to svd3 - for det F <= 0 or any sigma <= 0.5.
+__device__ __forceinline__ void jacobi_rot_fast(float& app, float& aqq, float& apq, float& apr, float& aqr, float* vp,
+                                                float* vq) {
+    const float d = aqq - app;
+    const float two = apq + apq;
+    const float w = fmaf(d, d, two * two);
+    const float r = w * rsqrtf(fmaxf(w, 1e-37f)); // sqrt(w); 0 for w == 0
+    const float den = fmaxf(fabsf(d) + r, 1e-37f);
+    const float num = __int_as_float(__float_as_int(two) ^ (__float_as_int(d) & 0x80000000));
+    const float t = __fdividef(num, den);
+    const float c = rsqrtf(fmaf(t, t, 1.0f));
+    const float s = t * c;
+    const float t_apq = t * apq;
+    app -= t_apq;
+    aqq += t_apq;
+    apq = 0.0f;
+    const float npr = c * apr - s * aqr;
+    const float nqr = s * apr + c * aqr;
+    apr = npr;
+    aqr = nqr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float a = vp[k], b = vq[k];
+        vp[k] = c * a - s * b;
+        vq[k] = s * a + c * b;
+    }
+}
+
+__device__ __forceinline__ bool svd3_fast(const float* F, float* U, float* S, float* Sm1, float* V) {
+    const float detF = F[0] * (F[4] * F[8] - F[7] * F[5]) - F[3] * (F[1] * F[8] - F[7] * F[2]) + F[6] * (F[1] * F[5] - F[4] * F[2]);
+    if (!(detF > 0.0f)) return false;
+    const double f0 = F[0], f1 = F[1], f2 = F[2], f3 = F[3], f4 = F[4], f5 = F[5], f6 = F[6], f7 = F[7], f8 = F[8];
+    float a00 = (float)(f0 * f0 + f1 * f1 + f2 * f2 - 1.0);
+    float a11 = (float)(f3 * f3 + f4 * f4 + f5 * f5 - 1.0);
+    float a22 = (float)(f6 * f6 + f7 * f7 + f8 * f8 - 1.0);
+    float a01 = (float)(f0 * f3 + f1 * f4 + f2 * f5);
+    float a02 = (float)(f0 * f6 + f1 * f7 + f2 * f8);
+    float a12 = (float)(f3 * f6 + f4 * f7 + f5 * f8);
+    float v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
+#pragma unroll 1
+    for (int sweep = 0; sweep < 6; ++sweep) {
+        jacobi_rot_fast(a00, a11, a01, a02, a12, v0, v1);
+        jacobi_rot_fast(a00, a22, a02, a01, a12, v0, v2);
+        jacobi_rot_fast(a11, a22, a12, a01, a02, v1, v2);
+        const float off2 = a01 * a01 + a02 * a02; // a12 was just annihilated
+        const float dg2 = a00 * a00 + a11 * a11 + a22 * a22;
+        if (off2 <= 1e-12f * dg2) break;
+    }
+    if (!(fminf(a00, fminf(a11, a22)) > -0.75f)) return false;
+    auto finish = [&](int i, float mu, const float* v) {
+        const float x = 1.0f + mu;
+        const float sm1 = __fdividef(mu, 1.0f + x * rsqrtf(x));
+        const float sig = 1.0f + sm1;
+        const float inv = __fdividef(1.0f, sig);
+        Sm1[i] = sm1;
+        S[i] = sig;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float b = F[r] * v[0] + F[3 + r] * v[1] + F[6 + r] * v[2];
+            U[3 * i + r] = b * inv;
+            V[3 * i + r] = v[r];
+        }
+    };
+    finish(0, a00, v0);
+    finish(1, a11, v1);
+    finish(2, a22, v2);
+    return true;
+}
+#endif
+
 } // namespace b2
