@@ -114,3 +114,30 @@ def test_prefix_sum_known_answer(pipe3, oracle_mod):
         exp = np.concatenate([[0], np.cumsum(v.astype(np.uint64))[:-1]]).astype(np.uint32)
         assert np.array_equal(got, exp)
         assert np.array_equal(oracle_mod.prefix_sum(v), exp)
+
+
+@pytest.mark.parametrize("cell_width", [0.1, 0.37, 1.0 / 3.0, 2.5])
+def test_round_ties_and_their_neighbours(pipe3, oracle_mod, cell_width):
+    """round(p / h) is evaluated without an IEEE division on the fast path (common.cuh round_div): particles
+    exactly on, one ulp below and one ulp above half-integer quotients - for cell widths that are not powers of
+    two, at small and large coordinates (inside the +-511-block range of pack_key3) - must land in the same blocks and cells as the oracle's true division."""
+    rng = np.random.default_rng(7)
+    h = np.float32(cell_width)
+    ks = np.concatenate([rng.integers(-40, 40, 600), rng.integers(-1900, 1900, 600)]).astype(np.float32)
+    base = ((ks + np.float32(0.5)) * h).astype(np.float32)
+    variants = [base, np.nextafter(base, np.float32(np.inf)), np.nextafter(base, np.float32(-np.inf)),
+                np.nextafter(np.nextafter(base, np.float32(np.inf)), np.float32(np.inf))]
+    x = np.concatenate(variants).astype(np.float32)
+    n = len(x)
+    scene = scenes.elastic_cube_3d(4, y_offset=3.0)
+    parts = np.repeat(scene["particles"][:1], n).copy()
+    parts["position"][:, 0] = x
+    parts["position"][:, 1] = rng.permutation(x)
+    parts["position"][:, 2] = (rng.integers(0, 3, n).astype(np.float32) + np.float32(0.5)) * h
+    scene["particles"] = parts
+    scene["cell_width"] = float(h)
+    scene["grid_capacity"] = 1 << 16
+    data, (gb, gn, gs), (ob, on, os_) = _run_both(scene, pipe3, oracle_mod)
+    assert not data.status()[1], "test scene must fit the grid capacity"
+    parity.assert_sort_equal(gb, gs, ob, os_)
+    data.close()

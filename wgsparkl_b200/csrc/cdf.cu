@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
             int tb = 0;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                float cf = rintf(__fdiv_rn(pp[a], h)) - 1.0f;
+                float cf = round_div(pp[a], h, inv_h) - 1.0f;
                 int c = (int)cf;
                 int l = c & (B - 1);
                 tb += l * ((a == 0) ? 1 : (a == 1) ? T : T * T);

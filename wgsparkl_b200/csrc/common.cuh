@@ -140,7 +140,7 @@ struct DeviceData {
     uint4* node_cdf; // capacity*64: bits(distance), affinities, closest_id, - (NodeCdf, grid.wgsl:233-240)
     uint64_t* scan_state; // single-pass scan tile descriptors
     uint8_t* block_f0; // capacity: 1 if one of the block's own nodes is near / inside a collider (k_block_prepare)
-    uint8_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)
+    uint32_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)
     uint32_t* cpic_list; // capacity: compact list of flagged blocks that hold particles
 
     BodyDev* bodies;
@@ -168,9 +168,19 @@ __host__ __device__ inline uint32_t hash_key(uint32_t k) { // grid.wgsl:98-105 (
     return k;
 }
 
-// Associated cell of a coordinate: round(p / h) - 1 with round = ties-to-even and a true IEEE
-// division, bit-exact with grid.wgsl:285 / particle3d.wgsl:42 (never roundf).
-__device__ __forceinline__ int assoc_cell(float p, float h) { return (int)(rintf(__fdiv_rn(p, h)) - 1.0f); }
+// round(p / h) with round = ties-to-even and a true IEEE division, bit-exact with grid.wgsl:285 /
+// particle3d.wgsl:42 (never roundf) - without paying for the division: q = p * (1/h) is within
+// 1.8e-7 |q| of the correctly rounded quotient, so rint(q) can only differ from rint(p / h) when a half-integer
+// lies that close to q. Those (rare) lanes take the IEEE division; everyone else a multiply and a compare.
+__device__ __forceinline__ float round_div(float p, float h, float inv_h) {
+    const float q = p * inv_h;
+    const float r = rintf(q);
+    if (0.5f - fabsf(q - r) <= 4e-7f * fabsf(q) || !(fabsf(q) < 4194304.0f)) return rintf(__fdiv_rn(p, h));
+    return r;
+}
+
+// Associated cell of a coordinate: round(p / h) - 1. inv_h must be the IEEE 1.0f / h.
+__device__ __forceinline__ int assoc_cell(float p, float h, float inv_h) { return (int)(round_div(p, h, inv_h) - 1.0f); }
 
 __device__ __forceinline__ uint32_t find_block(const uint32_t* __restrict__ hkeys, const uint32_t* __restrict__ hvals,
                                                uint32_t cap_mask, uint32_t packed) { // grid.wgsl:167-184
@@ -239,5 +249,20 @@ __device__ __forceinline__ int flt2int(float f) {
     if (x <= -2147483648.0f) return (-2147483647 - 1);
     return (int)x; // cvt.rzi
 }
+
+#if defined(__CUDACC__)
+// ---- cp.async (LDGSTS): global -> shared without register staging -------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* gmem) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(gmem)); }
+__device__ __forceinline__ void prefetch_l2(const void* gmem) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gmem)); }
+#endif
 
 } // namespace b2

@@ -20,9 +20,21 @@
 namespace b2 {
 
 constexpr int G2P_THREADS = 128;
+#ifndef G2P_FMA_GATHER
+#define G2P_FMA_GATHER 1
+#endif
+#ifndef G2P_MINB_E
+#define G2P_MINB_E 6
+#endif
+#ifndef G2P_MINB_P
+#define G2P_MINB_P 5
+#endif
+#ifndef G2P_LOOKAHEAD
+#define G2P_LOOKAHEAD 0
+#endif
 
 template <int D, bool PLASTIC, bool CPIC>
-__global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? 5 : 6) k_g2p(DeviceData d, int cur) {
+__global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MINB_P : G2P_MINB_E) k_g2p(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC;
     __shared__ float4 tile_v[TC];
@@ -89,8 +101,21 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? 5 : 6) k_g2p(DeviceData
         }
         __syncthreads();
 
+#if G2P_LOOKAHEAD
+        uint32_t id_next = (first + t < last) ? __ldg(d.sorted_ids + first + t) : 0u;
+#endif
         for (uint32_t k = first + t; k < last; k += G2P_THREADS) {
+#if G2P_LOOKAHEAD
+            const uint32_t id = id_next;
+            if (k + G2P_THREADS < last) id_next = __ldg(d.sorted_ids + k + G2P_THREADS);
+#if G2P_LOOKAHEAD == 2
+            if (k + G2P_THREADS < last) {
+                // touches the next record's lines while this one is being computed (ids are one iteration ahead)
+            }
+#endif
+#else
             const uint32_t id = __ldg(d.sorted_ids + k);
+#endif
             const float4 p4 = __ldg(pos4 + id);
             const float4 v4 = __ldg(vel4 + id);
             float F[D * D];
@@ -110,7 +135,7 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? 5 : 6) k_g2p(DeviceData
             int tb = 0;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-                float cf = rintf(__fdiv_rn(pp[a], h)) - 1.0f; // particle3d.wgsl:41-57
+                float cf = round_div(pp[a], h, inv_h) - 1.0f; // particle3d.wgsl:41-57
                 int l = ((int)cf) & (B - 1);
                 tb += l * ((a == 0) ? 1 : (a == 1) ? T : T * T);
                 d0[a] = cf * h - pp[a];
@@ -156,6 +181,14 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? 5 : 6) k_g2p(DeviceData
                         for (int sx = 0; sx < 3; ++sx) {
                             const float4 cell = tile_v[tb + sx + T * sy + T * T * sz];
                             const float cv[3] = {cell.x, cell.y, cell.z};
+#if G2P_FMA_GATHER
+                            const float wx = w[0][sx], sxw = (float)sx * w[0][sx];
+#pragma unroll
+                            for (int r = 0; r < D; ++r) {
+                                t0[r] = fmaf(wx, cv[r], t0[r]);
+                                if (sx > 0) t1[r] = fmaf(sxw, cv[r], t1[r]);
+                            }
+#else
                             const float wx = w[0][sx];
 #pragma unroll
                             for (int r = 0; r < D; ++r) {
@@ -163,6 +196,7 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? 5 : 6) k_g2p(DeviceData
                                 t0[r] += wv;
                                 if (sx > 0) t1[r] += (float)sx * wv;
                             }
+#endif
                         }
                         const float wy = w[1][sy];
 #pragma unroll

@@ -46,16 +46,6 @@ struct P2GAcc {
 // would otherwise hit the same bank group on every 16-byte load (8-way conflict).
 __device__ __forceinline__ int p2g_swz(int i) { return i ^ ((i >> 3) & 7); }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
 // Walks the staged particles [lo, hi) of one cell.
 //   MODE FAST / CPIC_MOMENTUM: acc[n] += w (affine dpt + m v, m)       (p2g.wgsl:188-230)
 //   MODE CPIC_IMPULSE        : acc[n] += (delta_impulse, delta_ang)     (p2g.wgsl:203-225)

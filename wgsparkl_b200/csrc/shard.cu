@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_emigrate(DeviceData d, int cur, void* l
     if (i >= d.counters->n_live) return;
     float4 p = d.pos4[cur][i];
     if (__float_as_uint(p.w) & FLAG_DEAD) return;
-    const int bx = assoc_cell(p.x, d.sim->cell_width) >> Dim<D>::LOG_BLOCK;
+    const int bx = assoc_cell(p.x, d.sim->cell_width, 1.0f / d.sim->cell_width) >> Dim<D>::LOG_BLOCK;
     const int dir = (bx < d.sim->slab_lo) ? 0 : (bx >= d.sim->slab_hi) ? 1 : -1;
     if (dir < 0) return;
     const uint32_t slot = atomicAdd(&d.counters->send_count[dir], 1u);

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < d.counters->n_live;
     const float h = d.sim->cell_width;
+    const float inv_h = 1.0f / h;
     int bx = 0, by = 0, bz = 0;
     uint32_t cell = 0;
     uint32_t key = NONE;
@@ -78,12 +79,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
     if (active) {
         float4 p = d.pos4[cur][i];
         dead = (__float_as_uint(p.w) & FLAG_DEAD) != 0u; // emigrated (k_emigrate): parked, then dropped
-        int cx = assoc_cell(p.x, h), cy = assoc_cell(p.y, h);
+        int cx = assoc_cell(p.x, h, inv_h), cy = assoc_cell(p.y, h, inv_h);
         bx = cx >> Dim<D>::LOG_BLOCK; // floor(c / BLOCK), grid.wgsl:286
         by = cy >> Dim<D>::LOG_BLOCK;
         cell = (cx & (Dim<D>::BLOCK - 1)) + (cy & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK;
         if (D == 3) {
-            int cz = assoc_cell(p.z, h);
+            int cz = assoc_cell(p.z, h, inv_h);
             bz = cz >> Dim<D>::LOG_BLOCK;
             cell += (cz & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK * Dim<D>::BLOCK;
         }
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
                 uint32_t hn = d.nbr[i * Dim<D>::NASSOC + o];
                 if (hn != NONE) flag |= d.block_f0[hn];
             }
-            d.block_flags[i] = (uint8_t)flag;
+            d.block_flags[i] = (uint32_t)flag;
             if (flag && d.cell_start[i * CELLS_PER_BLOCK] != d.cell_start[(i + 1) * CELLS_PER_BLOCK])
                 d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
         }

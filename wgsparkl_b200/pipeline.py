@@ -14,7 +14,8 @@ from . import abi
 from .solver import SimulationParams, particles_to_abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libb200mpm.so")
+# B200MPM_LIB: development override used by tools/build_variant.py for A/B kernel timing.
+_LIB_PATH = os.environ.get("B200MPM_LIB") or os.path.join(_HERE, "libb200mpm.so")
 _lib = None
 
 
