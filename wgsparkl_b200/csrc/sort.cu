@@ -36,22 +36,21 @@ __global__ void __launch_bounds__(SORT_THREADS) k_clear(DeviceData d) {
 }
 
 // ---- insertion_index + mark_block_as_active (grid.wgsl:121-164, 323-334) -------------------------
+// Claims the hash slot of a block. `won` reports that THIS call created the entry, in which case the caller owes
+// the block its dense index (hvals[slot], block_vid[index]); see k_touch for how those are handed out.
 template <int D>
-__device__ __forceinline__ uint32_t insert_block(const DeviceData& d, int bx, int by, int bz) {
+__device__ __forceinline__ uint32_t claim_block(const DeviceData& d, int bx, int by, int bz, bool& won) {
     const uint32_t mask = d.capacity - 1;
     const uint32_t key = pack_key<D>(bx, by, bz);
     uint32_t slot = hash_key(key) & mask;
+    won = false;
     for (uint32_t k = 0; k <= mask; ++k) {
         uint32_t cur = *((volatile uint32_t*)(d.hkeys + slot));
         if (cur == key) return slot;
         if (cur == NONE) {
             uint32_t prev = atomicCAS(d.hkeys + slot, NONE, key);
             if (prev == NONE) {
-                uint32_t hid = atomicAdd(&d.counters->num_active_blocks, 1u);
-                if (hid < d.capacity) {
-                    d.block_vid[hid] = make_int4(bx, by, bz, 0);
-                    d.hvals[slot] = hid;
-                }
+                won = true;
                 return slot;
             }
             if (prev == key) return slot;
@@ -62,86 +61,158 @@ __device__ __forceinline__ uint32_t insert_block(const DeviceData& d, int bx, in
     return NONE;
 }
 
+__device__ __forceinline__ void publish_block(const DeviceData& d, uint32_t slot, uint32_t hid, int4 vid) {
+    if (hid < d.capacity) {
+        d.block_vid[hid] = vid;
+        d.hvals[slot] = hid;
+    }
+}
+
 // ---- touch_particle_blocks (sort.wgsl:26-36) ------------------------------------------------------
-// One thread per particle; consecutive lanes that map to the same block (the common case: the
-// buffers are already in last substep's sorted order) elect one leader that performs the
-// 2^D insertions, the others only fetch the slot of their block from the leader.
+// These three streaming kernels (touch, count, scatter) are chains of dependent long-latency operations per
+// particle (load -> hash probe -> atomic -> store). With one particle per thread the 64 warps an SM can hold
+// do not cover that latency (ncu: >90 % of warp time in long_scoreboard at < 1 TB/s), so every thread carries
+// SORT_ITEMS particles whose loads / probes / atomics are issued back to back: a warp owns 32 * SORT_ITEMS
+// CONSECUTIVE particles (item j of lane l is particle warp_base + 32 j + l, so every access stays coalesced).
+//
+// k_touch: consecutive particles that map to the same block (the common case: the buffers are already in
+// last substep's sorted order) form a run; the run leaders' 2^D insertions of blocks_associated_to_block
+// (grid.wgsl:300-320) are done by ALL lanes of the warp at once, 32 / 2^D leaders per round.
+//
+// Dense block indices come from ONE counter (num_active_blocks); every substep re-creates ~20 k blocks per
+// million particles, so the blocks a warp creates in one round share a single atomic on it.
+#ifndef SORT_ITEMS_N
+#define SORT_ITEMS_N 4
+#endif
+constexpr int SORT_ITEMS = SORT_ITEMS_N;
+constexpr int SORT_PER_WARP = 32 * SORT_ITEMS;
+constexpr int SORT_PER_CTA = SORT_THREADS * SORT_ITEMS;
+
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < d.counters->n_live;
+    constexpr int NA = Dim<D>::NASSOC, WARPS = SORT_THREADS / 32, PER_ROUND = 32 / NA;
+    __shared__ int4 s_lead[WARPS][SORT_PER_WARP]; // run leaders of a warp: block (x, y, z), then the slot in .w
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = (blockIdx.x * WARPS + warp) * SORT_PER_WARP;
+    const uint32_t n_live = d.counters->n_live;
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
-    int bx = 0, by = 0, bz = 0;
-    uint32_t cell = 0;
-    uint32_t key = NONE;
-    bool dead = false;
-    if (active) {
-        float4 p = d.pos4[cur][i];
-        dead = (__float_as_uint(p.w) & FLAG_DEAD) != 0u; // emigrated (k_emigrate): parked, then dropped
-        int cx = assoc_cell(p.x, h, inv_h), cy = assoc_cell(p.y, h, inv_h);
-        bx = cx >> Dim<D>::LOG_BLOCK; // floor(c / BLOCK), grid.wgsl:286
-        by = cy >> Dim<D>::LOG_BLOCK;
-        cell = (cx & (Dim<D>::BLOCK - 1)) + (cy & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK;
-        if (D == 3) {
-            int cz = assoc_cell(p.z, h, inv_h);
-            bz = cz >> Dim<D>::LOG_BLOCK;
-            cell += (cz & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK * Dim<D>::BLOCK;
-        }
-        key = dead ? NONE : pack_key<D>(bx, by, bz);
+    const float4* __restrict__ pos4 = d.pos4[cur];
+
+    float4 p[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t i = warp_base + j * 32 + lane;
+        p[j] = (i < n_live) ? pos4[i] : make_float4(0.f, 0.f, 0.f, __uint_as_float(FLAG_DEAD));
     }
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool leader = active && !dead && (lane == 0 || prev_key != key);
-    const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
-    // For every run leader (usually one per warp) the 2^D insertions of blocks_associated_to_block
-    // (grid.wgsl:300-320) are spread over 2^D lanes: one probe latency instead of 2^D in a row.
-    uint32_t slot = NONE;
-    for (uint32_t rem = leaders; rem; rem &= rem - 1) {
-        const int L = __ffs(rem) - 1;
-        const int lbx = __shfl_sync(0xffffffffu, bx, L), lby = __shfl_sync(0xffffffffu, by, L),
-                  lbz = __shfl_sync(0xffffffffu, bz, L);
-        uint32_t s = NONE;
-        if (lane < (uint32_t)Dim<D>::NASSOC) {
-            const int ox = lane & 1, oy = (lane >> 1) & 1, oz = (D == 3) ? (lane >> 2) & 1 : 0;
-            s = insert_block<D>(d, lbx + ox, lby + oy, lbz + oz);
-        }
-        s = __shfl_sync(0xffffffffu, s, 0); // offset (0,..,0): the slot that identifies the particle's block
-        if ((int)lane == L) slot = s;
+    uint32_t cell[SORT_ITEMS], lmask[SORT_ITEMS];
+    bool alive[SORT_ITEMS];
+    uint32_t before = 0; // leaders in items < j
+    uint32_t last_key = 0;
+    bool last_alive = false;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        // emigrated particles (k_emigrate) and the tail beyond n_live are not sorted: parked, then dropped
+        alive[j] = (__float_as_uint(p[j].w) & FLAG_DEAD) == 0u;
+        const int cx = assoc_cell(p[j].x, h, inv_h), cy = assoc_cell(p[j].y, h, inv_h);
+        const int cz = (D == 3) ? assoc_cell(p[j].z, h, inv_h) : 0;
+        const int bx = cx >> Dim<D>::LOG_BLOCK, by = cy >> Dim<D>::LOG_BLOCK, bz = cz >> Dim<D>::LOG_BLOCK; // grid.wgsl:286
+        cell[j] = (cx & (Dim<D>::BLOCK - 1)) + (cy & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK +
+                  ((D == 3) ? (cz & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK * Dim<D>::BLOCK : 0);
+        const uint32_t key = pack_key<D>(bx, by, bz);
+        // run leader: alive, and the previous particle (lane - 1, or lane 31 of the previous item) is dead or elsewhere
+        uint32_t pk = __shfl_up_sync(0xffffffffu, key, 1);
+        bool pa = __shfl_up_sync(0xffffffffu, (int)alive[j], 1) != 0;
+        if (lane == 0) pk = last_key, pa = last_alive;
+        const bool leader = alive[j] && (!pa || pk != key);
+        lmask[j] = __ballot_sync(0xffffffffu, leader);
+        if (leader) s_lead[warp][before + __popc(lmask[j] & ((1u << lane) - 1u))] = make_int4(bx, by, bz, (int)NONE);
+        before += __popc(lmask[j]);
+        last_key = __shfl_sync(0xffffffffu, key, 31);
+        last_alive = __shfl_sync(0xffffffffu, (int)alive[j], 31) != 0;
     }
-    const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
-    const int src = below ? (31 - __clz(below)) : 0;
-    slot = __shfl_sync(0xffffffffu, slot, src);
-    if (active) d.pkey[i] = (slot == NONE || dead) ? NONE : (slot * CELLS_PER_BLOCK + cell);
+    const uint32_t num_leaders = before;
+    __syncwarp();
+    for (uint32_t q0 = 0; q0 < num_leaders; q0 += PER_ROUND) {
+        const uint32_t q = q0 + lane / NA, o = lane % NA;
+        if (q < num_leaders) {
+            const int4 L = s_lead[warp][q];
+            const int bx = L.x + (int)(o & 1), by = L.y + (int)((o >> 1) & 1), bz = L.z + ((D == 3) ? (int)((o >> 2) & 1) : 0);
+            bool won;
+            const uint32_t slot = claim_block<D>(d, bx, by, bz, won);
+            // the blocks this round created take their dense indices with ONE atomic per warp
+            const uint32_t active_lanes = __activemask();
+            const uint32_t wmask = __ballot_sync(active_lanes, won);
+            if (wmask) {
+                const int first = __ffs(wmask) - 1;
+                uint32_t base = 0;
+                if ((int)lane == first) base = atomicAdd(&d.counters->num_active_blocks, (uint32_t)__popc(wmask));
+                base = __shfl_sync(active_lanes, base, first);
+                if (won) publish_block(d, slot, base + __popc(wmask & ((1u << lane) - 1u)), make_int4(bx, by, bz, 0));
+            }
+            if (o == 0) s_lead[warp][q].w = (int)slot; // offset (0,..,0): the slot that identifies the run's block
+        }
+    }
+    __syncwarp();
+    before = 0;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t i = warp_base + j * 32 + lane;
+        const uint32_t upto = before + __popc(lmask[j] & (0xffffffffu >> (31 - lane))); // leaders at or before me
+        before += __popc(lmask[j]);
+        if (i < n_live) {
+            uint32_t pk = NONE;
+            if (alive[j]) {
+                const uint32_t slot = (uint32_t)s_lead[warp][upto - 1].w;
+                if (slot != NONE) pk = slot * CELLS_PER_BLOCK + cell[j];
+            }
+            d.pkey[i] = pk;
+        }
+    }
+
 }
 
 // ---- update_block_particle_count (sort.wgsl:89-99), one bin per cell ---------------------------------
 __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < d.counters->n_live;
-    uint32_t ck = NONE;
-    if (active) {
-        const uint32_t pk = d.pkey[i];
-        if (pk != NONE) {
-            const uint32_t hid = d.hvals[pk >> 6];
-            if (hid < d.capacity) ck = hid * CELLS_PER_BLOCK + (pk & 63u);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SORT_PER_WARP;
+    const uint32_t n_live = d.counters->n_live;
+    uint32_t ck[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t i = warp_base + j * 32 + lane;
+        ck[j] = (i < n_live) ? d.pkey[i] : NONE;
+    }
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        if (ck[j] != NONE) {
+            const uint32_t hid = d.hvals[ck[j] >> 6];
+            ck[j] = (hid < d.capacity) ? hid * CELLS_PER_BLOCK + (ck[j] & 63u) : NONE;
         }
     }
     // Runs of consecutive lanes in the same cell (the buffers are nearly sorted already) share one atomic.
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t prev = __shfl_up_sync(0xffffffffu, ck, 1);
-    const bool leader = (lane == 0) || (prev != ck);
-    const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
-    const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
-    const int L = 31 - __clz(below);
-    const uint32_t above = (L == 31) ? 0u : (leaders >> (L + 1));
-    const int run = above ? __ffs(above) : (32 - L);
-    uint32_t base = 0;
-    if (leader && ck != NONE) base = atomicAdd(d.cell_start + ck, (uint32_t)run);
-    base = __shfl_sync(0xffffffffu, base, L);
-    if (active) {
-        d.pkey[i] = ck;
-        d.rank[i] = base + (lane - (uint32_t)L);
+    uint32_t base[SORT_ITEMS];
+    int lead[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, ck[j], 1);
+        const bool leader = (lane == 0) || (prev != ck[j]);
+        const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
+        const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
+        const int L = 31 - __clz(below);
+        const uint32_t above = (L == 31) ? 0u : (leaders >> (L + 1));
+        const int run = above ? __ffs(above) : (32 - L);
+        lead[j] = L;
+        base[j] = (leader && ck[j] != NONE) ? atomicAdd(d.cell_start + ck[j], (uint32_t)run) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t i = warp_base + j * 32 + lane;
+        const uint32_t b = __shfl_sync(0xffffffffu, base[j], lead[j]);
+        if (i < n_live) {
+            d.pkey[i] = ck[j];
+            d.rank[i] = b + (lane - (uint32_t)lead[j]);
+        }
     }
 }
 
@@ -276,19 +347,35 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
                 d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
         }
     }
-    if (i >= d.counters->n_live) return;
-    uint32_t ck = d.pkey[i];
-    if (ck != NONE) {
-        const uint32_t dest = d.cell_start[ck] + d.rank[i];
-        d.sorted_ids[dest] = i;
-        if (d.has_bodies) d.cdf_aff[cur ^ 1][dest] = 0u; // default cdf; k_g2p_cdf overwrites the flagged blocks
-    } else {
-        // Particle of a dropped block (capacity overflow): parked after the sorted range so that
-        // its state survives the ping-pong (see k_g2p tail).
-        uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-        uint32_t total = d.cell_start[nb * CELLS_PER_BLOCK];
-        uint32_t k = atomicAdd(&d.counters->dropped_particles, 1u);
-        d.sorted_ids[total + k] = i;
+    // particles: SORT_ITEMS per thread, see k_touch
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SORT_PER_WARP;
+    const uint32_t n_live = d.counters->n_live;
+    if (warp_base >= n_live) return;
+    uint32_t ck[SORT_ITEMS], rk[SORT_ITEMS], dest[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t p = warp_base + j * 32 + lane;
+        ck[j] = (p < n_live) ? d.pkey[p] : NONE;
+        rk[j] = (p < n_live) ? d.rank[p] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) dest[j] = (ck[j] != NONE) ? d.cell_start[ck[j]] + rk[j] : NONE;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t p = warp_base + j * 32 + lane;
+        if (p >= n_live) continue;
+        if (ck[j] != NONE) {
+            d.sorted_ids[dest[j]] = p;
+            if (d.has_bodies) d.cdf_aff[cur ^ 1][dest[j]] = 0u; // default cdf; k_g2p_cdf overwrites the flagged blocks
+        } else {
+            // Particle of a dropped block (capacity overflow): parked after the sorted range so that
+            // its state survives the ping-pong (see k_g2p tail).
+            uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+            uint32_t total = d.cell_start[nb * CELLS_PER_BLOCK];
+            uint32_t k = atomicAdd(&d.counters->dropped_particles, 1u);
+            d.sorted_ids[total + k] = p;
+        }
     }
 }
 
@@ -301,13 +388,13 @@ void launch_clear(const LaunchCfg& c, const DeviceData& d) {
 }
 void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
-    if (c.dim == 2) k_touch<2><<<div_up(d.n, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d, cur);
-    else k_touch<3><<<div_up(d.n, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d, cur);
+    if (c.dim == 2) k_touch<2><<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d, cur);
+    else k_touch<3><<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 void launch_count(const LaunchCfg& c, const DeviceData& d) {
     if (d.n == 0) return;
-    k_count<<<div_up(d.n, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d);
+    k_count<<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
 void launch_scan_cells(const LaunchCfg& c, const DeviceData& d) {
@@ -331,9 +418,10 @@ void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur) {
     // and in practice far fewer; the grid is sized for whichever is larger)
     uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
     if (max_blocks > d.capacity) max_blocks = d.capacity;
-    uint64_t threads = d.has_bodies ? (max_blocks > d.n ? max_blocks : d.n) : d.n;
-    if (c.dim == 2) k_scatter<2><<<div_up(threads, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d, cur);
-    else k_scatter<3><<<div_up(threads, SORT_THREADS), SORT_THREADS, 0, c.stream>>>(d, cur);
+    uint64_t ctas_p = div_up(d.n, SORT_PER_CTA), ctas_b = d.has_bodies ? div_up(max_blocks, SORT_THREADS) : 0;
+    int ctas = (int)(ctas_p > ctas_b ? ctas_p : ctas_b);
+    if (c.dim == 2) k_scatter<2><<<ctas, SORT_THREADS, 0, c.stream>>>(d, cur);
+    else k_scatter<3><<<ctas, SORT_THREADS, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len, uint64_t* scan_state,
