@@ -5,7 +5,9 @@
 
 A "step" is one testbed frame of the hot path = 20 substeps (sand3.rs:54 / elastic_cut3.rs:54) over
 the synthetic scene named in `config.workload`. At N=1 that is BASELINE.json configs[1]: the 3D
-corotated-elastic cube drop on a static ground cuboid, 1M particles. Particle state is resident in
+corotated-elastic cube drop on a static ground cuboid, 1M particles. At N>1 it is configs[4], the 3D
+Drucker-Prager sand dam break, slab-sharded along x with 2M particles per GPU (weak scaling; N=8 is the
+16M-particle scene the north star names); `--workload cube` runs the stretched cube instead. Particle state is resident in
 HBM when the timed region starts (it lives there in the reference too: src/pipeline.rs:130-168 uploads
 once); `e2e` times the same frames through the C ABI with HOST buffers: per frame the body poses and
 velocities are uploaded from host memory (src_testbed/step.rs:79-119) and the body poses plus all
@@ -36,9 +38,10 @@ UNIT = "particle-substeps/s"
 BYTES_P2G = 66.0
 BYTES_G2P_ELASTIC = 162.0
 BYTES_G2P_SAND = 218.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_g2p launch at 1M particles, from the committed
-# `ncu --set full` capture (profiles/); None until a capture of the current kernel is committed.
-G2P_NCU_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_g2p launch on the 1M-particle cube, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_full_1M_cube.md: 77.67 MB read + 62.43 MB written).
+G2P_NCU_TRAFFIC_BYTES = 140.09e6
+G2P_NCU_TRAFFIC_PARTICLES = 1_000_000
 
 
 def load_peaks():
@@ -102,12 +105,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_scene(n_side, contact=True, nx=None):
+DAM_SLAB = (50, 200, 200)  # particles per GPU of the sand dam: 2M (x 8 GPUs = the 16M scene of configs[4])
+
+
+def resolve_workload(args, world):
+    if args.workload != "auto":
+        return args.workload
+    return "cube" if world == 1 else "dam"
+
+
+def build_scene(args, world, workload):
     from wgsparkl_b200 import scenes
 
-    # configs[1]: 3D elastic cube drop, n_side^3 particles. The cube starts just above the ground cuboid
-    # so that the timed region covers the contact phase (CPIC active), the more expensive regime.
-    return scenes.elastic_cube_3d(n_side, y_offset=-5.0 if contact else 60.0, grid_capacity=60_000, nx=nx)
+    if workload == "dam":
+        # configs[4]: sand dam break inside a 4-wall box, 2M particles per GPU, slabs along x.
+        return scenes.sand_dam_3d(DAM_SLAB[0] * world, DAM_SLAB[1], DAM_SLAB[2], grid_capacity=65_536)
+    # configs[1]: 3D elastic cube drop, n_side^3 particles (stretched along x for N > 1). The cube starts just
+    # above the ground cuboid so that the timed region covers the contact phase (CPIC active), the more
+    # expensive regime.
+    return scenes.elastic_cube_3d(args.n_side, y_offset=-5.0, grid_capacity=60_000, nx=args.n_side * world)
+
+
+def workload_name(workload, world, n_total):
+    if workload == "dam":
+        return ("3D Drucker-Prager sand dam break in a 4-wall box (BASELINE configs[4]), %d particles = %d per GPU"
+                % (n_total, n_total // world))
+    return ("3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])"
+            + ("" if world == 1 else ", stretched to %d x 1M particles along x" % world))
 
 
 def frame_io_arrays(scene):
@@ -137,9 +161,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     hbm_peak, peak_kind = load_peaks()
 
-    # N = 1: BASELINE configs[1] (1M-particle elastic cube). N > 1: the same block stretched along x to N x 1M
-    # particles and slab-sharded over the N GPUs (weak scaling; migration + node halo over NCCL every substep).
-    scene = build_scene(args.n_side, nx=args.n_side * world)
+    # N = 1: BASELINE configs[1] (1M-particle elastic cube). N > 1: configs[4], the sand dam break at 2M
+    # particles per GPU, slab-sharded over the N GPUs (weak scaling; migration + node halo every substep).
+    workload = resolve_workload(args, world)
+    scene = build_scene(args, world, workload)
     n_total = len(scene["particles"])
     spf = scene["substeps_per_frame"]
     stream = torch.cuda.Stream(device=local_rank)
@@ -211,47 +236,53 @@ def run_ours(args):
     h2d = nb * (poses.dtype.itemsize + vels.dtype.itemsize)
     d2h = nb * poses.dtype.itemsize + n_local * 16
 
-    roof = None
     nblocks, overflow = data.status()
-    if sharded is None:
-        # per-kernel durations (CUDA events around each pass, on the launching stream) for the roofline
-        pipe.set_timestamps(True)
-        frames_prof = max(1, min(args.steps, 3))
+    # Per-kernel durations for the roofline: CUDA events around each pass, on the launching stream. At N > 1 this
+    # runs AFTER both timed regions, on each rank's own slab with the exchanges off (plain substeps), rank 0 reports.
+    pipe.set_timestamps(True)
+    frames_prof = max(1, min(args.steps, 3))
+    with torch.cuda.stream(stream):
         for _ in range(frames_prof):
-            frame_device()
-        t = pipe.timings_ms()
-        pipe.set_timestamps(False)
-        launches_per_kernel = frames_prof * spf
-        g2p_ms = t["g2p"] / launches_per_kernel
-        p2g_ms = t["p2g"] / launches_per_kernel
-        g2p_gbs = BYTES_G2P_ELASTIC * n_total / (g2p_ms * 1e-3) / 1e9
-        p2g_gbs = BYTES_P2G * n_total / (p2g_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_g2p (grid_update + g2p + particles_update)",
-                "achieved": g2p_gbs, "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s",
-                "frac": g2p_gbs / hbm_peak, "traffic": G2P_NCU_TRAFFIC_BYTES,
-                "bytes_per_particle": BYTES_G2P_ELASTIC, "ms_per_launch": g2p_ms,
-                "p2g": {"achieved": p2g_gbs, "frac": p2g_gbs / hbm_peak, "bytes_per_particle": BYTES_P2G,
-                        "ms_per_launch": p2g_ms, "note": "both P2G instantiations, serialised (timestamps mode)"},
-                "pass_ms_per_substep": {k: v / launches_per_kernel for k, v in t.items()}}
+            pipe.queue_step(data, spf)
+    torch.cuda.synchronize()
+    t = pipe.timings_ms()
+    pipe.set_timestamps(False)
+    launches_per_kernel = frames_prof * spf
+    sand = workload == "dam"
+    bytes_g2p = BYTES_G2P_SAND if sand else BYTES_G2P_ELASTIC
+    n_roof = data.num_live() if sharded is not None else n_total
+    g2p_ms = t["g2p"] / launches_per_kernel
+    p2g_ms = t["p2g"] / launches_per_kernel
+    g2p_gbs = bytes_g2p * n_roof / (g2p_ms * 1e-3) / 1e9
+    p2g_gbs = BYTES_P2G * n_roof / (p2g_ms * 1e-3) / 1e9
+    traffic = None
+    if G2P_NCU_TRAFFIC_BYTES is not None and not sand and world == 1 and n_total == G2P_NCU_TRAFFIC_PARTICLES:
+        traffic = G2P_NCU_TRAFFIC_BYTES
+    roof = {"bound": "hbm", "kernel": "k_g2p (grid_update + g2p + particles_update)",
+            "achieved": g2p_gbs, "peak": hbm_peak, "peak_source": peak_kind, "unit": "GB/s",
+            "frac": g2p_gbs / hbm_peak, "traffic": traffic,
+            "bytes_per_particle": bytes_g2p, "particles_per_launch": int(n_roof), "ms_per_launch": g2p_ms,
+            "p2g": {"achieved": p2g_gbs, "frac": p2g_gbs / hbm_peak, "bytes_per_particle": BYTES_P2G,
+                    "ms_per_launch": p2g_ms, "note": "both P2G instantiations, serialised (timestamps mode)"},
+            "pass_ms_per_substep": {k: v / launches_per_kernel for k, v in t.items()}}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])"
-                   + ("" if world == 1 else ", stretched to %d x 1M particles along x" % world),
+        "config": {"workload": workload_name(workload, world, n_total),
                    "particles_total": n_total, "particles_per_gpu": n_total // world, "substeps_per_step": spf,
                    "cell_width": scene["cell_width"], "active_blocks_rank0": nblocks,
                    "parallelism": "1 GPU" if world == 1 else
-                   "%d slabs along x (particle migration + node-halo exchange over NCCL every substep)" % world,
+                   "%d slabs along x (particle migration + node-halo exchange over NVLink peer stores, body "
+                   "impulses all-reduced over NCCL, every substep)" % world,
                    "l2": "inputs larger than L2 (%.0f MB of particle state per GPU)" % (n_total // world * 220 / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
-    if roof is not None:
-        out["roofline"] = roof
+    out["roofline"] = roof
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, scene)
     if rank == 0:
@@ -294,7 +325,11 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     oracle.set_threads(cores)
-    scene = build_scene(args.n_side)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = resolve_workload(args, world)
+    # bounded sample of the arm's workload: the cube as is; of the sand dam, ONE GPU's share (2M particles) -
+    # the metric is per particle-substep, and 16M particles would take minutes per substep on the host.
+    scene = build_scene(args, 1, workload)
     n = len(scene["particles"])
     spf = scene["substeps_per_frame"]
     sim = oracle.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
@@ -316,8 +351,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D corotated-elastic cube drop on a static ground cuboid (BASELINE configs[1])",
-                   "particles_per_gpu": n, "substeps_per_step": sample,
+        "config": {"workload": workload_name(workload, world, n * world),
+                   "particles_sampled": n, "substeps_per_step": sample,
                    "note": "CPU restatement of the reference's WGSL kernels (oracle/), OpenMP; the Rust/wgpu reference cannot be built here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d substeps per step x %d steps of the full %d-particle scene" % (sample, args.steps, n)},
@@ -333,6 +368,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=100, help="cube side in particles (100 -> 1M particles)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "cube", "dam"],
+                    help="auto: cube (configs[1]) at N=1, sand dam (configs[4], 2M particles per GPU) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -615,6 +615,8 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
     ALLOC(dev.block_flags, capacity);
     ALLOC(dev.block_f0, capacity);
     ALLOC(dev.cpic_list, capacity);
+    dev.g2p_list_len = capacity + ncap / G2P_ITEM + 1;
+    ALLOC(dev.g2p_list, dev.g2p_list_len);
     ALLOC(dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2);
     ALLOC(dev.bodies, B200MPM_MAX_BODIES);
     ALLOC(dev.sim, 1);

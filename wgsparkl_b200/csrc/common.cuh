@@ -94,6 +94,8 @@ struct Counters {
     uint32_t work_g2p;
     uint32_t work_cdf;
     uint32_t num_cpic_blocks; // blocks (with particles) whose tile holds a collider this substep
+    uint32_t num_g2p_items; // entries at the FRONT of g2p_list this substep (collider-side blocks: slow items first)
+    uint32_t num_g2p_back; // entries at the BACK of g2p_list (all other blocks), filled downwards from the end
     uint32_t dropped_particles; // particles whose block was dropped (overflow) or that left the slab
     uint32_t n_live; // particles currently held (== n unless the data is a slab of a sharded run)
     uint32_t send_count[2]; // emigrants packed for the -x / +x neighbour (sharded runs)
@@ -101,6 +103,16 @@ struct Counters {
     uint32_t shard_seq; // substep sequence number of the peer-to-peer exchange flags
     uint32_t n_base; // live count at the start of the substep: where the immigrants are appended
 };
+
+// G2P work items: a block's sorted range in parts of at most this many particles (k_scatter builds the list).
+// Bounded items keep the last scheduling round short when blocks differ a lot in population (a compressed
+// material packs 3x the seeding density into the bottom blocks), and blocks without particles are never visited.
+constexpr uint32_t G2P_ITEM = 512;
+constexpr uint32_t G2P_MAX_PARTS = 255;
+__host__ __device__ inline uint32_t g2p_parts(uint32_t n) {
+    const uint32_t p = (n + G2P_ITEM - 1) / G2P_ITEM;
+    return p < G2P_MAX_PARTS ? p : G2P_MAX_PARTS;
+}
 
 // ---- all device pointers of one MpmData --------------------------------------------------
 struct DeviceData {
@@ -142,6 +154,8 @@ struct DeviceData {
     uint8_t* block_f0; // capacity: 1 if one of the block's own nodes is near / inside a collider (k_block_prepare)
     uint32_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)
     uint32_t* cpic_list; // capacity: compact list of flagged blocks that hold particles
+    uint32_t* g2p_list; // g2p_list_len: (block | part << 24) work items of <= G2P_ITEM particles
+    uint32_t g2p_list_len; // capacity + n / G2P_ITEM + 1
 
     BodyDev* bodies;
     SimState* sim;

@@ -19,7 +19,11 @@
 
 namespace b2 {
 
-constexpr int G2P_THREADS = 128;
+#ifndef G2P_THREADS_N
+#define G2P_THREADS_N 128
+#endif
+constexpr int G2P_THREADS = G2P_THREADS_N;
+constexpr int G2P_CTA_SCALE = 128 / G2P_THREADS; // CTAs per SM scale with 1 / CTA size
 #ifndef G2P_FMA_GATHER
 #define G2P_FMA_GATHER 1
 #endif
@@ -34,7 +38,7 @@ constexpr int G2P_THREADS = 128;
 #endif
 
 template <int D, bool PLASTIC, bool CPIC>
-__global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MINB_P : G2P_MINB_E) k_g2p(DeviceData d, int cur) {
+__global__ void __launch_bounds__(G2P_THREADS, (PLASTIC ? G2P_MINB_P : G2P_MINB_E) * G2P_CTA_SCALE) k_g2p(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC;
     __shared__ float4 tile_v[TC];
@@ -58,15 +62,26 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MINB_P : G2P_MINB_E
     const float4* __restrict__ Fb = d.Fb[cur];
     const float* __restrict__ Fc = d.Fc[cur];
 
+    // (block, part) items of <= G2P_ITEM particles from k_scatter: collider-side blocks first (front of the list)
+    const uint32_t nfront = d.counters->num_g2p_items, nitems = nfront + d.counters->num_g2p_back;
     while (true) {
         __syncthreads();
-        if (t == 0) s_next = atomicAdd(&d.counters->work_g2p, 1u);
+        if (t == 0) {
+            const uint32_t w = atomicAdd(&d.counters->work_g2p, 1u);
+            s_next = (w < nitems) ? d.g2p_list[w < nfront ? w : d.g2p_list_len - 1u - (w - nfront)] : NONE;
+        }
         __syncthreads();
-        const uint32_t b = s_next;
-        if (b >= nb) break;
-        const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
-        const uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
-        if (first == last) continue;
+        const uint32_t item = s_next;
+        if (item == NONE) break;
+        const uint32_t b = item & 0xffffffu;
+        uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
+        uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
+        {
+            const uint32_t parts = g2p_parts(last - first), part = item >> 24;
+            const uint32_t per = (last - first + parts - 1) / parts;
+            first = min(first + part * per, last);
+            last = min(first + per, last);
+        }
         if (t < NA) s_nbr[t] = d.nbr[b * NA + t];
         __syncthreads();
         // Stage the tile; grid_update (grid_update.wgsl:45-64) on the fly.
@@ -343,7 +358,7 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MINB_P : G2P_MINB_E
 
 template <int D>
 static void launch_g2p_dim(const LaunchCfg& c, const DeviceData& d, int cur) {
-    const int grid = c.num_sms * 8;
+    const int grid = c.num_sms * 8 * G2P_CTA_SCALE;
     if (d.has_plastic) {
         if (d.has_bodies) k_g2p<D, true, true><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);
         else k_g2p<D, true, false><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) k_begin_substep(DeviceData d) {
         c->work_g2p = 0;
         c->work_cdf = 0;
         c->num_cpic_blocks = 0;
+        c->num_g2p_items = 0;
+        c->num_g2p_back = 0;
         c->dropped_particles = 0;
     }
     if (id < d.sim->num_bodies) {

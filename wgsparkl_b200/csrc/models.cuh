@@ -107,18 +107,14 @@ __device__ __forceinline__ bool dp_project_sv(const Material& m, const float* sv
 //     J^2 - 1 = det(I + M) - 1 = tr M + ((tr M)^2 - tr M^2) / 2 + det M,   J - 1 = (J^2 - 1) / (1 + J)
 //   Everything is a polynomial in the SMALL matrix M, so (Sigma - 1) and (J - 1) keep their relative accuracy
 //   (the stiffness multiplies them by 1e7..1e9), at ~1/3 of the instructions of the Jacobi SVD.
-// Returns false (caller falls back to the SVD) when the strain is too large or F is inverted.
-__device__ __forceinline__ bool corotated_stress_small_strain3(const Material& m, const float* F, float* tau) {
-    const double f0 = F[0], f1 = F[1], f2 = F[2], f3 = F[3], f4 = F[4], f5 = F[5], f6 = F[6], f7 = F[7], f8 = F[8];
-    const float m00 = (float)(f0 * f0 + f1 * f1 + f2 * f2 - 1.0);
-    const float m11 = (float)(f3 * f3 + f4 * f4 + f5 * f5 - 1.0);
-    const float m22 = (float)(f6 * f6 + f7 * f7 + f8 * f8 - 1.0);
-    const float m01 = (float)(f0 * f3 + f1 * f4 + f2 * f5);
-    const float m02 = (float)(f0 * f6 + f1 * f7 + f2 * f8);
-    const float m12 = (float)(f3 * f6 + f4 * f7 + f5 * f8);
+// Valid while small_strain3() holds (|M|_F <= 0.1, F not inverted); the caller takes the SVD path otherwise.
+__device__ __forceinline__ bool small_strain3(const ShiftedGram3& g) {
+    const float tr2 = g.a00 * g.a00 + g.a11 * g.a11 + g.a22 * g.a22 + 2.0f * (g.a01 * g.a01 + g.a02 * g.a02 + g.a12 * g.a12);
+    return (tr2 <= 0.01f) && (g.detF > 0.0f);
+}
+__device__ __forceinline__ void corotated_stress_small_strain3(const Material& m, const float* F, const ShiftedGram3& g, float* tau) {
+    const float m00 = g.a00, m11 = g.a11, m22 = g.a22, m01 = g.a01, m02 = g.a02, m12 = g.a12;
     const float tr2 = m00 * m00 + m11 * m11 + m22 * m22 + 2.0f * (m01 * m01 + m02 * m02 + m12 * m12); // tr M^2 = |M|_F^2
-    const float detF = F[0] * (F[4] * F[8] - F[7] * F[5]) - F[3] * (F[1] * F[8] - F[7] * F[2]) + F[6] * (F[1] * F[5] - F[4] * F[2]);
-    if (!(tr2 <= 0.01f) || !(detF > 0.0f)) return false;
     // Horner: X = M (c1 + M (c2 + M (c3 + M (c4 + M (c5 + c6 M))))), symmetric 3x3 as (00, 11, 22, 01, 02, 12)
     float q00 = -0.2255859375f * m00 + 0.24609375f, q11 = -0.2255859375f * m11 + 0.24609375f,
           q22 = -0.2255859375f * m22 + 0.24609375f;
@@ -163,7 +159,6 @@ __device__ __forceinline__ bool corotated_stress_small_strain3(const Material& m
             tau[c * 3 + r] = s;
             tau[r * 3 + c] = s;
         }
-    return true;
 }
 
 // Steps (6)-(8) of the particle update (particle_update.wgsl:95-127): phase/stretch test,
@@ -173,8 +168,16 @@ template <int D, bool PLASTIC>
 __device__ __forceinline__ void constitutive_update(const Material& m, uint32_t& flags, float* F, float4& plastic,
                                                     float* tau) {
     const bool neo = (m.model == B200MPM_MODEL_NEO_HOOKEAN);
+    ShiftedGram3 gram;
+    if (D == 3) gram = shifted_gram3(F);
     if (D == 3 && !PLASTIC && !neo) {
-        if (corotated_stress_small_strain3(m, F, tau)) return;
+        // The choice is made per WARP: a warp with even one strongly strained particle would execute both paths
+        // one after the other, so it takes the SVD path for everybody instead (same result, one pass).
+        const bool small = small_strain3(gram);
+        if (__ballot_sync(__activemask(), !small) == 0u) {
+            corotated_stress_small_strain3(m, F, gram, tau);
+            return;
+        }
     }
     float U[D * D], S[D], Sm1[D], V[D * D];
     float phase = (flags & FLAG_PHASE_BROKEN) ? 0.0f : m.phase;
@@ -182,7 +185,7 @@ __device__ __forceinline__ void constitutive_update(const Material& m, uint32_t&
     const bool need_svd = !neo || (PLASTIC && (may_stretch || phase == 0.0f));
     if (need_svd) {
         bool have = false;
-        if (D == 3) have = svd3_fast(F, U, S, Sm1, V);
+        if (D == 3) have = svd3_fast(F, gram, U, S, Sm1, V);
         if (!have) {
             if (D == 2) svd2(F, U, S, V);
             else svd3<4>(F, U, S, V);

@@ -331,20 +331,44 @@ template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) d.counters->prev_active_blocks = min(d.counters->num_active_blocks, d.capacity); // for the next clear
-    if (d.has_bodies) {
-        // CPIC work list: a block runs the collider-aware paths iff one of the 2^D blocks its tile overlaps
-        // has a node near / inside a collider. (i doubles as a block index here.)
+    {
+        // Per-block work lists (i doubles as a block index here; the grid covers capacity blocks).
         const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-        if (i < nb) {
-            int flag = 0;
+        uint32_t np = 0;
+        if (i < nb) np = d.cell_start[(i + 1) * CELLS_PER_BLOCK] - d.cell_start[i * CELLS_PER_BLOCK];
+        int flag = 0;
+        if (d.has_bodies && i < nb) {
+            // CPIC: a block runs the collider-aware paths iff one of the 2^D blocks its tile overlaps has a node
+            // near / inside a collider.
 #pragma unroll
             for (int o = 0; o < Dim<D>::NASSOC; ++o) {
                 uint32_t hn = d.nbr[i * Dim<D>::NASSOC + o];
                 if (hn != NONE) flag |= d.block_f0[hn];
             }
             d.block_flags[i] = (uint32_t)flag;
-            if (flag && d.cell_start[i * CELLS_PER_BLOCK] != d.cell_start[(i + 1) * CELLS_PER_BLOCK])
-                d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
+            if (flag && np != 0u) d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
+        }
+        // G2P items: blocks that hold particles, in parts of <= G2P_ITEM particles. Collider-side blocks cost
+        // several times more per particle (ghost-velocity gather), so they go to the FRONT of the list and are
+        // scheduled first; everything else fills the list from the back. One atomic per warp and list end.
+        const uint32_t parts = g2p_parts(np);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t mine = ((flag != 0) == (side == 0)) ? parts : 0u;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)(threadIdx.x & 31) >= o) incl += v;
+            }
+            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+            if (warp_total == 0u) continue; // (warp-uniform)
+            uint32_t base = 0;
+            if ((threadIdx.x & 31) == 31)
+                base = atomicAdd(side == 0 ? &d.counters->num_g2p_items : &d.counters->num_g2p_back, warp_total);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+            for (uint32_t p = 0; p < mine; ++p)
+                d.g2p_list[side == 0 ? base + p : d.g2p_list_len - 1u - (base + p)] = i | (p << 24);
         }
     }
     // particles: SORT_ITEMS per thread, see k_touch
@@ -418,7 +442,7 @@ void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur) {
     // and in practice far fewer; the grid is sized for whichever is larger)
     uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
     if (max_blocks > d.capacity) max_blocks = d.capacity;
-    uint64_t ctas_p = div_up(d.n, SORT_PER_CTA), ctas_b = d.has_bodies ? div_up(max_blocks, SORT_THREADS) : 0;
+    uint64_t ctas_p = div_up(d.n, SORT_PER_CTA), ctas_b = div_up(max_blocks, SORT_THREADS);
     int ctas = (int)(ctas_p > ctas_b ? ctas_p : ctas_b);
     if (c.dim == 2) k_scatter<2><<<ctas, SORT_THREADS, 0, c.stream>>>(d, cur);
     else k_scatter<3><<<ctas, SORT_THREADS, 0, c.stream>>>(d, cur);

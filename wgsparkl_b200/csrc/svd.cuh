@@ -202,9 +202,10 @@ __host__ __device__ inline void svd3(const float* F, float* U, float* S, float* 
 //   * rolled sweep loop that stops once |off(M)| <= 1e-6 |diag(M)| (3 sweeps for almost every matrix, f32
 //     round-off floor is ~2e-7) - a rolled body also keeps the kernel inside the instruction cache;
 //   * no sorting (every use on the path is symmetric in the singular triplets) and no Gram-Schmidt:
-//     with det F > 0 and all sigma > 0.5,  u_i = F v_i / sigma_i  directly.
+//     with det F > 0 and all sigma > 0.2,  u_i = F v_i / sigma_i  directly.
 // Also returns sigma_i - 1 (accurate relative to itself), which the strain / stress formulas consume.
-// Returns false - caller falls back to svd3 - for det F <= 0 or any sigma <= 0.5.
+// Returns false - caller falls back to svd3 - for det F <= 0 or any sigma <= 0.2 (there sigma - 1 from mu has
+// lost more than ~1e-6 of relative accuracy to the cancellation in 1 + mu).
 __device__ __forceinline__ void jacobi_rot_fast(float& app, float& aqq, float& apq, float& apr, float& aqr, float* vp,
                                                 float* vq) {
     const float d = aqq - app;
@@ -232,16 +233,26 @@ __device__ __forceinline__ void jacobi_rot_fast(float& app, float& aqq, float& a
     }
 }
 
-__device__ __forceinline__ bool svd3_fast(const float* F, float* U, float* S, float* Sm1, float* V) {
-    const float detF = F[0] * (F[4] * F[8] - F[7] * F[5]) - F[3] * (F[1] * F[8] - F[7] * F[2]) + F[6] * (F[1] * F[5] - F[4] * F[2]);
-    if (!(detF > 0.0f)) return false;
+// M = F^T F - I formed in f64 (products of two f32 are exact there) and rounded ONCE to f32, plus det F.
+struct ShiftedGram3 {
+    float a00, a11, a22, a01, a02, a12, detF;
+};
+__device__ __forceinline__ ShiftedGram3 shifted_gram3(const float* F) {
+    ShiftedGram3 g;
+    g.detF = F[0] * (F[4] * F[8] - F[7] * F[5]) - F[3] * (F[1] * F[8] - F[7] * F[2]) + F[6] * (F[1] * F[5] - F[4] * F[2]);
     const double f0 = F[0], f1 = F[1], f2 = F[2], f3 = F[3], f4 = F[4], f5 = F[5], f6 = F[6], f7 = F[7], f8 = F[8];
-    float a00 = (float)(f0 * f0 + f1 * f1 + f2 * f2 - 1.0);
-    float a11 = (float)(f3 * f3 + f4 * f4 + f5 * f5 - 1.0);
-    float a22 = (float)(f6 * f6 + f7 * f7 + f8 * f8 - 1.0);
-    float a01 = (float)(f0 * f3 + f1 * f4 + f2 * f5);
-    float a02 = (float)(f0 * f6 + f1 * f7 + f2 * f8);
-    float a12 = (float)(f3 * f6 + f4 * f7 + f5 * f8);
+    g.a00 = (float)(f0 * f0 + f1 * f1 + f2 * f2 - 1.0);
+    g.a11 = (float)(f3 * f3 + f4 * f4 + f5 * f5 - 1.0);
+    g.a22 = (float)(f6 * f6 + f7 * f7 + f8 * f8 - 1.0);
+    g.a01 = (float)(f0 * f3 + f1 * f4 + f2 * f5);
+    g.a02 = (float)(f0 * f6 + f1 * f7 + f2 * f8);
+    g.a12 = (float)(f3 * f6 + f4 * f7 + f5 * f8);
+    return g;
+}
+
+__device__ __forceinline__ bool svd3_fast(const float* F, const ShiftedGram3& g, float* U, float* S, float* Sm1, float* V) {
+    if (!(g.detF > 0.0f)) return false;
+    float a00 = g.a00, a11 = g.a11, a22 = g.a22, a01 = g.a01, a02 = g.a02, a12 = g.a12;
     float v0[3] = {1, 0, 0}, v1[3] = {0, 1, 0}, v2[3] = {0, 0, 1};
 #pragma unroll 1
     for (int sweep = 0; sweep < 6; ++sweep) {
@@ -252,7 +263,7 @@ __device__ __forceinline__ bool svd3_fast(const float* F, float* U, float* S, fl
         const float dg2 = a00 * a00 + a11 * a11 + a22 * a22;
         if (off2 <= 1e-12f * dg2) break;
     }
-    if (!(fminf(a00, fminf(a11, a22)) > -0.75f)) return false;
+    if (!(fminf(a00, fminf(a11, a22)) > -0.96f)) return false; // sigma <= 0.2: 1 + mu cancels, svd3 uses |F v|
     auto finish = [&](int i, float mu, const float* v) {
         const float x = 1.0f + mu;
         const float sm1 = __fdividef(mu, 1.0f + x * rsqrtf(x));
