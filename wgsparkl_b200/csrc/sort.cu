@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
         const uint32_t parts = g2p_parts(np);
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
-            const uint32_t mine = ((flag != 0) == (side == 0)) ? parts : 0u;
+            const bool slow = (flag != 0) || np > G2P_ITEM + G2P_ITEM / 4; // collider-side, or densely populated
+            const uint32_t mine = (slow == (side == 0)) ? parts : 0u;
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
