@@ -78,6 +78,27 @@ pub enum b200mpm_pipeline {}
 pub enum b200mpm_data {}
 
 #[link(name = "b200mpm")]
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b200mpm_block_info {
+    pub vid: [i32; 3],
+    pub first_particle: u32,
+    pub num_particles: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b200mpm_node {
+    pub momentum_velocity_mass: [f32; 4],
+    pub cdf_distance: f32,
+    pub cdf_affinities: u32,
+    pub cdf_closest_id: u32,
+}
+
+pub const B200MPM_PARTICLE_RECORD_BYTES: u32 = 128;
+pub const B200MPM_HALO_BLOCK_BYTES: u32 = 1040;
+pub const B200MPM_SHARD_HEADER_BYTES: u32 = 16;
+
 extern "C" {
     pub fn b200mpm_last_error() -> *const c_char;
     pub fn b200mpm_pipeline_create(device: c_int, dim: c_int, out: *mut *mut b200mpm_pipeline) -> c_int;
@@ -112,4 +133,51 @@ extern "C" {
     pub fn b200mpm_data_status(d: *mut b200mpm_data, num_active_blocks: *mut u32) -> c_int;
     pub fn b200mpm_sort_only(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;
     pub fn b200mpm_prefix_sum_u32(p: *mut b200mpm_pipeline, data: *mut u32, len: usize) -> c_int;
+    pub fn b200mpm_read_grid(
+        d: *mut b200mpm_data,
+        blocks: *mut b200mpm_block_info,
+        nodes: *mut b200mpm_node,
+        capacity: usize,
+        num_blocks: *mut usize,
+    ) -> c_int;
+    pub fn b200mpm_read_sorted_ids(d: *mut b200mpm_data, out: *mut u32) -> c_int;
+
+    // ---- multi-GPU slab sharding (one process per GPU) ----
+    pub fn b200mpm_data_create_ex(
+        p: *mut b200mpm_pipeline,
+        params: *const b200mpm_sim_params,
+        particles: *const b200mpm_particle,
+        num_particles: usize,
+        particle_ids: *const u32,
+        particle_capacity: usize,
+        bodies: *const b200mpm_body,
+        num_bodies: usize,
+        cell_width: f32,
+        grid_capacity: u32,
+        out: *mut *mut b200mpm_data,
+    ) -> c_int;
+    pub fn b200mpm_slab_configure(d: *mut b200mpm_data, x_lo: i32, x_hi: i32) -> c_int;
+    pub fn b200mpm_data_num_live(d: *mut b200mpm_data, num_live: *mut usize) -> c_int;
+    pub fn b200mpm_shard_emigrate(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_left: *mut c_void, dev_right: *mut c_void, cap_records: u32) -> c_int;
+    pub fn b200mpm_shard_immigrate(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_buffer: *const c_void, cap_records: u32) -> c_int;
+    pub fn b200mpm_shard_step_begin(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;
+    pub fn b200mpm_shard_halo_pack(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_left: *mut c_void, dev_right: *mut c_void, cap_blocks: u32) -> c_int;
+    pub fn b200mpm_shard_halo_add(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_buffer: *const c_void, cap_blocks: u32) -> c_int;
+    pub fn b200mpm_shard_impulses(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_buf: *mut i32, write: c_int) -> c_int;
+    pub fn b200mpm_shard_step_end(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;
+    pub fn b200mpm_nccl_unique_id(out: *mut c_void, bytes: usize) -> c_int;
+    pub fn b200mpm_shard_comm_init(
+        p: *mut b200mpm_pipeline,
+        d: *mut b200mpm_data,
+        rank: c_int,
+        world: c_int,
+        unique_id: *const c_void,
+        migration_cap_records: u32,
+        halo_cap_blocks: u32,
+    ) -> c_int;
+    pub fn b200mpm_shard_step(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, num_substeps: u32) -> c_int;
+    pub fn b200mpm_shard_p2p_export(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, handle_out: *mut c_void, bytes: usize) -> c_int;
+    pub fn b200mpm_shard_p2p_connect(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, handles: *const c_void, num_handles: usize) -> c_int;
+    pub fn b200mpm_read_positions_unordered(d: *mut b200mpm_data, out: *mut f32, capacity: usize, count: *mut usize) -> c_int;
+    pub fn b200mpm_read_particles_unordered(d: *mut b200mpm_data, out: *mut b200mpm_particle, ids: *mut u32, capacity: usize, count: *mut usize) -> c_int;
 }

@@ -101,3 +101,16 @@ def test_cpp_host_mirror_compiles_and_reports_no_device(tmp_path):
         assert "stepped" in res.stdout
     else:
         assert "no device" in res.stdout
+
+
+def test_rust_sys_file_declares_every_symbol():
+    """rust/wgsparkl_b200_sys.rs (the binding a wgsparkl maintainer adds; no rustc here) must name every function
+    include/b200mpm.h declares."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "b200mpm.h")).read()
+    rust = open(os.path.join(root, "rust", "wgsparkl_b200_sys.rs")).read()
+    declared = set(re.findall(r"\b(b200mpm_[a-z0-9_]+)\s*\(", header))
+    missing = sorted(f for f in declared if ("fn %s(" % f) not in rust)
+    assert not missing, missing

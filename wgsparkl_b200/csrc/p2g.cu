@@ -4,15 +4,17 @@
 // linked lists of the 3^D neighbouring cells (27 x max-list-length shared-memory iterations with
 // two barriers each, 16 hash probes per thread).
 //
-// B200 design (DESIGN.md §P2G): a block-local SCATTER over cell-sorted particles.
-//   * one CTA per active block; the block's particles (a contiguous range of the sorted order) are
-//     staged into shared memory with cp.async (LDGSTS, 16 bytes per request, no register staging);
-//   * ONE THREAD PER CELL: the thread walks the contiguous run of its cell's particles and reduces
+// B200 design (DESIGN.md §4 P2G): a block-local SCATTER over cell-sorted particles.
+//   * one WARP per half block (32 cells): a CTA is a single warp and an independent worker with its own
+//     staging buffers, tile and position in the dynamic work queue, so there is no CTA barrier anywhere;
+//     the warp's particles (a contiguous range of the sorted order, in windows of 256) are staged into
+//     shared memory with cp.async (LDGSTS, 16 bytes per request, no register staging);
+//   * ONE LANE PER CELL: the lane walks the contiguous run of its cell's particles and reduces
 //     their 3^D stencil contributions in REGISTERS (27 x 4 accumulators in 3D) — the segmented
 //     reduction over the cell's run never touches memory and costs ~8 issue slots per
 //     particle-node pair, against ~25 for a lane-per-node layout and ~44 for a shuffle-based
 //     segmented reduction;
-//   * the per-cell partial stencils are merged into the block's (BLOCK+2)^D shared-memory tile
+//   * the per-cell partial stencils are merged into the warp's (BLOCK+2)^D shared-memory tile
 //     in 3^D conflict-free phases (in phase s every cell adds to node cell+s: all distinct), so the
 //     shared-memory reduction needs no atomics (shared f32 atomics are CAS loops on sm_100);
 //   * the tile is flushed with one vector reduction per node (RED.E.ADD.F32x4, sm_90+) into the
