@@ -202,6 +202,12 @@ int b200mpm_read_body_vels(b200mpm_data* d, b200mpm_velocity* vels, size_t n);
 /* particles.positions (src/solver/particle3d.rs:177): vec4 per particle (2D: xy00), in the
  * caller's original particle order. `out` holds 4*num_particles floats. */
 int b200mpm_read_positions(b200mpm_data* d, float* out);
+/* Same result, asynchronous: the positions as of the work enqueued so far are gathered on the pipeline's stream
+ * and copied into `out` (which should be page-locked host memory, or the copy serialises) on a separate copy
+ * stream, overlapping with whatever is enqueued next; `out` is valid after b200mpm_sync. At most two readbacks
+ * are in flight (the third waits for the first). This is the wgpu staging-buffer + map_async pattern of the
+ * reference's readbacks (src_testbed/step.rs:131-176). */
+int b200mpm_read_positions_async(b200mpm_data* d, float* out);
 /* Full particle state, original order. */
 int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out);
 /* Sparse grid after the last substep, in the device's own block order.

@@ -129,6 +129,7 @@ extern "C" {
     pub fn b200mpm_read_body_poses(d: *mut b200mpm_data, poses: *mut b200mpm_pose, n: usize) -> c_int;
     pub fn b200mpm_read_body_vels(d: *mut b200mpm_data, vels: *mut b200mpm_velocity, n: usize) -> c_int;
     pub fn b200mpm_read_positions(d: *mut b200mpm_data, out: *mut f32) -> c_int;
+    pub fn b200mpm_read_positions_async(d: *mut b200mpm_data, out: *mut f32) -> c_int;
     pub fn b200mpm_read_particles(d: *mut b200mpm_data, out: *mut b200mpm_particle) -> c_int;
     pub fn b200mpm_data_status(d: *mut b200mpm_data, num_active_blocks: *mut u32) -> c_int;
     pub fn b200mpm_sort_only(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;

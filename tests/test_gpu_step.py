@@ -204,3 +204,34 @@ def test_timings_use_reference_pass_names(pipe3):
     assert tuple(t.keys()) == abi.PASS_NAMES
     assert t["p2g"] > 0.0 and t["g2p"] > 0.0 and t["grid sort"] > 0.0
     data.close()
+
+
+def test_async_position_readback_matches_blocking(pipe3):
+    """b200mpm_read_positions_async: snapshots taken between steps land (after sync) with exactly the values
+    the blocking read returns at the same points (up to atomic-order noise), also with three readbacks enqueued back to back."""
+    import torch
+
+    scene = scenes.elastic_cube_3d(12, y_offset=-5.0)
+    n = len(scene["particles"])
+
+    def fresh():
+        return MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+
+    data = fresh()
+    expected = []
+    for _ in range(3):
+        pipe3.queue_step(data, 5)
+        expected.append(data.read_positions().copy())
+    data.close()
+
+    data = fresh()
+    outs = [torch.empty((n, 4), dtype=torch.float32).pin_memory().numpy() for _ in range(3)]
+    for k in range(3):
+        pipe3.queue_step(data, 5)
+        data.read_positions_async(outs[k])
+    pipe3.sync()
+    # (two runs are not bit-identical: the node reductions are floating-point atomics)
+    for k in range(3):
+        assert np.allclose(outs[k], expected[k], rtol=0.0, atol=2e-5)
+    assert np.abs(outs[1] - outs[0]).max() > 2e-4 and np.abs(outs[2] - outs[1]).max() > 2e-4, "snapshots must differ"
+    data.close()

@@ -92,6 +92,11 @@ struct b200mpm_data {
     bool sharded = false;
     cudaStream_t side = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // Asynchronous position readback (b200mpm_read_positions_async): two device staging slots, a copy stream.
+    cudaStream_t copy_stream = nullptr;
+    float4* pos_stage[2] = {nullptr, nullptr};
+    cudaEvent_t pos_gathered[2] = {nullptr, nullptr}, pos_copied[2] = {nullptr, nullptr};
+    int pos_slot = 0;
 };
 
 namespace {
@@ -740,6 +745,12 @@ void b200mpm_data_destroy(b200mpm_data* d) {
         if (d->peer_arena[k]) cudaIpcCloseMemHandle(d->peer_arena[k]);
     if (d->arena) cudaFree(d->arena);
     if (d->side) cudaStreamDestroy(d->side);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (d->pos_stage[k]) cudaFree(d->pos_stage[k]);
+        if (d->pos_gathered[k]) cudaEventDestroy(d->pos_gathered[k]);
+        if (d->pos_copied[k]) cudaEventDestroy(d->pos_copied[k]);
+    }
     for (void* p : d->allocs) cudaFree(p);
     if (d->staging) cudaFree(d->staging);
     if (d->pinned) cudaFreeHost(d->pinned);
@@ -772,6 +783,8 @@ int b200mpm_sync(b200mpm_pipeline* p) {
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null pipeline");
     CU_TRY(cudaSetDevice(p->device));
     CU_TRY(cudaStreamSynchronize(p->stream));
+    for (b200mpm_data* d : p->children) // pending asynchronous readbacks
+        if (d->copy_stream) CU_TRY(cudaStreamSynchronize(d->copy_stream));
     return B200MPM_OK;
 }
 
@@ -810,6 +823,9 @@ int b200mpm_write_sim_params(b200mpm_data* d, const b200mpm_sim_params* params) 
     return B200MPM_OK;
 }
 
+static_assert(B200MPM_MAX_BODIES * sizeof(b200mpm_pose) <= 2048 && B200MPM_MAX_BODIES * sizeof(b200mpm_velocity) <= 2048,
+              "body uploads use 2 KB halves of the pinned / staging areas");
+
 int b200mpm_write_body_poses(b200mpm_data* d, const b200mpm_pose* poses, size_t n) {
     if (!d || (!poses && n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (n > d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "more poses than bodies");
@@ -821,11 +837,13 @@ int b200mpm_write_body_poses(b200mpm_data* d, const b200mpm_pose* poses, size_t 
     if (r) return r;
     r = ensure_staging(d, 4096);
     if (r) return r;
+    // Poses and velocities use disjoint halves of the 4 KB pinned / staging areas, and the synchronisation in
+    // front of the host copy covers the previous use of this half: no trailing synchronisation, the upload
+    // overlaps with the host preparing the next call.
     CU_TRY(cudaStreamSynchronize(p->stream));
     std::memcpy(d->pinned, poses, n * sizeof(b200mpm_pose));
     CU_TRY(cudaMemcpyAsync(d->staging, d->pinned, n * sizeof(b200mpm_pose), cudaMemcpyHostToDevice, p->stream));
     launch_write_poses(p->cfg(), d->dev, (const b200mpm_pose*)d->staging, (uint32_t)n);
-    CU_TRY(cudaStreamSynchronize(p->stream)); // staging is reused by the next write
     return B200MPM_OK;
 }
 
@@ -840,8 +858,10 @@ int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_
     if (r) return r;
     r = ensure_staging(d, 4096);
     if (r) return r;
+    char* pinned_half = (char*)d->pinned + 2048;
+    char* staging_half = (char*)d->staging + 2048;
     CU_TRY(cudaStreamSynchronize(p->stream));
-    std::memcpy(d->pinned, vels, n * sizeof(b200mpm_velocity));
+    std::memcpy(pinned_half, vels, n * sizeof(b200mpm_velocity));
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k)
             if (vels[i].linear[k] != 0.0f || vels[i].angular[k] != 0.0f) {
@@ -853,9 +873,8 @@ int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_
                         }
                 d->bodies_react = true;
             }
-    CU_TRY(cudaMemcpyAsync(d->staging, d->pinned, n * sizeof(b200mpm_velocity), cudaMemcpyHostToDevice, p->stream));
-    launch_write_vels(p->cfg(), d->dev, (const b200mpm_velocity*)d->staging, (uint32_t)n);
-    CU_TRY(cudaStreamSynchronize(p->stream));
+    CU_TRY(cudaMemcpyAsync(staging_half, pinned_half, n * sizeof(b200mpm_velocity), cudaMemcpyHostToDevice, p->stream));
+    launch_write_vels(p->cfg(), d->dev, (const b200mpm_velocity*)staging_half, (uint32_t)n);
     return B200MPM_OK;
 }
 
@@ -901,6 +920,34 @@ int b200mpm_read_positions(b200mpm_data* d, float* out) {
     launch_gather_positions(p->cfg(), d->dev, d->cur, (float4*)d->staging);
     CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_read_positions_async(b200mpm_data* d, float* out) {
+    if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (d->dev.n == 0) return B200MPM_OK;
+    b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
+    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_positions_unordered");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t bytes = (size_t)d->dev.n * sizeof(float4);
+    if (!d->copy_stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY(cudaMalloc(&d->pos_stage[k], bytes));
+            CU_TRY(cudaEventCreateWithFlags(&d->pos_gathered[k], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&d->pos_copied[k], cudaEventDisableTiming));
+            CU_TRY(cudaEventRecord(d->pos_copied[k], d->copy_stream));
+        }
+    }
+    const int slot = d->pos_slot ^= 1;
+    // the slot's previous copy must have left the device before the gather overwrites it
+    CU_TRY(cudaStreamWaitEvent(p->stream, d->pos_copied[slot], 0));
+    launch_gather_positions(p->cfg(), d->dev, d->cur, d->pos_stage[slot]);
+    CU_TRY(cudaEventRecord(d->pos_gathered[slot], p->stream));
+    CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->pos_gathered[slot], 0));
+    CU_TRY(cudaMemcpyAsync(out, d->pos_stage[slot], bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+    CU_TRY(cudaEventRecord(d->pos_copied[slot], d->copy_stream));
     return B200MPM_OK;
 }
 

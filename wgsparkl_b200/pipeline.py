@@ -53,6 +53,7 @@ EXPORTS = (
     "b200mpm_read_body_poses",
     "b200mpm_read_body_vels",
     "b200mpm_read_positions",
+    "b200mpm_read_positions_async",
     "b200mpm_read_particles",
     "b200mpm_read_grid",
     "b200mpm_read_sorted_ids",
@@ -118,6 +119,7 @@ def load_library():
                  "b200mpm_read_body_vels"):
         getattr(L, name).argtypes = [vp, vp, sz]
     L.b200mpm_read_positions.argtypes = [vp, vp]
+    L.b200mpm_read_positions_async.argtypes = [vp, vp]
     L.b200mpm_read_particles.argtypes = [vp, vp]
     L.b200mpm_read_grid.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
     L.b200mpm_read_sorted_ids.argtypes = [vp, vp]
@@ -305,6 +307,14 @@ class MpmData:
         if out is None:
             out = np.zeros((self.num_particles, 4), dtype=np.float32)
         _check(load_library().b200mpm_read_positions(self._h, abi.ptr(out)))
+        return out
+
+    def read_positions_async(self, out: np.ndarray):
+        """Asynchronous variant: `out` ((n, 4) float32, page-locked for a real overlap) is valid after
+        `MpmPipeline.sync()`; the copy runs on its own stream while the next substeps execute."""
+        if out.dtype != np.float32 or out.size < 4 * self.num_particles or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float32 array with room for 4 * num_particles values")
+        _check(load_library().b200mpm_read_positions_async(self._h, abi.ptr(out)))
         return out
 
     def read_particles(self):
