@@ -235,3 +235,32 @@ def test_async_position_readback_matches_blocking(pipe3):
         assert np.allclose(outs[k], expected[k], rtol=0.0, atol=2e-5)
     assert np.abs(outs[1] - outs[0]).max() > 2e-4 and np.abs(outs[2] - outs[1]).max() > 2e-4, "snapshots must differ"
     data.close()
+
+
+@pytest.mark.parametrize("plastic", [False, True])
+def test_dense_cells_multi_part_blocks(pipe3, oracle_mod, plastic):
+    """32 particles per cell (4x the seeding density, what a strongly compressed material reaches): blocks hold
+    up to 2048 particles, so G2P work items are split into parts (g2p_list), P2G stages several windows per
+    half-block, and for sand the large-strain SVD path runs. One substep from a moving state against the oracle."""
+    scene = scenes.sand_column_3d(8, 8, 8, y_offset=-5.0) if plastic else scenes.elastic_cube_3d(8, y_offset=-5.0)
+    n_side = (16, 32, 8)  # two blocks along x, each completely filled: cells [0, 4) <=> coordinates [0.5, 4.5)
+    i, j, k = np.meshgrid(np.arange(n_side[0]), np.arange(n_side[1]), np.arange(n_side[2]), indexing="ij")
+    rng = np.random.default_rng(11)
+    pos = np.stack([(i.ravel() + 0.5) * 0.5 + 0.5, (j.ravel() + 0.5) * 0.125 + 0.5, (k.ravel() + 0.5) * 0.5 + 0.5], axis=1)
+    pos += rng.uniform(-0.02, 0.02, size=pos.shape)
+    parts = np.repeat(scene["particles"][:1], len(pos)).copy()
+    parts["position"][:, :3] = pos.astype(np.float32)
+    parts["velocity"][:, :3] = rng.normal(0.0, 0.5, size=(len(pos), 3)).astype(np.float32)
+    parts["velocity"][:, 1] -= 3.0
+    F = np.tile(np.eye(3, dtype=np.float32).reshape(1, 9), (len(pos), 1))
+    F += rng.normal(0.0, 0.02 if plastic else 0.15, size=F.shape).astype(np.float32)  # elastic: beyond the polynomial path
+    parts["def_grad"][:, :9] = F
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, parts)
+    gb, gn = data.read_grid()
+    ob, on = sim.read_grid()
+    assert gb["num_particles"].max() > 1024, "test scene must produce multi-part blocks"
+    parity.assert_grid_close(gb, gn, ob, on, TOL)
+    g, o = data.read_particles(), sim.read_particles()
+    parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
+    data.close()
