@@ -221,6 +221,16 @@ int b200mpm_read_sorted_ids(b200mpm_data* d, uint32_t* out);
  * grid.wgsl:126-128). */
 int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks);
 
+/* Block-capacity growth - the part the reference leaves as a stub ("TODO: handle grid buffer resizing",
+ * src/grid/grid.rs:43-118). b200mpm_data_reserve_grid replaces the capacity-sized arrays by larger ones
+ * (capacity rounded up to a power of two like grid.rs:283; never shrinks; synchronises; the grid readback is
+ * empty until the next substep). b200mpm_data_set_auto_grow(d, max_load) with max_load in (0, 1] makes every
+ * b200mpm_step / b200mpm_shard_step call check the active block count left by the previous substeps (one stream
+ * synchronisation per call) and double the capacity while count > max_load * capacity; 0 (the default) keeps
+ * the reference's fixed capacity. */
+int b200mpm_data_reserve_grid(b200mpm_data* d, uint32_t grid_capacity);
+int b200mpm_data_set_auto_grow(b200mpm_data* d, float max_load);
+
 /* Run only the "grid sort" pass (WgGrid::queue_sort, src/grid/grid.rs:30-207) — mirrors the
  * reference's gpu_grid_sort smoke test (grid.rs:347-402). */
 int b200mpm_sort_only(b200mpm_pipeline* p, b200mpm_data* d);

@@ -132,6 +132,8 @@ extern "C" {
     pub fn b200mpm_read_positions_async(d: *mut b200mpm_data, out: *mut f32) -> c_int;
     pub fn b200mpm_read_particles(d: *mut b200mpm_data, out: *mut b200mpm_particle) -> c_int;
     pub fn b200mpm_data_status(d: *mut b200mpm_data, num_active_blocks: *mut u32) -> c_int;
+    pub fn b200mpm_data_reserve_grid(d: *mut b200mpm_data, grid_capacity: u32) -> c_int;
+    pub fn b200mpm_data_set_auto_grow(d: *mut b200mpm_data, max_load: f32) -> c_int;
     pub fn b200mpm_sort_only(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;
     pub fn b200mpm_prefix_sum_u32(p: *mut b200mpm_pipeline, data: *mut u32, len: usize) -> c_int;
     pub fn b200mpm_read_grid(

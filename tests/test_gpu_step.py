@@ -264,3 +264,49 @@ def test_dense_cells_multi_part_blocks(pipe3, oracle_mod, plastic):
     parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
     parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
     data.close()
+
+
+def test_grid_capacity_growth(pipe3):
+    """b200mpm_data_reserve_grid / set_auto_grow (the reference's stubbed resize, grid.rs:43-118): a run that
+    starts with a block capacity too small for where the particles are going must, with auto-growth on, end
+    like a run that had plenty of capacity from the start - and without it, report the overflow."""
+    scene = scenes.sand_column_3d(12, 12, 12, y_offset=10.0)  # cohesionless: an outward velocity field disperses it
+    pos = scene["particles"]["position"][:, :3]
+    radial = pos - pos.mean(axis=0)
+    scene["particles"]["velocity"][:, :3] = (40.0 * radial / np.abs(radial).max()).astype(np.float32)
+
+    def run(capacity, auto):
+        data = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], capacity)
+        if auto:
+            data.set_auto_grow(0.5)
+        for _ in range(48):
+            pipe3.queue_step(data, 5)
+        out = data.read_particles(), data.status()
+        data.close()
+        return out
+
+    (ref, (nb_ref, over_ref)) = run(8192, False)
+    assert not over_ref and nb_ref > 256, "the cloud must spread over more blocks than the small capacity"
+    (_, (_, over_small)) = run(64, False)
+    assert over_small, "without growth the small capacity must overflow (and say so)"
+    (got, (nb, over)) = run(64, True)
+    assert not over and nb == nb_ref
+    assert parity.field_rel_err(got["position"], ref["position"]) <= 1e-5  # two runs: atomic-order noise only
+    assert parity.field_rel_err(got["velocity"], ref["velocity"]) <= 5e-3
+
+
+def test_reserve_grid_between_steps(pipe3):
+    scene = scenes.elastic_cube_3d(12, y_offset=-5.0)
+    a = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], 1024)
+    b = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], 1024)
+    pipe3.queue_step(a, 10)
+    pipe3.queue_step(b, 10)
+    b.reserve_grid(5000)  # -> 8192, graphs re-captured
+    pipe3.queue_step(a, 10)
+    pipe3.queue_step(b, 10)
+    pa, pb = a.read_particles(), b.read_particles()
+    assert parity.field_rel_err(pb["position"], pa["position"]) <= 2e-6
+    assert parity.field_rel_err(pb["velocity"], pa["velocity"]) <= 1e-4
+    assert a.status()[0] == b.status()[0]
+    a.close()
+    b.close()

@@ -63,6 +63,9 @@ struct b200mpm_data {
     bool sorted_indirect = true; // sorted_ids is an indirection into `cur` (no full substep since the last sort)
     uint32_t num_bodies = 0;
     std::vector<void*> allocs;
+    std::vector<void*> grid_allocs; // the capacity-sized arrays (replaced by b200mpm_data_reserve_grid)
+    float auto_grow_load = 0.0f; // > 0: grow the grid when more than this fraction of the block capacity is active
+    uint32_t particle_cap = 0;
     void* staging = nullptr; // device staging for readbacks / host writes
     size_t staging_bytes = 0;
     void* pinned = nullptr; // pinned host mirror of small transfers
@@ -104,11 +107,11 @@ namespace {
 void orphan_data(b200mpm_data* d) { d->pipe = nullptr; }
 
 template <class T>
-int dev_alloc(b200mpm_data* d, T** out, size_t count, bool zero = true) {
+int dev_alloc(b200mpm_data* d, T** out, size_t count, bool zero = true, std::vector<void*>* list = nullptr) {
     void* p = nullptr;
     size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
     CU_TRY(cudaMalloc(&p, bytes));
-    d->allocs.push_back(p);
+    (list ? list : &d->allocs)->push_back(p);
     if (zero) CU_TRY(cudaMemsetAsync(p, 0, bytes, d->pipe->stream));
     *out = (T*)p;
     return 0;
@@ -130,6 +133,30 @@ int ensure_pinned(b200mpm_data* d, size_t bytes) {
     d->pinned_bytes = 0;
     CU_TRY(cudaMallocHost(&d->pinned, bytes));
     d->pinned_bytes = bytes;
+    return 0;
+}
+
+// The sparse grid's arrays, all sized by the block capacity (= hash capacity, a power of two; grid.rs:283).
+// Their contents are rebuilt by every substep, so a reallocation does not have to carry anything over.
+int alloc_grid(b200mpm_data* d, uint32_t capacity) {
+    DeviceData& dev = d->dev;
+    const int na = (d->pipe->dim == 2) ? 4 : 8;
+    auto* L = &d->grid_allocs;
+    int r = 0;
+    if ((r = dev_alloc(d, &dev.hkeys, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.hvals, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.block_vid, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.cell_start, (size_t)capacity * CELLS_PER_BLOCK + 1, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.nbr, (size_t)capacity * na, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.node_mv, (size_t)capacity * CELLS_PER_BLOCK, true, L))) return r;
+    if (dev.has_bodies && (r = dev_alloc(d, &dev.node_cdf, (size_t)capacity * CELLS_PER_BLOCK, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.block_flags, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.block_f0, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.cpic_list, capacity, true, L))) return r;
+    dev.g2p_list_len = capacity + d->particle_cap / G2P_ITEM + 1;
+    if ((r = dev_alloc(d, &dev.g2p_list, dev.g2p_list_len, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2, true, L))) return r;
+    dev.capacity = capacity;
     return 0;
 }
 
@@ -610,19 +637,14 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
     ALLOC(dev.pkey, ncap);
     ALLOC(dev.rank, ncap);
     ALLOC(dev.sorted_ids, ncap);
-    ALLOC(dev.hkeys, capacity);
-    ALLOC(dev.hvals, capacity);
-    ALLOC(dev.block_vid, capacity);
-    ALLOC(dev.cell_start, (size_t)capacity * CELLS_PER_BLOCK + 1);
-    ALLOC(dev.nbr, (size_t)capacity * (D == 2 ? 4 : 8));
-    ALLOC(dev.node_mv, (size_t)capacity * CELLS_PER_BLOCK);
-    if (dev.has_bodies) ALLOC(dev.node_cdf, (size_t)capacity * CELLS_PER_BLOCK);
-    ALLOC(dev.block_flags, capacity);
-    ALLOC(dev.block_f0, capacity);
-    ALLOC(dev.cpic_list, capacity);
-    dev.g2p_list_len = capacity + ncap / G2P_ITEM + 1;
-    ALLOC(dev.g2p_list, dev.g2p_list_len);
-    ALLOC(dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2);
+    d->particle_cap = ncap;
+    {
+        int _r = alloc_grid(d, capacity);
+        if (_r != 0) {
+            b200mpm_data_destroy(d);
+            return _r;
+        }
+    }
     ALLOC(dev.bodies, B200MPM_MAX_BODIES);
     ALLOC(dev.sim, 1);
     ALLOC(dev.counters, 1);
@@ -752,6 +774,7 @@ void b200mpm_data_destroy(b200mpm_data* d) {
         if (d->pos_copied[k]) cudaEventDestroy(d->pos_copied[k]);
     }
     for (void* p : d->allocs) cudaFree(p);
+    for (void* p : d->grid_allocs) cudaFree(p);
     if (d->staging) cudaFree(d->staging);
     if (d->pinned) cudaFreeHost(d->pinned);
     delete d;
@@ -760,9 +783,66 @@ void b200mpm_data_destroy(b200mpm_data* d) {
 size_t b200mpm_data_num_particles(const b200mpm_data* d) { return d ? d->n_live_host : 0; }
 size_t b200mpm_data_num_bodies(const b200mpm_data* d) { return d ? d->num_bodies : 0; }
 
+int b200mpm_data_reserve_grid(b200mpm_data* d, uint32_t grid_capacity) {
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null data");
+    b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
+    if (grid_capacity == 0 || grid_capacity > (1u << 24))
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "grid_capacity must be in [1, 2^24]");
+    uint32_t capacity = 1;
+    while (capacity < grid_capacity) capacity <<= 1; // grid.rs:283
+    if (capacity <= d->dev.capacity) return B200MPM_OK;
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    // The captured substep graphs hold the old pointers and the old capacity.
+    for (auto& gp : d->graph_exec)
+        for (auto& g : gp)
+            if (g) {
+                cudaGraphExecDestroy(g);
+                g = nullptr;
+            }
+    for (void* q : d->grid_allocs) cudaFree(q);
+    d->grid_allocs.clear();
+    int r = alloc_grid(d, capacity);
+    if (r) return r;
+    // Nothing of the old grid has to be cleared by the next k_begin_substep, and the (sticky) overflow flag is
+    // about the capacity that was just replaced.
+    const uint32_t zero = 0;
+    CU_TRY(cudaMemcpyAsync(&d->dev.counters->prev_active_blocks, &zero, sizeof(zero), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaMemcpyAsync(&d->dev.counters->overflow, &zero, sizeof(zero), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_data_set_auto_grow(b200mpm_data* d, float max_load) {
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null data");
+    if (!(max_load >= 0.0f && max_load <= 1.0f)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "max_load must be in [0, 1]");
+    d->auto_grow_load = max_load;
+    return B200MPM_OK;
+}
+
+namespace {
+// Auto-growth (off by default: the reference's capacity is fixed and its overflow silent). Looks at the block
+// count the previous substeps left behind - one 4-byte readback, i.e. a stream synchronisation per step call.
+int maybe_grow_grid(b200mpm_pipeline* p, b200mpm_data* d) {
+    if (!(d->auto_grow_load > 0.0f)) return B200MPM_OK;
+    uint32_t nb = 0;
+    CU_TRY(cudaMemcpyAsync(&nb, &d->dev.counters->num_active_blocks, sizeof(nb), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    uint64_t want = d->dev.capacity;
+    while ((double)nb > (double)d->auto_grow_load * (double)want && want < (1ull << 24)) want <<= 1;
+    if (want > d->dev.capacity) return b200mpm_data_reserve_grid(d, (uint32_t)want);
+    return B200MPM_OK;
+}
+} // namespace
+
 int b200mpm_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps) {
     if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
     CU_TRY(cudaSetDevice(p->device));
+    {
+        int r = maybe_grow_grid(p, d);
+        if (r) return r;
+    }
     for (uint32_t s = 0; s < num_substeps; ++s) run_substep(p, d);
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;
@@ -1256,6 +1336,10 @@ int b200mpm_shard_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_subste
     if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
     if (!d->comm) return fail(B200MPM_ERR_INVALID_ARGUMENT, "b200mpm_shard_comm_init has not been called");
     CU_TRY(cudaSetDevice(p->device));
+    {
+        int r = maybe_grow_grid(p, d); // per rank: the capacity is a local property of each slab
+        if (r) return r;
+    }
     for (uint32_t s = 0; s < num_substeps; ++s) run_phase(p, d, PHASE_SHARDED);
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;

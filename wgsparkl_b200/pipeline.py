@@ -58,6 +58,8 @@ EXPORTS = (
     "b200mpm_read_grid",
     "b200mpm_read_sorted_ids",
     "b200mpm_data_status",
+    "b200mpm_data_reserve_grid",
+    "b200mpm_data_set_auto_grow",
     "b200mpm_sort_only",
     "b200mpm_prefix_sum_u32",
     "b200mpm_slab_configure",
@@ -119,6 +121,8 @@ def load_library():
                  "b200mpm_read_body_vels"):
         getattr(L, name).argtypes = [vp, vp, sz]
     L.b200mpm_read_positions.argtypes = [vp, vp]
+    L.b200mpm_data_reserve_grid.argtypes = [vp, ctypes.c_uint32]
+    L.b200mpm_data_set_auto_grow.argtypes = [vp, ctypes.c_float]
     L.b200mpm_read_positions_async.argtypes = [vp, vp]
     L.b200mpm_read_particles.argtypes = [vp, vp]
     L.b200mpm_read_grid.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
@@ -321,6 +325,14 @@ class MpmData:
         out = np.zeros(self.num_particles, dtype=abi.particle_dtype)
         _check(load_library().b200mpm_read_particles(self._h, abi.ptr(out)))
         return out
+
+    def reserve_grid(self, grid_capacity: int):
+        """Grow the block capacity (the reference's stubbed resize, grid.rs:43-118)."""
+        _check(load_library().b200mpm_data_reserve_grid(self._h, int(grid_capacity)))
+
+    def set_auto_grow(self, max_load: float):
+        """Double the block capacity whenever more than `max_load` of it is active at a step call (0 = off)."""
+        _check(load_library().b200mpm_data_set_auto_grow(self._h, float(max_load)))
 
     def status(self):
         """(num_active_blocks, overflowed)."""
