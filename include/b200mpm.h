@@ -221,6 +221,31 @@ int b200mpm_read_sorted_ids(b200mpm_data* d, uint32_t* out);
  * grid.wgsl:126-128). */
 int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks);
 
+/* ---- render hand-off: the step on the far side of the path (src_testbed/prep_vertex_buffer{2d,3d}.wgsl:40-108,
+ * src_testbed/prep_vertex_buffer.rs:11-57) -----------------------------------------------------------------------
+ * One InstanceData per particle, in the caller's ORIGINAL particle order, in the testbed's vertex-buffer layout
+ * (src_testbed/instancing3d.rs:66-73: three vec4 columns of the deformation gradient, vec4 position, base_color,
+ * color; 96 bytes). Like the shader it writes xyz of the deformation columns and of the position plus `color`,
+ * and reads (never writes) `base_color`; the w lanes are left as they are. */
+typedef struct b200mpm_instance {
+    float deformation[12]; /* 3 columns, each padded to 4 floats (2D: (F.x, 0), (F.y, 0), (0, 0, 1)) */
+    float position[4];
+    float base_color[4];
+    float color[4];
+} b200mpm_instance;
+enum { /* RenderMode (prep_vertex_buffer.rs:11-18, prep_vertex_buffer3d.wgsl:25-30) */
+    B200MPM_RENDER_DEFAULT = 0,
+    B200MPM_RENDER_VOLUME = 1,
+    B200MPM_RENDER_VELOCITY = 2,
+    B200MPM_RENDER_CDF_NORMALS = 3,
+    B200MPM_RENDER_CDF_DISTANCES = 4,
+    B200MPM_RENDER_CDF_SIGNS = 5
+};
+/* `dev_instances` is DEVICE memory with room for num_particles instances - typically the renderer's vertex buffer
+ * imported into CUDA (cudaImportExternalMemory on a Vulkan/D3D12 allocation), so that drawing needs no host round
+ * trip. Asynchronous on the pipeline's stream. Not available for sharded data (a slab holds a changing subset). */
+int b200mpm_prep_vertex_buffer(b200mpm_pipeline* p, b200mpm_data* d, b200mpm_instance* dev_instances, uint32_t mode);
+
 /* Block-capacity growth - the part the reference leaves as a stub ("TODO: handle grid buffer resizing",
  * src/grid/grid.rs:43-118). b200mpm_data_reserve_grid replaces the capacity-sized arrays by larger ones
  * (capacity rounded up to a power of two like grid.rs:283; never shrinks; synchronises; the grid readback is

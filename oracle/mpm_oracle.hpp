@@ -1390,6 +1390,50 @@ struct Sim {
         }
     }
 
+    // ---- render hand-off (src_testbed/prep_vertex_buffer3d.wgsl:40-95, prep_vertex_buffer2d.wgsl:39-94) ------
+    // inst: num_particles x 24 floats = {deformation 3 x vec4, position vec4, base_color vec4, color vec4};
+    // writes xyz of the deformation columns and of the position, and color; reads base_color.
+    void prep_vertex_buffer(uint32_t mode, float* inst) const {
+        for (uint32_t id = 0; id < num_particles(); ++id) {
+            float* o = inst + (size_t)id * 24;
+            const Dynamics<D>& dyn = particles_dyn[id];
+            if constexpr (D == 3) {
+                for (int c = 0; c < 3; ++c)
+                    for (int r = 0; r < 3; ++r) o[4 * c + r] = dyn.def_grad.at(r, c);
+                for (int k = 0; k < 3; ++k) o[12 + k] = particles_pos[id][k];
+            } else {
+                o[0] = dyn.def_grad.at(0, 0), o[1] = dyn.def_grad.at(1, 0), o[2] = 0.0f;
+                o[4] = dyn.def_grad.at(0, 1), o[5] = dyn.def_grad.at(1, 1), o[6] = 0.0f;
+                o[8] = 0.0f, o[9] = 0.0f, o[10] = 1.0f;
+                o[12] = particles_pos[id][0], o[13] = particles_pos[id][1], o[14] = 0.0f;
+            }
+            const float* base = o + 16;
+            float* col = o + 20;
+            for (int k = 0; k < 4; ++k) col[k] = base[k];
+            if (mode == 2) { // VELOCITY
+                for (int k = 0; k < D; ++k) col[k] = std::fabs(dyn.velocity[k]) * dt * 100.0f + 0.2f;
+            } else if (mode == 1) { // VOLUME
+                Svd<D> sv = svd(dyn.def_grad);
+                for (int k = 0; k < D; ++k) col[k] = (1.0f - sv.S[k]) / 0.005f + 0.2f;
+            } else if (mode == 3) { // CDF_NORMALS
+                bool zero = true;
+                for (int k = 0; k < D; ++k) zero = zero && dyn.cdf.normal[k] == 0.0f;
+                for (int k = 0; k < 3; ++k) col[k] = (zero || k >= D) ? 0.0f : (dyn.cdf.normal[k] + 1.0f) / 2.0f;
+            } else if (mode == 4) { // CDF_DISTANCES
+                const float dd = dyn.cdf.signed_distance / (cell_width * 1.5f);
+                col[0] = (dd > 0.0f) ? 0.0f : std::fabs(dd);
+                col[1] = (dd > 0.0f) ? std::fabs(dd) : 0.0f;
+                col[2] = 0.0f;
+            } else if (mode == 5) { // CDF_SIGNS
+                const uint32_t aff = dyn.cdf.affinity;
+                const uint32_t a = (aff >> 16) & (aff & 0x0000ffffu);
+                col[0] = (aff != 0u && a != 0u) ? 1.0f : 0.0f;
+                col[1] = (aff != 0u && a == 0u) ? 1.0f : 0.0f;
+                col[2] = 0.0f;
+            }
+        }
+    }
+
     // ---- constitutive models (src/models/*.wgsl) -----------------------------------------------
     static Mat<D> kirchoff_stress_corotated(ElasticCoefficients model, const Mat<D>& F) { // linear_elasticity.wgsl:14-41
         Svd<D> s = svd(F);

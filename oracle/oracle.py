@@ -58,6 +58,7 @@ def lib():
         L.oracle_project_point.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_exact_sigma.argtypes = [ctypes.c_int]
+        L.oracle_prep_vertex_buffer.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
         L.oracle_max_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -110,6 +111,12 @@ class OracleSim:
         out = np.zeros(self.n, dtype=abi.particle_dtype)
         lib().oracle_read_particles(self._h, abi.ptr(out))
         return out
+
+    def prep_vertex_buffer(self, instances, mode):
+        """prep_vertex_buffer{2d,3d}.wgsl main: updates `instances` (n x abi.instance_dtype) in place."""
+        assert instances.dtype == abi.instance_dtype and len(instances) == self.n
+        lib().oracle_prep_vertex_buffer(self._h, int(mode), abi.ptr(instances))
+        return instances
 
     def num_active_blocks(self):
         return int(lib().oracle_num_active_blocks(self._h))

@@ -420,6 +420,11 @@ int oracle_project_point(int dim, const b200mpm_body* b, const float* pt, float*
     vec_to<3>(r.point, out);
     return r.is_inside;
 }
+void oracle_prep_vertex_buffer(void* hv, uint32_t mode, float* inst) {
+    auto* h = (Handle*)hv;
+    DISPATCH(h, s.prep_vertex_buffer(mode, inst), s.prep_vertex_buffer(mode, inst));
+}
+
 // Test diagnostic: see exact_sigma_mode() in mpm_oracle.hpp. Process-wide.
 void oracle_set_exact_sigma(int on) { exact_sigma_mode() = (on != 0); }
 

@@ -95,6 +95,15 @@ pub struct b200mpm_node {
     pub cdf_closest_id: u32,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b200mpm_instance {
+    pub deformation: [f32; 12],
+    pub position: [f32; 4],
+    pub base_color: [f32; 4],
+    pub color: [f32; 4],
+}
+
 pub const B200MPM_PARTICLE_RECORD_BYTES: u32 = 128;
 pub const B200MPM_HALO_BLOCK_BYTES: u32 = 1040;
 pub const B200MPM_SHARD_HEADER_BYTES: u32 = 16;
@@ -134,6 +143,7 @@ extern "C" {
     pub fn b200mpm_data_status(d: *mut b200mpm_data, num_active_blocks: *mut u32) -> c_int;
     pub fn b200mpm_data_reserve_grid(d: *mut b200mpm_data, grid_capacity: u32) -> c_int;
     pub fn b200mpm_data_set_auto_grow(d: *mut b200mpm_data, max_load: f32) -> c_int;
+    pub fn b200mpm_prep_vertex_buffer(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_instances: *mut b200mpm_instance, mode: u32) -> c_int;
     pub fn b200mpm_sort_only(p: *mut b200mpm_pipeline, d: *mut b200mpm_data) -> c_int;
     pub fn b200mpm_prefix_sum_u32(p: *mut b200mpm_pipeline, data: *mut u32, len: usize) -> c_int;
     pub fn b200mpm_read_grid(

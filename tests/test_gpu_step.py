@@ -310,3 +310,43 @@ def test_reserve_grid_between_steps(pipe3):
     assert a.status()[0] == b.status()[0]
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_prep_vertex_buffer_all_render_modes(pipe2, pipe3, oracle_mod, dim):
+    """Render hand-off (src_testbed/prep_vertex_buffer{2d,3d}.wgsl): the instance buffer written on the device
+    from the device state, against the oracle's restatement, for every RenderMode."""
+    import torch
+
+    pipe = pipe3 if dim == 3 else pipe2
+    if dim == 3:
+        scene = scenes.elastic_cube_3d(10, y_offset=-5.0)
+    else:
+        scene = scenes.elastic_block_2d(24)
+        scene["particles"]["position"][:, 1] -= 9.9
+    scene["particles"]["velocity"][:, 1] = -3.0
+    parts, _, _ = developed_state(oracle_mod, scene, 40)
+    data, sim = one_substep_both(oracle_mod, pipe, scene, parts, n=3)
+    n = len(parts)
+    rng = np.random.default_rng(2)
+    init = np.zeros(n, dtype=abi.instance_dtype)
+    init["base_color"] = rng.uniform(0.0, 1.0, size=(n, 4)).astype(np.float32)
+    init["deformation"][:, :, 3] = 7.0  # padding lanes: must survive
+    init["position"][:, 3] = 9.0
+    o = sim.read_particles()
+    assert (o["cdf_affinity"] != 0).sum() > 20, "test scene must have collider-side particles"
+    for mode in range(6):
+        dev = torch.from_numpy(init.view(np.float32).reshape(n, 24).copy()).cuda()
+        pipe.prep_vertex_buffer(data, dev.data_ptr(), mode)
+        pipe.sync()
+        got = dev.cpu().numpy().reshape(-1).view(abi.instance_dtype)
+        ref = sim.prep_vertex_buffer(init.copy(), mode)
+        assert np.array_equal(got["base_color"], init["base_color"])
+        assert np.all(got["deformation"][:, :, 3] == 7.0) and np.all(got["position"][:, 3] == 9.0)
+        assert parity.field_rel_err(got["position"][:, :3], ref["position"][:, :3]) <= 2e-6
+        assert parity.field_rel_err(got["deformation"][:, :, :3], ref["deformation"][:, :, :3]) <= 1e-5
+        # VOLUME divides 1 - sigma by 0.005: an ulp of sigma is 2e-5 of colour; CDF modes follow normals /
+        # distances that agree to 1e-4 (test_one_substep_elastic_cube); the rest is exact arithmetic on equal inputs
+        tol = {abi.RENDER_VOLUME: 2e-3, abi.RENDER_VELOCITY: 1e-4, abi.RENDER_CDF_NORMALS: 1e-4, abi.RENDER_CDF_DISTANCES: 1e-4}.get(mode, 0.0)
+        assert np.abs(got["color"] - ref["color"]).max() <= tol * max(1.0, np.abs(ref["color"]).max()), mode
+    data.close()

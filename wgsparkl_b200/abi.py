@@ -85,6 +85,10 @@ assert body_dtype.itemsize == 37 * 4
 pose_dtype = np.dtype([("translation", "<f4", 3), ("rotation", "<f4", 4)])
 velocity_dtype = np.dtype([("linear", "<f4", 3), ("angular", "<f4", 3)])
 block_info_dtype = np.dtype([("vid", "<i4", 3), ("first_particle", "<u4"), ("num_particles", "<u4")])
+# InstanceData of the testbed's vertex buffer (src_testbed/instancing3d.rs:66-73)
+instance_dtype = np.dtype([("deformation", "<f4", (3, 4)), ("position", "<f4", 4), ("base_color", "<f4", 4), ("color", "<f4", 4)])
+assert instance_dtype.itemsize == 96
+RENDER_DEFAULT, RENDER_VOLUME, RENDER_VELOCITY, RENDER_CDF_NORMALS, RENDER_CDF_DISTANCES, RENDER_CDF_SIGNS = range(6)
 node_dtype = np.dtype(
     [
         ("momentum_velocity_mass", "<f4", 4),

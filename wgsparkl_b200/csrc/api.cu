@@ -1031,6 +1031,23 @@ int b200mpm_read_positions_async(b200mpm_data* d, float* out) {
     return B200MPM_OK;
 }
 
+int b200mpm_prep_vertex_buffer(b200mpm_pipeline* p, b200mpm_data* d, b200mpm_instance* dev_instances, uint32_t mode) {
+    if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
+    if (!dev_instances && d->dev.n) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null instance buffer");
+    if (mode > B200MPM_RENDER_CDF_SIGNS) return fail(B200MPM_ERR_INVALID_ARGUMENT, "unknown render mode");
+    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data holds a changing subset of the particles");
+    CU_TRY(cudaSetDevice(p->device));
+    cudaPointerAttributes attr{};
+    if (d->dev.n && (cudaPointerGetAttributes(&attr, dev_instances) != cudaSuccess ||
+                     (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged))) {
+        cudaGetLastError();
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "the instance buffer must be device memory");
+    }
+    launch_prep_vertex_buffer(p->cfg(), d->dev, d->cur, dev_instances, mode);
+    CU_TRY(cudaGetLastError());
+    return B200MPM_OK;
+}
+
 int b200mpm_read_positions_unordered(b200mpm_data* d, float* out, size_t capacity, size_t* count) {
     if (!d || !count) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     b200mpm_pipeline* p = d->pipe;

@@ -1,6 +1,7 @@
 // Rigid-body kernels ("update rigid particles" and "integrate_bodies" passes), per-substep counter
 // bookkeeping, and the readback / host-write helpers behind the C ABI.
 #include "launch.h"
+#include "svd.cuh"
 
 namespace b2 {
 
@@ -339,6 +340,64 @@ __global__ void k_gather_particles(DeviceData d, int cur, b200mpm_particle* out,
     }
 }
 
+// ---- prep_vertex_buffer (src_testbed/prep_vertex_buffer3d.wgsl:40-95, 2d: 39-94) -----------------------
+template <int D>
+__global__ void k_prep_vertex_buffer(DeviceData d, int cur, b200mpm_instance* inst, uint32_t mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.counters->n_live) return;
+    const float4 p = d.pos4[cur][i];
+    const float4 v = d.vel4[cur][i];
+    b200mpm_instance& o = inst[__float_as_uint(v.w)]; // instances are indexed by the original particle id
+    float F[9];
+    const float4 fa = d.Fa[cur][i];
+    F[0] = fa.x, F[1] = fa.y, F[2] = fa.z, F[3] = fa.w;
+    if (D == 3) {
+        const float4 fb = d.Fb[cur][i];
+        F[4] = fb.x, F[5] = fb.y, F[6] = fb.z, F[7] = fb.w, F[8] = d.Fc[cur][i];
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) o.deformation[4 * c + r] = F[3 * c + r];
+        o.position[0] = p.x, o.position[1] = p.y, o.position[2] = p.z;
+    } else {
+        o.deformation[0] = F[0], o.deformation[1] = F[1], o.deformation[2] = 0.0f;
+        o.deformation[4] = F[2], o.deformation[5] = F[3], o.deformation[6] = 0.0f;
+        o.deformation[8] = 0.0f, o.deformation[9] = 0.0f, o.deformation[10] = 1.0f;
+        o.position[0] = p.x, o.position[1] = p.y, o.position[2] = 0.0f;
+    }
+    const float base[4] = {o.base_color[0], o.base_color[1], o.base_color[2], o.base_color[3]};
+    float col[4] = {base[0], base[1], base[2], base[3]};
+    const float h = d.sim->cell_width, dt = d.sim->dt;
+    uint32_t aff = 0u;
+    float4 nd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d.has_bodies) {
+        aff = d.cdf_aff[cur][i];
+        if (aff != 0u) nd = d.cdf_nd[i]; // affinity == 0 <=> default cdf (zero normal, zero distance)
+    }
+    if (mode == B200MPM_RENDER_VELOCITY) {
+        const float vel[3] = {v.x, v.y, v.z};
+        for (int k = 0; k < D; ++k) col[k] = fabsf(vel[k]) * dt * 100.0f + 0.2f;
+    } else if (mode == B200MPM_RENDER_VOLUME) {
+        float U[9], S[3], V[9];
+        if (D == 3) svd3<4>(F, U, S, V);
+        else svd2(F, U, S, V);
+        for (int k = 0; k < D; ++k) col[k] = (1.0f - S[k]) / 0.005f + 0.2f;
+    } else if (mode == B200MPM_RENDER_CDF_NORMALS) {
+        const float n[3] = {nd.x, nd.y, (D == 3) ? nd.z : 0.0f};
+        const bool zero = n[0] == 0.0f && n[1] == 0.0f && n[2] == 0.0f;
+        for (int k = 0; k < 3; ++k) col[k] = (zero || k >= D) ? 0.0f : (n[k] + 1.0f) / 2.0f;
+    } else if (mode == B200MPM_RENDER_CDF_DISTANCES) {
+        const float dd = nd.w / (h * 1.5f);
+        col[0] = (dd > 0.0f) ? 0.0f : fabsf(dd);
+        col[1] = (dd > 0.0f) ? fabsf(dd) : 0.0f;
+        col[2] = 0.0f;
+    } else if (mode == B200MPM_RENDER_CDF_SIGNS) {
+        const uint32_t a = (aff >> 16) & (aff & 0x0000ffffu);
+        col[0] = (aff != 0u && a != 0u) ? 1.0f : 0.0f;
+        col[1] = (aff != 0u && a == 0u) ? 1.0f : 0.0f;
+        col[2] = 0.0f;
+    }
+    for (int k = 0; k < 4; ++k) o.color[k] = col[k];
+}
+
 __global__ void k_gather_sorted_ids(DeviceData d, int cur, int indirect, uint32_t* out) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= d.counters->n_live) return;
@@ -417,6 +476,12 @@ void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_i
                         uint32_t max_blocks) {
     if (c.dim == 2) k_gather_grid<2><<<c.num_sms * 8, CELLS_PER_BLOCK, 0, c.stream>>>(d, blocks, nodes, max_blocks);
     else k_gather_grid<3><<<c.num_sms * 8, CELLS_PER_BLOCK, 0, c.stream>>>(d, blocks, nodes, max_blocks);
+    ++*c.launch_counter;
+}
+void launch_prep_vertex_buffer(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_instance* inst, uint32_t mode) {
+    if (d.n == 0) return;
+    if (c.dim == 2) k_prep_vertex_buffer<2><<<div_up(d.n, 128), 128, 0, c.stream>>>(d, cur, inst, mode);
+    else k_prep_vertex_buffer<3><<<div_up(d.n, 128), 128, 0, c.stream>>>(d, cur, inst, mode);
     ++*c.launch_counter;
 }
 void launch_gather_sorted_ids(const LaunchCfg& c, const DeviceData& d, int cur, int indirect, uint32_t* out) {

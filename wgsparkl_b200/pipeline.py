@@ -58,6 +58,7 @@ EXPORTS = (
     "b200mpm_read_grid",
     "b200mpm_read_sorted_ids",
     "b200mpm_data_status",
+    "b200mpm_prep_vertex_buffer",
     "b200mpm_data_reserve_grid",
     "b200mpm_data_set_auto_grow",
     "b200mpm_sort_only",
@@ -122,6 +123,7 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz]
     L.b200mpm_read_positions.argtypes = [vp, vp]
     L.b200mpm_data_reserve_grid.argtypes = [vp, ctypes.c_uint32]
+    L.b200mpm_prep_vertex_buffer.argtypes = [vp, vp, vp, ctypes.c_uint32]
     L.b200mpm_data_set_auto_grow.argtypes = [vp, ctypes.c_float]
     L.b200mpm_read_positions_async.argtypes = [vp, vp]
     L.b200mpm_read_particles.argtypes = [vp, vp]
@@ -197,6 +199,11 @@ class MpmPipeline:
         _check(load_library().b200mpm_step(self._h, data._h, int(num_substeps)))
 
     step = queue_step
+
+    def prep_vertex_buffer(self, data: "MpmData", dev_instances: int, mode: int = abi.RENDER_DEFAULT):
+        """WgPrepVertexBuffer::queue (src_testbed/prep_vertex_buffer.rs:81-113): fills the renderer's instance
+        buffer - a DEVICE pointer to num_particles x abi.instance_dtype - from the device state. Asynchronous."""
+        _check(load_library().b200mpm_prep_vertex_buffer(self._h, data._h, int(dev_instances), int(mode)))
 
     def sort_only(self, data: "MpmData"):
         """WgGrid::queue_sort alone (grid.rs:30-207), as in the gpu_grid_sort test (grid.rs:347-402)."""
