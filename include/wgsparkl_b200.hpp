@@ -196,6 +196,9 @@ public:
         check(b200mpm_get_timings(h_, ms.data()));
         return ms;
     }
+    // WgPrepVertexBuffer::queue (src_testbed/prep_vertex_buffer.rs:81-113): fills the renderer's instance buffer
+    // (device memory, num_particles x b200mpm_instance) from the device state.
+    void prep_vertex_buffer(MpmData<DIM>& data, b200mpm_instance* dev_instances, uint32_t mode = B200MPM_RENDER_DEFAULT);
     b200mpm_pipeline* raw() { return h_; }
 
 private:
@@ -241,12 +244,28 @@ public:
         check(b200mpm_read_particles(h_, out.data()));
         return out;
     }
+    // particles.positions (particle3d.rs:177) as vec4 per particle; blocking / staged like map_async (valid after
+    // MpmPipeline::sync; `out_pinned` should be page-locked).
+    std::vector<float> read_positions() {
+        std::vector<float> out(4 * num_particles());
+        check(b200mpm_read_positions(h_, out.data()));
+        return out;
+    }
+    void read_positions_async(float* out_pinned) { check(b200mpm_read_positions_async(h_, out_pinned)); }
+    // The resize the reference leaves as a stub (grid.rs:43-118).
+    void reserve_grid(uint32_t grid_capacity) { check(b200mpm_data_reserve_grid(h_, grid_capacity)); }
+    void set_auto_grow(float max_load) { check(b200mpm_data_set_auto_grow(h_, max_load)); }
     b200mpm_data* raw() { return h_; }
 
 private:
     MpmData() = default;
     b200mpm_data* h_ = nullptr;
 };
+
+template <int DIM>
+inline void MpmPipeline<DIM>::prep_vertex_buffer(MpmData<DIM>& data, b200mpm_instance* dev_instances, uint32_t mode) {
+    check(b200mpm_prep_vertex_buffer(h_, data.raw(), dev_instances, mode));
+}
 
 template <int DIM>
 inline void MpmPipeline<DIM>::queue_step(MpmData<DIM>& data, uint32_t num_substeps, bool add_timestamps) {
