@@ -141,3 +141,26 @@ def test_round_ties_and_their_neighbours(pipe3, oracle_mod, cell_width):
     assert not data.status()[1], "test scene must fit the grid capacity"
     parity.assert_sort_equal(gb, gs, ob, os_)
     data.close()
+
+
+def test_nearly_full_hash_table(pipe3, oracle_mod):
+    """Long linear-probing chains (grid.wgsl:121-164): the capacity is the smallest power of two that still holds
+    the active blocks, so most insertions and every neighbour look-up walk over several occupied slots."""
+    scene = scenes.elastic_cube_3d(20, y_offset=3.0)  # 10^3 cells: 27..64 touched blocks
+    osim = oracle_mod.OracleSim(scene["dim"], scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], 4096)
+    for st in (0, 1, 2):
+        osim.stage(st)
+    nb = osim.num_active_blocks()
+    osim.close()
+    cap = 1
+    while cap < nb:
+        cap <<= 1
+    scene["grid_capacity"] = cap
+    assert nb > 0.6 * cap, (nb, cap)
+    data, (gb, gn, gs), (ob, on, os_) = _run_both(scene, pipe3, oracle_mod)
+    assert data.status() == (nb, False)
+    parity.assert_sort_equal(gb, gs, ob, os_)
+    pipe3.queue_step(data, 3)  # and the substep kernels walk the same chains (neighbour table)
+    assert np.all(np.isfinite(data.read_positions()))
+    assert not data.status()[1]
+    data.close()

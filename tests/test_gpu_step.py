@@ -350,3 +350,54 @@ def test_prep_vertex_buffer_all_render_modes(pipe2, pipe3, oracle_mod, dim):
         tol = {abi.RENDER_VOLUME: 2e-3, abi.RENDER_VELOCITY: 1e-4, abi.RENDER_CDF_NORMALS: 1e-4, abi.RENDER_CDF_DISTANCES: 1e-4}.get(mode, 0.0)
         assert np.abs(got["color"] - ref["color"]).max() <= tol * max(1.0, np.abs(ref["color"]).max()), mode
     data.close()
+
+
+def test_sixteen_colliders_of_every_shape(pipe3, oracle_mod):
+    """The cap of 16 coupled colliders (rigid_impulses.rs:42, collide.wgsl:36): fixed balls and rotating kinematic
+    capsules embedded in a block of sand, dynamic cuboids hovering just above it - affinity bits 0..15 and sign
+    bits are all in use. (Dynamic bodies embedded in E = 2e9 sand receive impulses beyond the i32(x 1e5) range of
+    rigid_impulses.wgsl:52-58, where the result is an overflow artefact in the reference too; impulses on dynamic
+    bodies are covered by test_two_way_coupling_bodies.) Three substeps from a developed state against the oracle."""
+    from wgsparkl_b200.rapier import ColliderBuilder, ColliderSet, RigidBodyBuilder, RigidBodySet, bodies_to_abi
+
+    scene = scenes.sand_column_3d(16, 12, 16, y_offset=-4.0)  # y in [-1.75, 3.75]
+    bodies, colliders = RigidBodySet(), ColliderSet()
+    rb = bodies.insert(RigidBodyBuilder.fixed().translation([0.0, -4.0, 0.0]))
+    colliders.insert_with_parent(ColliderBuilder.cuboid(100.0, 1.0, 100.0), rb, bodies)
+    k = 0
+    for ix in range(-2, 3):
+        for iz in (-1.5, 0.0, 1.5):
+            kind = k % 3
+            if kind == 0:
+                rb = bodies.insert(RigidBodyBuilder.fixed().translation([1.6 * ix, 0.2 + 0.4 * (k % 2), 1.7 * iz]))
+                shape = ColliderBuilder.ball(0.55)
+            elif kind == 1:
+                rb = bodies.insert(RigidBodyBuilder.kinematic_velocity_based().translation([1.6 * ix, 1.0, 1.7 * iz])
+                                   .rotation([0.3, 0.0, 0.2]).angvel([0.0, 2.0, 0.0]))
+                shape = ColliderBuilder.capsule_y(0.5, 0.35)
+            else:
+                rb = bodies.insert(RigidBodyBuilder.dynamic().translation([1.6 * ix, 4.45, 1.7 * iz]).rotation([0.0, 0.4, 0.1]))
+                shape = ColliderBuilder.cuboid(0.5, 0.3, 0.4).density(50.0)
+            colliders.insert_with_parent(shape, rb, bodies)
+            k += 1
+    scene["bodies"] = bodies_to_abi(bodies, colliders, 3)
+    assert len(scene["bodies"]) == 16
+    parts, poses, vels = developed_state(oracle_mod, scene, 12)
+    scene["bodies"]["translation"] = poses["translation"]
+    scene["bodies"]["rotation"] = poses["rotation"]
+    scene["bodies"]["linvel"] = vels["linear"]
+    scene["bodies"]["angvel"] = vels["angular"]
+    data, sim = one_substep_both(oracle_mod, pipe3, scene, parts, n=3)
+    g, o = data.read_particles(), sim.read_particles()
+    gb, gn = data.read_grid()
+    ob, on = sim.read_grid()
+    parity.assert_grid_close(gb, gn, ob, on, 1e-4)
+    used = np.bitwise_or.reduce(on["cdf_affinities"].ravel())
+    assert used & 0xFFFF == 0xFFFF and (used >> 16) != 0, "every collider must colour some node, some from inside"
+    assert (o["cdf_affinity"] != 0).mean() > 0.2, "a good part of the particles must be collider-side"
+    assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
+    parity.assert_particles_close(g, o, TOL, fields=("position", "def_grad"), tols={"position": 2e-6})
+    assert parity.field_rel_err(g["velocity"], o["velocity"]) <= 5e-3  # stiff sand (DESIGN.md §6)
+    assert parity.field_rel_err(data.read_body_poses()["translation"], sim.read_body_poses()["translation"]) <= 1e-5
+    assert parity.field_rel_err(data.read_body_vels()["linear"], sim.read_body_vels()["linear"]) <= 2e-3
+    data.close()
