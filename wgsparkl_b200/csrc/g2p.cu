@@ -232,37 +232,55 @@ __global__ void __launch_bounds__(G2P_THREADS, (PLASTIC ? G2P_MINB_P : G2P_MINB_
                 }
             } else {
                 // CPIC path (particles next to a collider only; g2p.wgsl:186-207): incompatible nodes
-                // contribute the particle's ghost velocity. Deliberately NOT unrolled: these particles are
-                // few, and the unrolled form triples the kernel's instruction-cache footprint.
+                // contribute the particle's ghost velocity. Rolled over the (sy, sz) rows, unrolled along x: the
+                // fully unrolled form triples the kernel's instruction-cache footprint, the fully rolled one spends
+                // more on index arithmetic and weight selection than on the gather itself.
+                // Against a body that neither moves nor can be moved the ghost velocity does not depend on the
+                // node: v_body(x) = 0, ghost = project_velocity(v_p, n_p).
+                const V3 ghost_static = project_velocity(pvel, normal);
 #pragma unroll 1
-                for (int n = 0; n < Dim<D>::NBH; ++n) {
-                    const int sx = n % 3, sy = (n / 3) % 3, sz = n / 9;
-                    const int idx = tb + sx + T * sy + T * T * sz;
-                    const float4 cell = tile_v[idx];
-                    const uint2 nc = tile_c[idx];
-                    float cv[3] = {cell.x, cell.y, cell.z};
-                    if (!affinities_are_compatible(pa, nc.x)) {
-                        V3 ghost = pvel;
-                        if (nc.y != NONE) {
-                            const BodyDev& body = d.bodies[nc.y];
-                            V3 center = v3(d0[0] + (float)sx * h, d0[1] + (float)sy * h,
-                                           (D == 3) ? d0[D - 1] + (float)sz * h : 0.0f) + ppos;
-                            V3 bpv = velocity_at_point<D>(body, center);
-                            ghost = bpv + project_velocity(pvel - bpv, normal);
-                        }
-                        cv[0] = ghost.x, cv[1] = ghost.y, cv[2] = ghost.z;
-                    }
-                    const float wxs = (sx == 0) ? w[0][0] : (sx == 1) ? w[0][1] : w[0][2];
+                for (int yz = 0; yz < (D == 3 ? 9 : 3); ++yz) {
+                    const int sy = yz % 3, sz = yz / 3;
                     const float wys = (sy == 0) ? w[1][0] : (sy == 1) ? w[1][1] : w[1][2];
                     const float wzs = (D == 3) ? ((sz == 0) ? w[D - 1][0] : (sz == 1) ? w[D - 1][1] : w[D - 1][2]) : 1.0f;
-                    const float wt = wxs * wys * wzs;
-                    const float sc[3] = {(float)sx, (float)sy, (float)sz};
+                    const float wyz = wys * wzs;
+                    const int row = tb + T * sy + T * T * sz;
+                    float t0[D], t1[D];
+#pragma unroll
+                    for (int r = 0; r < D; ++r) t0[r] = t1[r] = 0.0f;
+#pragma unroll
+                    for (int sx = 0; sx < 3; ++sx) {
+                        const float4 cell = tile_v[row + sx];
+                        const uint2 nc = tile_c[row + sx];
+                        float cv[3] = {cell.x, cell.y, cell.z};
+                        if (!affinities_are_compatible(pa, nc.x)) {
+                            V3 ghost = pvel;
+                            if (nc.y != NONE) {
+                                const BodyDev& body = d.bodies[nc.y];
+                                ghost = ghost_static;
+                                if (body.needs_impulse) {
+                                    V3 center = v3(d0[0] + (float)sx * h, d0[1] + (float)sy * h,
+                                                   (D == 3) ? d0[D - 1] + (float)sz * h : 0.0f) + ppos;
+                                    V3 bpv = velocity_at_point<D>(body, center);
+                                    ghost = bpv + project_velocity(pvel - bpv, normal);
+                                }
+                            }
+                            cv[0] = ghost.x, cv[1] = ghost.y, cv[2] = ghost.z;
+                        }
+                        const float wx = w[0][sx], sxw = (float)sx * w[0][sx];
+#pragma unroll
+                        for (int r = 0; r < D; ++r) {
+                            t0[r] = fmaf(wx, cv[r], t0[r]);
+                            if (sx > 0) t1[r] = fmaf(sxw, cv[r], t1[r]);
+                        }
+                    }
+                    const float syw = (float)sy * wyz, szw = (float)sz * wyz;
 #pragma unroll
                     for (int r = 0; r < D; ++r) {
-                        const float wv = wt * cv[r];
-                        vs[r] += wv;
-#pragma unroll
-                        for (int c = 0; c < D; ++c) mom[c][r] += sc[c] * wv;
+                        vs[r] = fmaf(wyz, t0[r], vs[r]);
+                        mom[0][r] = fmaf(wyz, t1[r], mom[0][r]);
+                        mom[1][r] = fmaf(syw, t0[r], mom[1][r]);
+                        if (D == 3) mom[D - 1][r] = fmaf(szw, t0[r], mom[D - 1][r]);
                     }
                 }
             }
