@@ -1,5 +1,5 @@
 """Runs one BASELINE config at full size on one GPU and reports throughput + sanity (diagnostic).
-    python tools/run_config.py sand4m|dam16m|mixed4m|cube1m [frames]"""
+    python tools/run_config.py sand4m|dam16m|dam2m|mixed4m|cube1m [frames]"""
 import os
 import sys
 import time
@@ -19,6 +19,8 @@ if name == "sand4m":
     scene = scenes.sand_column_3d(100, 400, 100, grid_capacity=131072)
 elif name == "dam16m":
     scene = scenes.sand_dam_3d(400, 200, 200)
+elif name == "dam2m":  # one GPU's slab of the N-GPU bench workload
+    scene = scenes.sand_dam_3d(50, 200, 200, grid_capacity=65536)
 elif name == "mixed4m":
     scene = scenes.mixed_coupled_3d(160, 160, 160, grid_capacity=131072, n_dynamic=4)
 else:

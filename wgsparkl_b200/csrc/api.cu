@@ -674,6 +674,7 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
         for (int k = 0; k < 9; ++k)
             if (s.two_ways && s.inv_inertia[k] != 0.0f) d->bodies_react = true;
     }
+    dev.bodies_react = d->bodies_react ? 1 : 0;
     std::vector<BodyDev> hb(B200MPM_MAX_BODIES);
     std::memset(hb.data(), 0, hb.size() * sizeof(BodyDev));
     for (size_t i = 0; i < num_bodies; ++i) {
@@ -945,13 +946,15 @@ int b200mpm_write_body_vels(b200mpm_data* d, const b200mpm_velocity* vels, size_
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k)
             if (vels[i].linear[k] != 0.0f || vels[i].angular[k] != 0.0f) {
-                if (!d->bodies_react)
-                    for (auto& gp : d->graph_exec) // the captured sharded substep has no impulse all-reduce yet
-                        if (gp[PHASE_SHARDED]) {
-                            cudaGraphExecDestroy(gp[PHASE_SHARDED]);
-                            gp[PHASE_SHARDED] = nullptr;
-                        }
+                if (!d->bodies_react) // the captured substeps have neither the impulse pass nor its all-reduce yet
+                    for (auto& gp : d->graph_exec)
+                        for (auto& g : gp)
+                            if (g) {
+                                cudaGraphExecDestroy(g);
+                                g = nullptr;
+                            }
                 d->bodies_react = true;
+                d->dev.bodies_react = 1;
             }
     CU_TRY(cudaMemcpyAsync(staging_half, pinned_half, n * sizeof(b200mpm_velocity), cudaMemcpyHostToDevice, p->stream));
     launch_write_vels(p->cfg(), d->dev, (const b200mpm_velocity*)staging_half, (uint32_t)n);

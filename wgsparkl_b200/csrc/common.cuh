@@ -121,6 +121,7 @@ struct DeviceData {
     uint32_t num_materials;
     int has_plastic; // any particle can reach phase == 0
     int has_bodies; // CPIC on
+    int bodies_react; // some body has mass or motion, i.e. impulses can matter (host-maintained, api.cu)
 
     // particle state, ping-pong (index 0/1). Layout: see DESIGN.md "Data layout in HBM".
     float4* pos4[2]; // x y z | bits(material id | flags)

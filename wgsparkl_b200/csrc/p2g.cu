@@ -98,6 +98,20 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
                 normal = v3(nd.x, nd.y, (D == 3) ? nd.z : 0.0f);
             }
         }
+        // Momentum pass next to a collider: which of the 3^D nodes are CPIC-incompatible with this particle
+        // (grid.wgsl:250-255). A particle away from every collider (pa == 0, the majority even in collider-side
+        // blocks) is compatible with all of them and never looks at the node colours.
+        uint32_t bad = 0u;
+        if (MODE == P2G_CPIC_MOMENTUM && pa != 0u) {
+#pragma unroll
+            for (int n = 0; n < Dim<D>::NBH; ++n) {
+                const uint2 nc = tcdf[tb + (n % 3) + T * ((n / 3) % 3) + T * T * (n / 9)];
+                if (!affinities_are_compatible(nc.x, pa)) {
+                    bad |= 1u << n;
+                    if (nc.y != NONE) any_incompatible = any_incompatible || (d.bodies[nc.y].needs_impulse != 0u);
+                }
+            }
+        }
 #pragma unroll
         for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz) {
             float az[D];
@@ -114,10 +128,11 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
                 for (int sx = 0; sx < 3; ++sx) {
                     const int n = sx + 3 * sy + 9 * sz;
                     const float wt = w[0][sx] * wyz;
-                    if (MODE != P2G_FAST) {
+                    if (MODE == P2G_CPIC_MOMENTUM && ((bad >> n) & 1u)) continue;
+                    if (MODE == P2G_CPIC_IMPULSE) {
                         const uint2 nc = tcdf[tb + sx + T * sy + T * T * sz];
                         const bool compatible = affinities_are_compatible(nc.x, pa);
-                        if (MODE == P2G_CPIC_IMPULSE) {
+                        {
                             if (!compatible && nc.y != NONE && d.bodies[nc.y].needs_impulse) { // p2g.wgsl:203-225
                                 const BodyDev& body = d.bodies[nc.y];
                                 V3 dpt = v3(d0[0] + (float)sx * h, d0[1] + (float)sy * h, (D == 3) ? d0[D - 1] + (float)sz * h : 0.0f);
@@ -141,10 +156,6 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
                             }
                             continue;
                         }
-                        if (!compatible) {
-                            if (nc.y != NONE) any_incompatible = any_incompatible || (d.bodies[nc.y].needs_impulse != 0u);
-                            continue;
-                        }
                     }
                     if (MODE != P2G_CPIC_IMPULSE) {
 #pragma unroll
@@ -163,8 +174,10 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
 // in the kernel (a CTA is a single warp), so some warps stage while others compute.
 //   CPIC = false: blocks whose tile holds no collider (block_flags == 0, or no bodies at all).
 //   CPIC = true : the few blocks next to a collider (compact list), further split into PARTS work items.
-template <int D, bool CPIC>
-__global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
+//   IMP (with CPIC): some body can react to impulses (DeviceData::bodies_react) - without it the per-node impulse
+//   accumulators (27 x 6 registers, 5 KB of shared memory) and the second pass are compiled out.
+template <int D, bool CPIC, bool IMP>
+__global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, LB = Dim<D>::LOG_BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC, NBH = Dim<D>::NBH;
     constexpr int WI = (D == 3) ? 6 : 3; // impulse components per node
@@ -178,7 +191,7 @@ __global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
     __shared__ uint32_t s_aff[CPIC ? CHUNK : 1]; // this substep's particle affinities (k_g2p_cdf, by sorted slot)
     __shared__ uint32_t s_nbr[NA];
     __shared__ uint2 tcdf[CPIC ? TC : 1];
-    __shared__ float timp[CPIC ? TC * WI : 1];
+    __shared__ float timp[IMP ? TC * WI : 1];
 
     const int lane = threadIdx.x;
     // A collider-side half-block is split into PARTS work items (each takes every cell's PARTS-th share of the
@@ -276,8 +289,10 @@ __global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
                     c = make_uint2(g.y, g.z);
                 }
                 tcdf[n] = c;
+                if (IMP) {
 #pragma unroll
-                for (int k = 0; k < WI; ++k) timp[n * WI + k] = 0.0f;
+                    for (int k = 0; k < WI; ++k) timp[n * WI + k] = 0.0f;
+                }
             }
             __syncwarp();
         }
@@ -316,7 +331,7 @@ __global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
                         __syncwarp();
                     }
         }
-        if (CPIC) {
+        if (IMP) {
             // Second pass, only if some particle/node pair of this work item is CPIC-incompatible with a collider
             // that can react: per-node body impulses (p2g.wgsl:201-226).
             if (__any_sync(0xffffffffu, incompatible)) {
@@ -358,7 +373,7 @@ __global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
             float4 c = tile[n];
             if (D == 2) c.w = 0.0f; // 2D stores (px, py, mass, 0)
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f) atomicAdd(d.node_mv + node, c);
-            if (CPIC) {
+            if (IMP) {
                 uint32_t cid = tcdf[n].y;
                 if (cid != NONE) { // p2g.wgsl:142-155: integer atomics, i32(x * 1e5)
                     BodyDev& body = d.bodies[cid];
@@ -381,8 +396,8 @@ __global__ void __launch_bounds__(32) k_p2g(DeviceData d, int cur) {
 void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
     const int grid = c.num_sms * 10; // 10 single-warp CTAs per SM (shared memory: 22 KB each)
-    if (c.dim == 2) k_p2g<2, false><<<grid, 32, 0, c.stream>>>(d, cur);
-    else k_p2g<3, false><<<grid, 32, 0, c.stream>>>(d, cur);
+    if (c.dim == 2) k_p2g<2, false, false><<<grid, 32, 0, c.stream>>>(d, cur);
+    else k_p2g<3, false, false><<<grid, 32, 0, c.stream>>>(d, cur);
     ++*c.launch_counter;
 }
 
@@ -390,9 +405,15 @@ void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
 // instantiations touch disjoint blocks and meet only in the commutative node reductions.
 void launch_p2g_cpic(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0 || !d.has_bodies) return;
-    const int grid = c.num_sms * 7;
-    if (c.dim == 2) k_p2g<2, true><<<grid, 32, 0, c.stream>>>(d, cur);
-    else k_p2g<3, true><<<grid, 32, 0, c.stream>>>(d, cur);
+    if (d.bodies_react) {
+        const int grid = c.num_sms * 7;
+        if (c.dim == 2) k_p2g<2, true, true><<<grid, 32, 0, c.stream>>>(d, cur);
+        else k_p2g<3, true, true><<<grid, 32, 0, c.stream>>>(d, cur);
+    } else { // every body is immovable and at rest: no impulse can have an effect (rigid_impulses.wgsl:94-137)
+        const int grid = c.num_sms * 9;
+        if (c.dim == 2) k_p2g<2, true, false><<<grid, 32, 0, c.stream>>>(d, cur);
+        else k_p2g<3, true, false><<<grid, 32, 0, c.stream>>>(d, cur);
+    }
     ++*c.launch_counter;
 }
 
