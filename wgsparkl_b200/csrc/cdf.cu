@@ -151,6 +151,12 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
                 for (int sy = 0; sy < 3; ++sy)
 #pragma unroll
                     for (int sx = 0; sx < 3; ++sx) particle_affinity |= t_aff[tb + sx + T * sy + T * T * sz] & 0xffffu;
+            if (particle_affinity == 0u) {
+                // No node of the stencil sees a collider: every MLS term is masked out (combined == 0 below), the
+                // system is singular and the result is Particle::default_cdf() whatever the sticky signs say.
+                new_aff[k] = 0u;
+                continue;
+            }
             for (uint32_t ic = 0; ic < num_bodies; ++ic) {
                 const uint32_t bit = 1u << ic, mask = 1u << (ic + 16);
                 if ((prev_affinity & bit) != 0u) { // sticky sign, even if the affinity bit is gone (g2p_cdf.wgsl:186-188)
