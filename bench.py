@@ -221,7 +221,8 @@ def run_ours(args):
             data.read_positions_async(host_pos[e2e_slot[0]])
             e2e_slot[0] ^= 1
         else:
-            data.read_positions_unordered(host_pos[0])  # D2H: this rank's slab, into pinned host memory
+            data.read_positions_unordered_async(host_pos[e2e_slot[0]])  # D2H of this rank's slab, same pattern
+            e2e_slot[0] ^= 1
 
     for _ in range(args.warmup):
         frame_device()

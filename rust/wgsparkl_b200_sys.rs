@@ -192,5 +192,6 @@ extern "C" {
     pub fn b200mpm_shard_p2p_export(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, handle_out: *mut c_void, bytes: usize) -> c_int;
     pub fn b200mpm_shard_p2p_connect(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, handles: *const c_void, num_handles: usize) -> c_int;
     pub fn b200mpm_read_positions_unordered(d: *mut b200mpm_data, out: *mut f32, capacity: usize, count: *mut usize) -> c_int;
+    pub fn b200mpm_read_positions_unordered_async(d: *mut b200mpm_data, out: *mut f32, capacity: usize, count: *mut usize) -> c_int;
     pub fn b200mpm_read_particles_unordered(d: *mut b200mpm_data, out: *mut b200mpm_particle, ids: *mut u32, capacity: usize, count: *mut usize) -> c_int;
 }

@@ -80,3 +80,20 @@ def test_single_slab_phased_path_matches_full_substep():
     assert parity.field_rel_err(got["position"], ref["position"]) <= 1e-6
     assert parity.field_rel_err(got["velocity"], ref["velocity"]) <= 1e-5
     grp.close()
+
+
+def test_async_unordered_readback_of_a_slab():
+    """b200mpm_read_positions_unordered_async on sharded data: same particles as the blocking call."""
+    import torch
+
+    scene = scenes.elastic_cube_3d(12, y_offset=-5.0)
+    scene["particles"]["velocity"][:, 0] = 6.0
+    grp = LocalSlabs(scene, 2)
+    grp.step(20)
+    for sh in grp.ranks:
+        ref = sh.data.read_positions_unordered()
+        out = torch.empty((sh.data.particle_capacity, 4), dtype=torch.float32).pin_memory().numpy()
+        n = sh.data.read_positions_unordered_async(out)
+        sh.pipe.sync()
+        assert n == len(ref) and np.array_equal(out[:n], ref)
+    grp.close()

@@ -1006,32 +1006,60 @@ int b200mpm_read_positions(b200mpm_data* d, float* out) {
     return B200MPM_OK;
 }
 
+namespace {
+// Two device staging slots + a copy stream: the gather of readback k+1 may run while copy k is still in flight.
+int ensure_async_readback(b200mpm_data* d) {
+    if (d->copy_stream) return B200MPM_OK;
+    const size_t bytes = (size_t)d->dev.n * sizeof(float4);
+    CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CU_TRY(cudaMalloc(&d->pos_stage[k], bytes));
+        CU_TRY(cudaEventCreateWithFlags(&d->pos_gathered[k], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&d->pos_copied[k], cudaEventDisableTiming));
+        CU_TRY(cudaEventRecord(d->pos_copied[k], d->copy_stream));
+    }
+    return B200MPM_OK;
+}
+int enqueue_async_positions(b200mpm_pipeline* p, b200mpm_data* d, float* out, size_t count, int unordered) {
+    const int slot = d->pos_slot ^= 1;
+    // the slot's previous copy must have left the device before the gather overwrites it
+    CU_TRY(cudaStreamWaitEvent(p->stream, d->pos_copied[slot], 0));
+    launch_gather_positions(p->cfg(), d->dev, d->cur, d->pos_stage[slot], unordered);
+    CU_TRY(cudaEventRecord(d->pos_gathered[slot], p->stream));
+    CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->pos_gathered[slot], 0));
+    CU_TRY(cudaMemcpyAsync(out, d->pos_stage[slot], count * sizeof(float4), cudaMemcpyDeviceToHost, d->copy_stream));
+    CU_TRY(cudaEventRecord(d->pos_copied[slot], d->copy_stream));
+    return B200MPM_OK;
+}
+} // namespace
+
 int b200mpm_read_positions_async(b200mpm_data* d, float* out) {
     if (!d || (!out && d->dev.n)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     if (d->dev.n == 0) return B200MPM_OK;
     b200mpm_pipeline* p = d->pipe;
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
-    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_positions_unordered");
+    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_positions_unordered_async");
     CU_TRY(cudaSetDevice(p->device));
-    const size_t bytes = (size_t)d->dev.n * sizeof(float4);
-    if (!d->copy_stream) {
-        CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; ++k) {
-            CU_TRY(cudaMalloc(&d->pos_stage[k], bytes));
-            CU_TRY(cudaEventCreateWithFlags(&d->pos_gathered[k], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&d->pos_copied[k], cudaEventDisableTiming));
-            CU_TRY(cudaEventRecord(d->pos_copied[k], d->copy_stream));
-        }
-    }
-    const int slot = d->pos_slot ^= 1;
-    // the slot's previous copy must have left the device before the gather overwrites it
-    CU_TRY(cudaStreamWaitEvent(p->stream, d->pos_copied[slot], 0));
-    launch_gather_positions(p->cfg(), d->dev, d->cur, d->pos_stage[slot]);
-    CU_TRY(cudaEventRecord(d->pos_gathered[slot], p->stream));
-    CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->pos_gathered[slot], 0));
-    CU_TRY(cudaMemcpyAsync(out, d->pos_stage[slot], bytes, cudaMemcpyDeviceToHost, d->copy_stream));
-    CU_TRY(cudaEventRecord(d->pos_copied[slot], d->copy_stream));
-    return B200MPM_OK;
+    int r = ensure_async_readback(d);
+    if (r) return r;
+    return enqueue_async_positions(p, d, out, d->dev.n, 0);
+}
+
+int b200mpm_read_positions_unordered_async(b200mpm_data* d, float* out, size_t capacity, size_t* count) {
+    if (!d || !count) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
+    CU_TRY(cudaSetDevice(p->device));
+    // The live count decides the copy size, so it is read first (4 bytes; waits for the enqueued substeps).
+    uint32_t n_live = 0;
+    CU_TRY(cudaMemcpyAsync(&n_live, &d->dev.counters->n_live, sizeof(n_live), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    *count = n_live;
+    if (n_live == 0) return B200MPM_OK;
+    if (!out || capacity < n_live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "output too small");
+    int r = ensure_async_readback(d);
+    if (r) return r;
+    return enqueue_async_positions(p, d, out, n_live, 1);
 }
 
 int b200mpm_prep_vertex_buffer(b200mpm_pipeline* p, b200mpm_data* d, b200mpm_instance* dev_instances, uint32_t mode) {

@@ -75,6 +75,7 @@ EXPORTS = (
     "b200mpm_shard_step_end",
     "b200mpm_read_particles_unordered",
     "b200mpm_read_positions_unordered",
+    "b200mpm_read_positions_unordered_async",
     "b200mpm_nccl_unique_id",
     "b200mpm_shard_comm_init",
     "b200mpm_shard_step",
@@ -144,6 +145,7 @@ def load_library():
     L.b200mpm_shard_step_end.argtypes = [vp, vp]
     L.b200mpm_read_particles_unordered.argtypes = [vp, vp, vp, sz, ctypes.POINTER(sz)]
     L.b200mpm_read_positions_unordered.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
+    L.b200mpm_read_positions_unordered_async.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
     L.b200mpm_nccl_unique_id.argtypes = [vp, sz]
     L.b200mpm_shard_comm_init.argtypes = [vp, vp, i32, i32, vp, u32, u32]
     L.b200mpm_shard_step.argtypes = [vp, vp, u32]
@@ -413,6 +415,13 @@ class MpmData:
         n = ctypes.c_size_t(0)
         _check(load_library().b200mpm_read_positions_unordered(self._h, abi.ptr(out), out.shape[0], ctypes.byref(n)))
         return out[: n.value]
+
+    def read_positions_unordered_async(self, out: np.ndarray) -> int:
+        """Like read_positions_unordered, but the copy overlaps with later work: returns the live count at once,
+        `out[:count]` (page-locked for a real overlap) is valid after `MpmPipeline.sync()`."""
+        n = ctypes.c_size_t(0)
+        _check(load_library().b200mpm_read_positions_unordered_async(self._h, abi.ptr(out), out.shape[0], ctypes.byref(n)))
+        return int(n.value)
 
     def read_particles_unordered(self):
         """(particles, ids) of the live particles in device order."""
