@@ -19,26 +19,14 @@
 
 namespace b2 {
 
-#ifndef G2P_THREADS_N
-#define G2P_THREADS_N 128
-#endif
-constexpr int G2P_THREADS = G2P_THREADS_N;
-constexpr int G2P_CTA_SCALE = 128 / G2P_THREADS; // CTAs per SM scale with 1 / CTA size
-#ifndef G2P_FMA_GATHER
-#define G2P_FMA_GATHER 1
-#endif
-#ifndef G2P_MINB_E
-#define G2P_MINB_E 6
-#endif
-#ifndef G2P_MINB_P
-#define G2P_MINB_P 5
-#endif
-#ifndef G2P_LOOKAHEAD
-#define G2P_LOOKAHEAD 0
-#endif
+constexpr int G2P_THREADS = 128;
+// CTAs per SM: 6 x 128 threads at 80 registers (elastic), 5 at 96 (plastic: the SVD + return mapping need the
+// room). Measured alternatives (tools/build_variant.py): 5 / 7 elastic and 4 / 6 plastic are all slower or equal,
+// 64- and 32-thread CTAs are 20 % / 60 % slower.
+constexpr int G2P_MIN_CTAS_ELASTIC = 6, G2P_MIN_CTAS_PLASTIC = 5;
 
 template <int D, bool PLASTIC, bool CPIC>
-__global__ void __launch_bounds__(G2P_THREADS, (PLASTIC ? G2P_MINB_P : G2P_MINB_E) * G2P_CTA_SCALE) k_g2p(DeviceData d, int cur) {
+__global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : G2P_MIN_CTAS_ELASTIC) k_g2p(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC;
     __shared__ float4 tile_v[TC];
@@ -116,21 +104,8 @@ __global__ void __launch_bounds__(G2P_THREADS, (PLASTIC ? G2P_MINB_P : G2P_MINB_
         }
         __syncthreads();
 
-#if G2P_LOOKAHEAD
-        uint32_t id_next = (first + t < last) ? __ldg(d.sorted_ids + first + t) : 0u;
-#endif
         for (uint32_t k = first + t; k < last; k += G2P_THREADS) {
-#if G2P_LOOKAHEAD
-            const uint32_t id = id_next;
-            if (k + G2P_THREADS < last) id_next = __ldg(d.sorted_ids + k + G2P_THREADS);
-#if G2P_LOOKAHEAD == 2
-            if (k + G2P_THREADS < last) {
-                // touches the next record's lines while this one is being computed (ids are one iteration ahead)
-            }
-#endif
-#else
             const uint32_t id = __ldg(d.sorted_ids + k);
-#endif
             const float4 p4 = __ldg(pos4 + id);
             const float4 v4 = __ldg(vel4 + id);
             float F[D * D];
@@ -196,22 +171,12 @@ __global__ void __launch_bounds__(G2P_THREADS, (PLASTIC ? G2P_MINB_P : G2P_MINB_
                         for (int sx = 0; sx < 3; ++sx) {
                             const float4 cell = tile_v[tb + sx + T * sy + T * T * sz];
                             const float cv[3] = {cell.x, cell.y, cell.z};
-#if G2P_FMA_GATHER
                             const float wx = w[0][sx], sxw = (float)sx * w[0][sx];
 #pragma unroll
                             for (int r = 0; r < D; ++r) {
                                 t0[r] = fmaf(wx, cv[r], t0[r]);
                                 if (sx > 0) t1[r] = fmaf(sxw, cv[r], t1[r]);
                             }
-#else
-                            const float wx = w[0][sx];
-#pragma unroll
-                            for (int r = 0; r < D; ++r) {
-                                float wv = wx * cv[r];
-                                t0[r] += wv;
-                                if (sx > 0) t1[r] += (float)sx * wv;
-                            }
-#endif
                         }
                         const float wy = w[1][sy];
 #pragma unroll
@@ -376,7 +341,7 @@ __global__ void __launch_bounds__(G2P_THREADS, (PLASTIC ? G2P_MINB_P : G2P_MINB_
 
 template <int D>
 static void launch_g2p_dim(const LaunchCfg& c, const DeviceData& d, int cur) {
-    const int grid = c.num_sms * 8 * G2P_CTA_SCALE;
+    const int grid = c.num_sms * 8;
     if (d.has_plastic) {
         if (d.has_bodies) k_g2p<D, true, true><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);
         else k_g2p<D, true, false><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);

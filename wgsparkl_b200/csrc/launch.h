@@ -15,7 +15,6 @@ struct LaunchCfg {
 // "update rigid particles" pass + per-substep counter reset.
 void launch_begin_substep(const LaunchCfg& c, const DeviceData& d);
 // "grid sort" pass (WgGrid::queue_sort, src/grid/grid.rs:30-207).
-void launch_clear(const LaunchCfg& c, const DeviceData& d);
 void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur);
 void launch_count(const LaunchCfg& c, const DeviceData& d);
 void launch_scan_cells(const LaunchCfg& c, const DeviceData& d);
