@@ -79,7 +79,15 @@ typedef struct b200mpm_particle {
 } b200mpm_particle;
 
 /* Analytic collider shapes handled by collide() (src/collision/collide.wgsl:23-55). */
-enum { B200MPM_SHAPE_BALL = 0, B200MPM_SHAPE_CUBOID = 1, B200MPM_SHAPE_CAPSULE = 2 };
+enum {
+    B200MPM_SHAPE_BALL = 0,
+    B200MPM_SHAPE_CUBOID = 1,
+    B200MPM_SHAPE_CAPSULE = 2,
+    /* mesh colliders: no analytic projection (collide.wgsl:41 skips them); they act through their sample points,
+     * see b200mpm_data_set_rigid_particles */
+    B200MPM_SHAPE_TRIMESH = 3, /* 3D; also what a heightfield is converted to (particle3d.rs:123-132) */
+    B200MPM_SHAPE_POLYLINE = 4 /* 2D */
+};
 
 /*
  * One coupled collider + its parent body = one BodyCouplingEntry (src/pipeline.rs:107-117);
@@ -245,6 +253,21 @@ enum { /* RenderMode (prep_vertex_buffer.rs:11-18, prep_vertex_buffer3d.wgsl:25-
  * imported into CUDA (cudaImportExternalMemory on a Vulkan/D3D12 allocation), so that drawing needs no host round
  * trip. Asynchronous on the pipeline's stream. Not available for sharded data (a slab holds a changing subset). */
 int b200mpm_prep_vertex_buffer(b200mpm_pipeline* p, b200mpm_data* d, b200mpm_instance* dev_instances, uint32_t mode);
+
+/* ---- mesh colliders: trimesh / heightfield (3D) and polyline (2D) coupling -----------------------------------
+ * GpuRigidParticles::from_rapier (src/solver/particle3d.rs:101-160, particle2d.rs:80-140): the host samples every
+ * mesh collider (sample_mesh / sample_polyline, sampling step = cell_width, pipeline.rs:140) and hands over, in the
+ * colliders' LOCAL frames,
+ *   vertices          3 floats per collider vertex (2D: z = 0),      vertex_colliders  its collider index,
+ *   samples           3 floats per sample point,                      sample_ids        4 uint32 per sample point:
+ *                     the vertex ids of its triangle (2D: segment, third id ignored) and its collider index.
+ * Collider index = position in the `bodies` array of b200mpm_data_create, whose shape_type must be
+ * B200MPM_SHAPE_TRIMESH / _POLYLINE for these colliders. Every substep then runs the reference's
+ * transform_sample_points / transform_shape_points, mark + touch_rigid_particle_blocks and p2g_cdf
+ * (rigid_particle_update.wgsl:26-50, sort.wgsl:38-86, p2g_cdf.wgsl:51-190). Call once, before stepping. */
+int b200mpm_data_set_rigid_particles(b200mpm_data* d, const float* vertices, const uint32_t* vertex_colliders,
+                                     size_t num_vertices, const float* samples, const uint32_t* sample_ids,
+                                     size_t num_samples);
 
 /* Block-capacity growth - the part the reference leaves as a stub ("TODO: handle grid buffer resizing",
  * src/grid/grid.rs:43-118). b200mpm_data_reserve_grid replaces the capacity-sized arrays by larger ones

@@ -26,6 +26,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -806,6 +807,16 @@ struct Sim {
     std::vector<MassProperties<D>> mprops;
     std::vector<IntegerImpulse<D>> body_impulses;
 
+    // Rigid particles: sample points of trimesh (3D) / polyline (2D) colliders (GpuRigidParticles, particle3d.rs:82-88,
+    // particle2d.rs:62-68) and the collider vertices they refer to (ShapeBuffers of wgrapier).
+    std::vector<Vec<D>> rigid_local_pts, rigid_world_pts; // sample points
+    std::vector<std::array<uint32_t, 4>> rigid_ids; // (vertex a, b, c, collider); 2D: (a, b, -, collider)
+    std::vector<uint32_t> rigid_needs_block; // one bit per sample point
+    std::vector<uint32_t> rigid_node_linked_lists; // next pointers
+    std::vector<NodeLinkedList> nodes_rigid_linked_lists;
+    std::vector<Vec<D>> vertex_local_pts, vertex_world_pts;
+    std::vector<uint32_t> vertex_collider_ids;
+
     size_t num_particles() const { return particles_pos.size(); }
     size_t num_bodies() const { return collision_shapes.size(); }
 
@@ -820,6 +831,7 @@ struct Sim {
         active_blocks.assign(c, ActiveBlockHeader<D>{});
         nodes.assign((size_t)c * NUM_CELL_PER_BLOCK, Node<D>{Vec<D>::zero(), 0.0f, {0.0f, 0, NONE}});
         nodes_linked_lists.assign((size_t)c * NUM_CELL_PER_BLOCK, NodeLinkedList{NONE, 0});
+        nodes_rigid_linked_lists.assign((size_t)c * NUM_CELL_PER_BLOCK, NodeLinkedList{NONE, 0});
         scan_values.assign(c, 0);
     }
 
@@ -960,13 +972,169 @@ struct Sim {
     void queue_sort() {
         reset_hmap();
         touch_particle_blocks();
-        // (mark/touch_rigid_particle_blocks: no rigid sample points — analytic colliders only)
+        mark_rigid_particles_needing_block();
+        touch_rigid_particle_blocks();
         update_block_particle_count();
         copy_particles_len_to_scan_value();
         prefix_sum(scan_values);
         copy_scan_values_to_first_particles();
         reset();
         finalize_particles_sort();
+        sort_rigid_particles(); // MpmPipeline::queue_step (pipeline.rs:220-221)
+    }
+
+    // ---- rigid particles -----------------------------------------------------------------------------------
+    void set_rigid_particles(const float* vertices, const uint32_t* vertex_colliders, size_t nv, const float* samples,
+                             const uint32_t* ids4, size_t ns) {
+        vertex_local_pts.resize(nv);
+        vertex_world_pts.resize(nv);
+        vertex_collider_ids.assign(vertex_colliders, vertex_colliders + nv);
+        for (size_t i = 0; i < nv; ++i)
+            for (int k = 0; k < D; ++k) vertex_local_pts[i][k] = vertices[3 * i + k];
+        rigid_local_pts.resize(ns);
+        rigid_world_pts.resize(ns);
+        rigid_ids.resize(ns);
+        for (size_t i = 0; i < ns; ++i) {
+            for (int k = 0; k < D; ++k) rigid_local_pts[i][k] = samples[3 * i + k];
+            rigid_ids[i] = {ids4[4 * i], ids4[4 * i + 1], ids4[4 * i + 2], ids4[4 * i + 3]};
+        }
+        rigid_needs_block.assign((ns + 31) / 32, 0u);
+        rigid_node_linked_lists.assign(ns, NONE);
+        transform_rigid_points();
+    }
+    // transform_sample_points / transform_shape_points (rigid_particle_update.wgsl:26-50)
+    void transform_rigid_points() {
+        for (size_t i = 0; i < rigid_local_pts.size(); ++i) rigid_world_pts[i] = poses[rigid_ids[i][3]].mulPt(rigid_local_pts[i]);
+        for (size_t i = 0; i < vertex_local_pts.size(); ++i)
+            vertex_world_pts[i] = poses[vertex_collider_ids[i]].mulPt(vertex_local_pts[i]);
+    }
+    // sort.wgsl:54-86: a sample point asks for its own block iff that block is missing while one of the other
+    // blocks its stencil reaches exists.
+    void mark_rigid_particles_needing_block() {
+        for (size_t id = 0; id < rigid_world_pts.size(); ++id) {
+            BlockVirtualId<D> blocks[NUM_ASSOC_BLOCKS];
+            blocks_associated_to_block(block_associated_to_point(rigid_world_pts[id]), blocks);
+            int i = 0;
+            for (; i < NUM_ASSOC_BLOCKS; ++i)
+                if (find_block_header_id(blocks[i]) != NONE) break;
+            const uint32_t bit = 1u << (id % 32);
+            if (i > 0 && i < NUM_ASSOC_BLOCKS) rigid_needs_block[id / 32] |= bit;
+            else rigid_needs_block[id / 32] &= ~bit;
+        }
+    }
+    void touch_rigid_particle_blocks() { // sort.wgsl:38-52
+        for (size_t id = 0; id < rigid_world_pts.size(); ++id)
+            if (rigid_needs_block[id / 32] & (1u << (id % 32))) mark_block_as_active(block_associated_to_point(rigid_world_pts[id]));
+    }
+    void sort_rigid_particles() { // sort.wgsl:139-161 (the node lists are reset by `reset`, grid.wgsl:362-379)
+        for (uint32_t b = 0; b < num_active_blocks; ++b)
+            for (uint32_t n = 0; n < NUM_CELL_PER_BLOCK; ++n) nodes_rigid_linked_lists[(size_t)b * NUM_CELL_PER_BLOCK + n] = NodeLinkedList{NONE, 0};
+        for (uint32_t id = 0; id < (uint32_t)rigid_world_pts.size(); ++id) {
+            const Vec<D> pt = rigid_world_pts[id];
+            uint32_t hid = find_block_header_id(block_associated_to_point(pt));
+            if (hid == NONE) continue; // cannot affect the simulation
+            uint32_t local[3] = {0, 0, 0};
+            associated_cell_index_in_block_off_by_one(pt, local);
+            NodeLinkedList& list = nodes_rigid_linked_lists[node_id(hid * NUM_CELL_PER_BLOCK, local)];
+            rigid_node_linked_lists[id] = list.head;
+            list.head = id;
+            list.len += 1;
+        }
+    }
+    // One candidate primitive against one node (p2g_cdf.wgsl:116-190): a projection that falls strictly inside
+    // the segment / on the face interior colours the node.
+    bool project_on_primitive(uint32_t rigid_id, Vec<D> cell_pos, float& distance, bool& sign) const {
+        const auto& ids = rigid_ids[rigid_id];
+        if constexpr (D == 2) {
+            const Vec<2> a = vertex_world_pts[ids[0]], b = vertex_world_pts[ids[1]];
+            // wgparry Segment::projectLocalPoint (not vendored): clamp to the end points
+            const Vec<2> ab = b - a, ap = cell_pos - a;
+            const float ab_ap = dot(ab, ap), sqnab = dot(ab, ab);
+            Vec<2> proj;
+            if (ab_ap <= 0.0f) proj = a;
+            else if (ab_ap >= sqnab) proj = b;
+            else proj = a + ab * (ab_ap / sqnab);
+            const bool ne_a = proj[0] != a[0] || proj[1] != a[1], ne_b = proj[0] != b[0] || proj[1] != b[1];
+            if (!(ne_a && ne_b)) return false;
+            const Vec<2> dpt = cell_pos - proj;
+            distance = length(dpt);
+            sign = (dpt[0] * -ab[1] + dpt[1] * ab[0]) < 0.0f;
+            return true;
+        } else {
+            const Vec<3> a = vertex_world_pts[ids[0]], b = vertex_world_pts[ids[1]], c = vertex_world_pts[ids[2]];
+            const Vec<3> ap = cell_pos - a, bp = cell_pos - b, cp = cell_pos - c;
+            const Vec<3> ab = b - a, ac = c - a, bc = c - b;
+            const Vec<3> n = cross(ab, ac);
+            const float n_length = length(n);
+            if (n_length != 0.0f && dot(cross(ab, n), ap) <= 0.0f && dot(cross(bc, n), bp) <= 0.0f && dot(cross(ac, n), cp) >= 0.0f) {
+                const float signed_dist = dot(n, ap) / n_length;
+                sign = signed_dist < 0.0f;
+                distance = std::fabs(signed_dist);
+                return true;
+            }
+            return false;
+        }
+    }
+    // p2g_cdf (p2g_cdf.wgsl:51-114): every node gathers the rigid particles listed in the 3^D cells whose stencil
+    // contains it, one list element per iteration, and merges the per-iteration result into its cdf.
+    void p2g_cdf() {
+        if (rigid_world_pts.empty()) return;
+        for (uint32_t bid = 0; bid < num_active_blocks; ++bid) {
+            const BlockVirtualId<D> vid = active_blocks[bid].virtual_id;
+            for_each_tid([&](const uint32_t* tid) {
+                const uint32_t global_id = node_id(bid * NUM_CELL_PER_BLOCK, tid);
+                const Vec<D> cell_pos = cell_pos_of(vid, tid);
+                NodeCdf node_cdf = nodes[global_id].cdf;
+                // heads of the lists of the contributing cells: global cell = 4 vid + tid - shift, shift in {0,1,2}^D
+                uint32_t heads[27];
+                uint32_t max_len = 0;
+                const int nsh = (D == 2) ? 9 : 27;
+                for (int sh = 0; sh < nsh; ++sh) {
+                    int shift[3] = {sh % 3, (sh / 3) % 3, sh / 9};
+                    BlockVirtualId<D> nb;
+                    uint32_t local[3] = {0, 0, 0};
+                    for (int k = 0; k < D; ++k) {
+                        const int cell = vid.id[k] * BLOCK + (int)tid[k] - shift[k];
+                        const int blk = (cell >= 0) ? cell / BLOCK : -((-cell + BLOCK - 1) / BLOCK);
+                        nb.id[k] = blk;
+                        local[k] = (uint32_t)(cell - blk * BLOCK);
+                    }
+                    heads[sh] = NONE;
+                    const uint32_t hid = find_block_header_id(nb);
+                    if (hid != NONE) {
+                        const NodeLinkedList& l = nodes_rigid_linked_lists[node_id(hid * NUM_CELL_PER_BLOCK, local)];
+                        heads[sh] = l.head;
+                        max_len = std::max(max_len, l.len);
+                    }
+                }
+                for (uint32_t it = 0; it < max_len; ++it) {
+                    NodeCdf result{1.0e10f, 0u, NONE};
+                    for (int sh = 0; sh < nsh; ++sh) {
+                        const uint32_t rid = heads[sh];
+                        if (rid == NONE) continue;
+                        heads[sh] = rigid_node_linked_lists[rid];
+                        float distance;
+                        bool sign;
+                        if (project_on_primitive(rid, cell_pos, distance, sign)) {
+                            const uint32_t collider_id = rigid_ids[rid][3];
+                            result.affinities |= (1u << collider_id) | ((uint32_t)sign << (collider_id + 16));
+                            if (distance < result.distance) {
+                                result.distance = distance;
+                                result.closest_id = collider_id;
+                            }
+                        }
+                    }
+                    if (result.closest_id != NONE) {
+                        node_cdf.affinities |= result.affinities;
+                        if (result.distance < node_cdf.distance) {
+                            node_cdf.distance = result.distance;
+                            node_cdf.closest_id = result.closest_id;
+                        }
+                    }
+                }
+                nodes[global_id].cdf = node_cdf;
+            });
+        }
     }
 
     // ---- collide (collision/collide.wgsl:23-55) + grid_update_cdf (grid_update_cdf.wgsl:16-39) --
@@ -975,6 +1143,7 @@ struct Sim {
         NodeCdf cdf{MAX_FLT, 0u, NONE};
         float dist_cap = cell_width * 1.5f;
         for (uint32_t i = 0; i < (uint32_t)num_bodies(); ++i) {
+            if (collision_shapes[i].type == B200MPM_SHAPE_TRIMESH || collision_shapes[i].type == B200MPM_SHAPE_POLYLINE) continue;
             ProjectionResult<D> proj = project_point_on_boundary(collision_shapes[i], poses[i], point);
             Vec<D> dpt = proj.point - point;
             bool all_le = true;
@@ -1663,9 +1832,10 @@ struct Sim {
     // ---- MpmPipeline::queue_step (pipeline.rs:195-281) -------------------------------------------
     void substep() {
         update_world_mass_properties(); // "update rigid particles"
+        transform_rigid_points();
         queue_sort(); // "grid sort"
         grid_update_cdf(); // "grid_update_cdf"
-        // "p2g_cdf": no rigid sample points (analytic colliders only) => node cdf unchanged
+        p2g_cdf(); // "p2g_cdf"
         g2p_cdf(); // "g2p_cdf"
         p2g(); // "p2g"
         grid_update(); // "grid_update"

@@ -59,6 +59,8 @@ def lib():
         L.oracle_set_threads.argtypes = [ctypes.c_int]
         L.oracle_set_exact_sigma.argtypes = [ctypes.c_int]
         L.oracle_prep_vertex_buffer.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]
+        L.oracle_set_rigid_particles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.oracle_max_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -111,6 +113,14 @@ class OracleSim:
         out = np.zeros(self.n, dtype=abi.particle_dtype)
         lib().oracle_read_particles(self._h, abi.ptr(out))
         return out
+
+    def set_rigid_particles(self, vertices, vertex_colliders, samples, ids):
+        """GpuRigidParticles (mesh collider sample points): see wgsparkl_b200.rapier.rigid_particles_to_abi."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        vc = np.ascontiguousarray(vertex_colliders, dtype=np.uint32)
+        sp = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 3)
+        ii = np.ascontiguousarray(ids, dtype=np.uint32).reshape(-1, 4)
+        lib().oracle_set_rigid_particles(self._h, abi.ptr(v), abi.ptr(vc), len(v), abi.ptr(sp), abi.ptr(ii), len(sp))
 
     def prep_vertex_buffer(self, instances, mode):
         """prep_vertex_buffer{2d,3d}.wgsl main: updates `instances` (n x abi.instance_dtype) in place."""

@@ -190,10 +190,13 @@ size_t read_grid(const Sim<D>& s, b200mpm_block_info* blocks, b200mpm_node* node
 template <int D>
 void stage(Sim<D>& s, int id) {
     switch (id) {
-    case B200MPM_PASS_UPDATE_RIGID_PARTICLES: s.update_world_mass_properties(); break;
+    case B200MPM_PASS_UPDATE_RIGID_PARTICLES:
+        s.update_world_mass_properties();
+        s.transform_rigid_points();
+        break;
     case B200MPM_PASS_GRID_SORT: s.queue_sort(); break;
     case B200MPM_PASS_GRID_UPDATE_CDF: s.grid_update_cdf(); break;
-    case B200MPM_PASS_P2G_CDF: break;
+    case B200MPM_PASS_P2G_CDF: s.p2g_cdf(); break;
     case B200MPM_PASS_G2P_CDF: s.g2p_cdf(); break;
     case B200MPM_PASS_P2G: s.p2g(); break;
     case B200MPM_PASS_GRID_UPDATE: s.grid_update(); break;
@@ -420,6 +423,13 @@ int oracle_project_point(int dim, const b200mpm_body* b, const float* pt, float*
     vec_to<3>(r.point, out);
     return r.is_inside;
 }
+void oracle_set_rigid_particles(void* hv, const float* vertices, const uint32_t* vertex_colliders, size_t nv,
+                                const float* samples, const uint32_t* ids4, size_t ns) {
+    auto* h = (Handle*)hv;
+    DISPATCH(h, s.set_rigid_particles(vertices, vertex_colliders, nv, samples, ids4, ns),
+             s.set_rigid_particles(vertices, vertex_colliders, nv, samples, ids4, ns));
+}
+
 void oracle_prep_vertex_buffer(void* hv, uint32_t mode, float* inst) {
     auto* h = (Handle*)hv;
     DISPATCH(h, s.prep_vertex_buffer(mode, inst), s.prep_vertex_buffer(mode, inst));

@@ -141,6 +141,15 @@ extern "C" {
     pub fn b200mpm_read_positions_async(d: *mut b200mpm_data, out: *mut f32) -> c_int;
     pub fn b200mpm_read_particles(d: *mut b200mpm_data, out: *mut b200mpm_particle) -> c_int;
     pub fn b200mpm_data_status(d: *mut b200mpm_data, num_active_blocks: *mut u32) -> c_int;
+    pub fn b200mpm_data_set_rigid_particles(
+        d: *mut b200mpm_data,
+        vertices: *const f32,
+        vertex_colliders: *const u32,
+        num_vertices: usize,
+        samples: *const f32,
+        sample_ids: *const u32,
+        num_samples: usize,
+    ) -> c_int;
     pub fn b200mpm_data_reserve_grid(d: *mut b200mpm_data, grid_capacity: u32) -> c_int;
     pub fn b200mpm_data_set_auto_grow(d: *mut b200mpm_data, max_load: f32) -> c_int;
     pub fn b200mpm_prep_vertex_buffer(p: *mut b200mpm_pipeline, d: *mut b200mpm_data, dev_instances: *mut b200mpm_instance, mode: u32) -> c_int;

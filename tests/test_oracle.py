@@ -198,3 +198,60 @@ def test_exact_sigma_mode_bounds_reference_rounding_noise(oracle_mod):
     a, b = run(0, 10), run(1, 10)
     assert 0.0 < parity.field_rel_err(a["velocity"], b["velocity"]) <= 5e-3
     assert parity.field_rel_err(a["position"], b["position"]) <= 2e-6
+
+
+def test_mesh_sampling_restatement():
+    """sample_triangle / sample_edge / sample_mesh (particle3d.rs:251-428): samples lie in their triangle, edges are
+    sampled once, and a cell_width-spaced grid over a big triangle has no unsampled cell."""
+    from wgsparkl_b200.rapier import sample_mesh, sample_polyline
+
+    v = np.array([[0, 0, 0], [10, 0, 0], [0, 8, 0], [10, 8, 3]], dtype=np.float32)
+    f = np.array([[0, 1, 2], [1, 3, 2]], dtype=np.uint32)
+    pts = sample_mesh(v, f, 1.0)
+    assert len(pts) > 100
+    for p, t in pts:
+        a, b, c = (v[int(i)].astype(np.float64) for i in f[t])
+        n = np.cross(b - a, c - a)
+        assert abs(np.dot(n, p - a)) / np.linalg.norm(n) < 1e-4  # in the plane
+        l = np.linalg.solve(np.stack([b - a, c - a, n], axis=1), p - a)
+        assert l[0] > -1e-4 and l[1] > -1e-4 and l[0] + l[1] < 1 + 1e-4  # in the triangle
+    cells = {(int(np.floor(p[0])), int(np.floor(p[1]))) for p, t in pts if t == 0}
+    inside = {(i, j) for i in range(10) for j in range(8) if (i + 1) / 10 + (j + 1) / 8 < 1.0}
+    assert inside <= cells, "every grid cell fully inside the triangle holds a sample"
+    edge_pts = [p for p, t in pts if abs(p[1] - (8 - 0.8 * p[0])) < 1e-4 and abs(p[2]) < 1e-6]
+    assert 5 < len(edge_pts) < 25  # the shared edge (1, 2) is sampled once, not twice
+    poly = sample_polyline(np.array([[0, 0], [3, 0], [3, 4]], dtype=np.float32), np.array([[0, 1], [1, 2]]), 1.0)
+    assert len(poly) == (1 + 4 + 1) + (1 + 5 + 1)  # a, shifts 0..floor(len), b per segment (particle2d.rs:206-234)
+
+
+def test_trimesh_box_agrees_with_analytic_cuboid(oracle_mod):
+    """p2g_cdf restatement: a box given as a triangle mesh colours the nodes near its faces with the same distance,
+    and (away from the surface plane itself) the same inside/outside sign, as the analytic cuboid of collide()."""
+    from wgsparkl_b200.rapier import ColliderBuilder, ColliderSet, RigidBodyBuilder, RigidBodySet, bodies_to_abi, rigid_particles_to_abi
+
+    he = (12.0, 3.0, 12.0)
+    grids = {}
+    for mesh in (False, True):
+        scene = scenes.elastic_cube_3d(10, y_offset=-5.0)
+        bodies, colliders = RigidBodySet(), ColliderSet()
+        rb = bodies.insert(RigidBodyBuilder.fixed().translation([0.0, -6.2, 0.0]))
+        shape = ColliderBuilder.trimesh(*scenes.box_trimesh(he)) if mesh else ColliderBuilder.cuboid(*he)
+        colliders.insert_with_parent(shape, rb, bodies)
+        scene["bodies"] = bodies_to_abi(bodies, colliders, 3)
+        sim = oracle_mod.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+        if mesh:
+            sim.set_rigid_particles(*rigid_particles_to_abi(bodies, colliders, 3, scene["cell_width"]))
+        for st in range(4):
+            sim.stage(st)
+        blocks, nodes = sim.read_grid()
+        grids[mesh] = {tuple(b["vid"]): nodes[i] for i, b in enumerate(blocks)}
+        sim.close()
+    assert len(grids[True]) > len(grids[False]), "sample points activate blocks below the particles' own"
+    n_both = 0
+    for vid, na in grids[False].items():
+        nb = grids[True][vid]
+        both = (na["cdf_affinities"] != 0) & (nb["cdf_affinities"] != 0)
+        n_both += int(both.sum())
+        assert np.allclose(na["cdf_distance"][both], nb["cdf_distance"][both], atol=1e-5)
+        assert np.array_equal(na["cdf_affinities"][both], nb["cdf_affinities"][both])
+    assert n_both > 300

@@ -17,6 +17,8 @@ MODEL_NEO_HOOKEAN = 1
 SHAPE_BALL = 0
 SHAPE_CUBOID = 1
 SHAPE_CAPSULE = 2
+SHAPE_TRIMESH = 3  # 3D mesh colliders act through their sample points (MpmData.set_rigid_particles)
+SHAPE_POLYLINE = 4  # 2D
 
 PASS_NAMES = (  # src/pipeline.rs:201-271
     "update rigid particles",

@@ -205,12 +205,17 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
     {
         PassTimer t(p, B200MPM_PASS_GRID_SORT);
         launch_touch(c, d->dev, d->cur);
+        launch_touch_rigid(c, d->dev);
         launch_count(c, d->dev);
         launch_scan_cells(c, d->dev);
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_UPDATE_CDF);
         launch_block_prepare(c, d->dev);
+    }
+    {
+        PassTimer t(p, B200MPM_PASS_P2G_CDF);
+        launch_p2g_cdf(c, d->dev);
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_SORT);
@@ -306,12 +311,15 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
         return;
     }
     launch_begin_substep(c, dev);
+    launch_transform_rigid(c, dev);
     launch_touch(c, dev, d->cur);
+    launch_touch_rigid(c, dev);
     if (side) {
         cudaEventRecord(d->ev[0], main);
         cudaStreamWaitEvent(side, d->ev[0], 0);
     }
     launch_block_prepare(cs, dev);
+    launch_p2g_cdf(cs, dev);
     if (side) cudaEventRecord(d->ev[1], side);
     launch_count(c, dev);
     launch_scan_cells(c, dev);
@@ -385,6 +393,7 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
     {
         PassTimer t(p, B200MPM_PASS_UPDATE_RIGID_PARTICLES);
         launch_begin_substep(c, d->dev);
+        launch_transform_rigid(c, d->dev);
     }
     run_sort(p, d);
     {
@@ -497,8 +506,9 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
         return fail(B200MPM_ERR_INVALID_ARGUMENT, "grid_capacity must be in [1, 2^24]");
     if (num_particles >= (1ull << 31)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "too many particles");
     for (size_t i = 0; i < num_bodies; ++i)
-        if (bodies[i].shape_type > B200MPM_SHAPE_CAPSULE)
-            return fail(B200MPM_ERR_INVALID_ARGUMENT, "unsupported collider shape (ball, cuboid, capsule only)");
+        if (bodies[i].shape_type > B200MPM_SHAPE_CAPSULE &&
+            bodies[i].shape_type != (uint32_t)(p->dim == 3 ? B200MPM_SHAPE_TRIMESH : B200MPM_SHAPE_POLYLINE))
+            return fail(B200MPM_ERR_INVALID_ARGUMENT, "unsupported collider shape (ball, cuboid, capsule; trimesh in 3D, polyline in 2D)");
     CU_TRY(cudaSetDevice(p->device));
 
     uint32_t capacity = 1;
@@ -784,6 +794,59 @@ void b200mpm_data_destroy(b200mpm_data* d) {
 size_t b200mpm_data_num_particles(const b200mpm_data* d) { return d ? d->n_live_host : 0; }
 size_t b200mpm_data_num_bodies(const b200mpm_data* d) { return d ? d->num_bodies : 0; }
 
+int b200mpm_data_set_rigid_particles(b200mpm_data* d, const float* vertices, const uint32_t* vertex_colliders,
+                                     size_t num_vertices, const float* samples, const uint32_t* sample_ids,
+                                     size_t num_samples) {
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null data");
+    b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
+    if (d->dev.num_rigid || d->dev.num_mesh_verts) return fail(B200MPM_ERR_INVALID_ARGUMENT, "rigid particles are already set");
+    if (num_samples == 0) return B200MPM_OK;
+    if (!vertices || !vertex_colliders || !samples || !sample_ids || num_vertices == 0)
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (num_samples >= (1ull << 31) || num_vertices >= (1ull << 31)) return fail(B200MPM_ERR_INVALID_ARGUMENT, "too many points");
+    const int prim = (p->dim == 3) ? 3 : 2;
+    for (size_t i = 0; i < num_vertices; ++i)
+        if (vertex_colliders[i] >= d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "vertex refers to an unknown collider");
+    for (size_t i = 0; i < num_samples; ++i) {
+        if (sample_ids[4 * i + 3] >= d->num_bodies) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sample refers to an unknown collider");
+        for (int k = 0; k < prim; ++k)
+            if (sample_ids[4 * i + k] >= num_vertices) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sample refers to an unknown vertex");
+    }
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    DeviceData& dev = d->dev;
+    std::vector<float4> hv(num_vertices), hs(num_samples);
+    std::vector<uint4> hi(num_samples);
+    for (size_t i = 0; i < num_vertices; ++i) hv[i] = make_float4(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2], 0.f);
+    for (size_t i = 0; i < num_samples; ++i) {
+        hs[i] = make_float4(samples[3 * i], samples[3 * i + 1], samples[3 * i + 2], 0.f);
+        hi[i] = make_uint4(sample_ids[4 * i], sample_ids[4 * i + 1], prim == 3 ? sample_ids[4 * i + 2] : 0u, sample_ids[4 * i + 3]);
+    }
+    int r = 0;
+    if ((r = dev_alloc(d, &dev.mv_local, num_vertices))) return r;
+    if ((r = dev_alloc(d, &dev.mv_world, num_vertices))) return r;
+    if ((r = dev_alloc(d, &dev.mv_body, num_vertices))) return r;
+    if ((r = dev_alloc(d, &dev.rp_local, num_samples))) return r;
+    if ((r = dev_alloc(d, &dev.rp_world, num_samples))) return r;
+    if ((r = dev_alloc(d, &dev.rp_ids, num_samples))) return r;
+    if ((r = dev_alloc(d, &dev.rp_needs_block, num_samples))) return r;
+    CU_TRY(cudaMemcpyAsync(dev.mv_local, hv.data(), num_vertices * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaMemcpyAsync(dev.mv_body, vertex_colliders, num_vertices * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaMemcpyAsync(dev.rp_local, hs.data(), num_samples * sizeof(float4), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaMemcpyAsync(dev.rp_ids, hi.data(), num_samples * sizeof(uint4), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    dev.num_mesh_verts = (uint32_t)num_vertices;
+    dev.num_rigid = (uint32_t)num_samples;
+    for (auto& gp : d->graph_exec) // the captured substeps do not contain the rigid-particle kernels
+        for (auto& g : gp)
+            if (g) {
+                cudaGraphExecDestroy(g);
+                g = nullptr;
+            }
+    return B200MPM_OK;
+}
+
 int b200mpm_data_reserve_grid(b200mpm_data* d, uint32_t grid_capacity) {
     if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null data");
     b200mpm_pipeline* p = d->pipe;
@@ -854,6 +917,7 @@ int b200mpm_sort_only(b200mpm_pipeline* p, b200mpm_data* d) {
     CU_TRY(cudaSetDevice(p->device));
     LaunchCfg c = p->cfg();
     launch_begin_substep(c, d->dev);
+    launch_transform_rigid(c, d->dev);
     run_sort(p, d);
     d->sorted_indirect = true;
     CU_TRY(cudaGetLastError());

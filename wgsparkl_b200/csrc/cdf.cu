@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
             uint32_t aff = 0u;
             if (hn != NONE) {
                 uint4 g = d.node_cdf[hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B];
-                dist = __uint_as_float(g.x);
-                aff = g.y;
+                dist = __uint_as_float(g.y);
+                aff = g.z;
             }
             t_dist[n] = dist;
             t_aff[n] = aff;

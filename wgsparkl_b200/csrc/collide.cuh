@@ -135,6 +135,7 @@ __device__ inline NodeCdf collide(const BodyDev* __restrict__ bodies, uint32_t n
     const float dist_cap = cell_width * 1.5f;
     for (uint32_t i = 0; i < num_bodies; ++i) {
         const BodyDev& b = bodies[i];
+        if (b.shape_type == B200MPM_SHAPE_TRIMESH || b.shape_type == B200MPM_SHAPE_POLYLINE) continue; // collide.wgsl:41
         // local = R^T (point - t)
         float d[D], loc[D], lp[D], wp[D];
 #pragma unroll

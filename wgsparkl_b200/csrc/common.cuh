@@ -150,7 +150,10 @@ struct DeviceData {
     uint32_t* cell_start; // capacity*64 + 1: per-cell particle counts, scanned in place
     uint32_t* nbr; // capacity * NASSOC: header ids of blocks vid + {0,1}^D
     float4* node_mv; // capacity*64: momentum xyz + mass (Node.momentum_velocity_mass, grid.wgsl:257-267)
-    uint4* node_cdf; // capacity*64: bits(distance), affinities, closest_id, - (NodeCdf, grid.wgsl:233-240)
+    // capacity*64: closest_id, bits(distance), affinities, - (NodeCdf, grid.wgsl:233-240). The first two words form
+    // one 64-bit key (distance in the high half; distances are >= 0, so the key orders like the distance) that the
+    // mesh-collider scatter lowers with a single atomicMin (k_p2g_cdf).
+    uint4* node_cdf;
     uint64_t* scan_state; // single-pass scan tile descriptors
     uint8_t* block_f0; // capacity: 1 if one of the block's own nodes is near / inside a collider (k_block_prepare)
     uint32_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)
@@ -159,6 +162,16 @@ struct DeviceData {
     uint32_t g2p_list_len; // capacity + n / G2P_ITEM + 1
 
     BodyDev* bodies;
+    // Rigid particles = sample points of trimesh / polyline colliders (GpuRigidParticles, particle3d.rs:82-88) and
+    // the collider vertices their primitives refer to; world-space copies are refreshed every substep.
+    uint32_t num_rigid, num_mesh_verts;
+    float4* rp_local;
+    float4* rp_world;
+    uint4* rp_ids; // (vertex a, b, c, collider index)
+    uint32_t* rp_needs_block; // one word per sample point (sort.wgsl:54-86)
+    float4* mv_local;
+    float4* mv_world;
+    uint32_t* mv_body;
     SimState* sim;
     Counters* counters;
 };

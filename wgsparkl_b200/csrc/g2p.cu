@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : 
                 out.w = mass;
                 if (CPIC && any_cdf) {
                     uint4 g = d.node_cdf[node];
-                    cdf = make_uint2(g.y, g.z);
+                    cdf = make_uint2(g.z, g.x); // (affinities, closest_id)
                 }
             }
             tile_v[n] = out;

@@ -54,6 +54,9 @@ void launch_impulses_io(const LaunchCfg& c, const DeviceData& d, int* buf, int w
 void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_info* blocks, b200mpm_node* nodes,
                         uint32_t max_blocks);
 void launch_gather_sorted_ids(const LaunchCfg& c, const DeviceData& d, int cur, int indirect, uint32_t* out);
+void launch_transform_rigid(const LaunchCfg& c, const DeviceData& d);
+void launch_touch_rigid(const LaunchCfg& c, const DeviceData& d);
+void launch_p2g_cdf(const LaunchCfg& c, const DeviceData& d);
 void launch_prep_vertex_buffer(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_instance* inst, uint32_t mode);
 void launch_write_poses(const LaunchCfg& c, const DeviceData& d, const b200mpm_pose* poses, uint32_t n);
 void launch_write_vels(const LaunchCfg& c, const DeviceData& d, const b200mpm_velocity* vels, uint32_t n);

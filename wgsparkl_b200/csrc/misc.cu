@@ -435,9 +435,9 @@ __global__ void k_gather_grid(DeviceData d, b200mpm_block_info* blocks, b200mpm_
         o.momentum_velocity_mass[D] = mass;
         if (d.has_bodies) {
             uint4 c = d.node_cdf[b * CELLS_PER_BLOCK + t];
-            o.cdf_distance = __uint_as_float(c.x);
-            o.cdf_affinities = c.y;
-            o.cdf_closest_id = c.z;
+            o.cdf_closest_id = c.x;
+            o.cdf_distance = __uint_as_float(c.y);
+            o.cdf_affinities = c.z;
         } else {
             o.cdf_distance = 1.0e10f; // collide() with no shapes (collide.wgsl:24-25)
             o.cdf_affinities = 0u;

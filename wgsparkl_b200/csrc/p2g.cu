@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
                 uint2 c = make_uint2(0u, NONE);
                 if (hn != NONE) {
                     uint4 g = d.node_cdf[hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B];
-                    c = make_uint2(g.y, g.z);
+                    c = make_uint2(g.z, g.x); // (affinities, closest_id)
                 }
                 tcdf[n] = c;
                 if (IMP) {

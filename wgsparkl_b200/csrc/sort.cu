@@ -156,6 +156,144 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
 
 }
 
+// ---- rigid particles (sample points of trimesh / polyline colliders) ---------------------------------------
+// transform_sample_points + transform_shape_points (rigid_particle_update.wgsl:26-50): world = R local + t with
+// the pose of the point's collider.
+template <int D>
+__global__ void k_transform_rigid(DeviceData d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vertex = i < d.num_mesh_verts;
+    const uint32_t j = vertex ? i : i - d.num_mesh_verts;
+    if (!vertex && j >= d.num_rigid) return;
+    const float4 l = vertex ? d.mv_local[j] : d.rp_local[j];
+    const BodyDev& b = d.bodies[vertex ? d.mv_body[j] : d.rp_ids[j].w];
+    const float lp[3] = {l.x, l.y, l.z};
+    float w[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        float s = b.rot[r] * lp[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) s = s + b.rot[k * D + r] * lp[k];
+        w[r] = s + b.trans[r];
+    }
+    (vertex ? d.mv_world : d.rp_world)[j] = make_float4(w[0], w[1], w[2], 0.f);
+}
+
+template <int D>
+__device__ __forceinline__ void rigid_block(const DeviceData& d, uint32_t i, int& bx, int& by, int& bz, uint32_t& cell) {
+    const float h = d.sim->cell_width, inv_h = 1.0f / h;
+    const float4 p = d.rp_world[i];
+    const int cx = assoc_cell(p.x, h, inv_h), cy = assoc_cell(p.y, h, inv_h), cz = (D == 3) ? assoc_cell(p.z, h, inv_h) : 0;
+    bx = cx >> Dim<D>::LOG_BLOCK, by = cy >> Dim<D>::LOG_BLOCK, bz = cz >> Dim<D>::LOG_BLOCK;
+    cell = (cx & (Dim<D>::BLOCK - 1)) + (cy & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK +
+           ((D == 3) ? (cz & (Dim<D>::BLOCK - 1)) * Dim<D>::BLOCK * Dim<D>::BLOCK : 0);
+}
+
+// mark_rigid_particles_needing_block (sort.wgsl:54-86): a sample point asks for its own block iff that block is
+// missing while another block its stencil reaches exists. Evaluated against the table as touch_particle_blocks
+// left it - hence a kernel of its own, before any sample point inserts anything.
+template <int D>
+__global__ void k_mark_rigid(DeviceData d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.num_rigid) return;
+    int bx, by, bz;
+    uint32_t cell;
+    rigid_block<D>(d, i, bx, by, bz, cell);
+    const uint32_t mask = d.capacity - 1;
+    uint32_t needs = 0u;
+    if (find_block(d.hkeys, d.hvals, mask, pack_key<D>(bx, by, bz)) == NONE) {
+        for (int o = 1; o < Dim<D>::NASSOC && !needs; ++o) {
+            const int ox = o & 1, oy = (o >> 1) & 1, oz = (D == 3) ? (o >> 2) & 1 : 0;
+            needs = find_block(d.hkeys, d.hvals, mask, pack_key<D>(bx + ox, by + oy, bz + oz)) != NONE;
+        }
+    }
+    d.rp_needs_block[i] = needs;
+}
+
+// touch_rigid_particle_blocks (sort.wgsl:38-52)
+template <int D>
+__global__ void k_touch_rigid(DeviceData d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.num_rigid || !d.rp_needs_block[i]) return;
+    int bx, by, bz;
+    uint32_t cell;
+    rigid_block<D>(d, i, bx, by, bz, cell);
+    bool won;
+    const uint32_t slot = claim_block<D>(d, bx, by, bz, won);
+    if (won) publish_block(d, slot, atomicAdd(&d.counters->num_active_blocks, 1u), make_int4(bx, by, bz, 0));
+}
+
+// p2g_cdf (p2g_cdf.wgsl:51-190). The reference sorts the sample points into per-cell linked lists and lets every
+// node GATHER the primitives of the 3^D cells around it. Here every sample point SCATTERS: it projects the 3^D nodes
+// of its stencil onto its own primitive and, where the projection falls inside the primitive, ORs the collider's
+// affinity / sign bits into the node and lowers the node's (distance, closest collider) pair with one 64-bit
+// atomicMin - no lists, no sort of the sample points, and the result does not depend on any order (the reference
+// breaks distance ties by list order; here the smaller collider index wins).
+template <int D>
+__global__ void k_p2g_cdf(DeviceData d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.num_rigid) return;
+    int bx, by, bz;
+    uint32_t cell;
+    rigid_block<D>(d, i, bx, by, bz, cell);
+    const uint32_t mask = d.capacity - 1;
+    // a sample point whose own block is inactive is in no list (sort.wgsl:149-152)
+    uint32_t hid[Dim<D>::NASSOC];
+    hid[0] = find_block(d.hkeys, d.hvals, mask, pack_key<D>(bx, by, bz));
+    if (hid[0] == NONE || hid[0] >= d.capacity) return;
+#pragma unroll
+    for (int o = 1; o < Dim<D>::NASSOC; ++o) {
+        const int ox = o & 1, oy = (o >> 1) & 1, oz = (D == 3) ? (o >> 2) & 1 : 0;
+        hid[o] = find_block(d.hkeys, d.hvals, mask, pack_key<D>(bx + ox, by + oy, bz + oz));
+        if (hid[o] >= d.capacity) hid[o] = NONE;
+    }
+    const float h = d.sim->cell_width;
+    const uint4 ids = d.rp_ids[i];
+    const uint32_t collider = ids.w;
+    const float4 A = d.mv_world[ids.x], Bv = d.mv_world[ids.y];
+    const float4 C = (D == 3) ? d.mv_world[ids.z] : make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int B = Dim<D>::BLOCK, LB = Dim<D>::LOG_BLOCK;
+    const int lx = cell & (B - 1), ly = (cell >> LB) & (B - 1), lz = (D == 3) ? (cell >> (2 * LB)) : 0;
+    for (int n = 0; n < Dim<D>::NBH; ++n) {
+        const int sx = n % 3, sy = (n / 3) % 3, sz = n / 9;
+        const int nx = lx + sx, ny = ly + sy, nz = lz + sz; // node, in cells relative to the own block's origin
+        const int o = (nx >= B) + 2 * (ny >= B) + ((D == 3) ? 4 * (nz >= B) : 0);
+        if (hid[o] == NONE) continue;
+        const uint32_t node = hid[o] * CELLS_PER_BLOCK + (nx & (B - 1)) + (ny & (B - 1)) * B + ((D == 3) ? (nz & (B - 1)) * B * B : 0);
+        const float px = (float)(bx * B + nx) * h, py = (float)(by * B + ny) * h, pz = (float)(bz * B + nz) * h;
+        float distance;
+        bool sign;
+        if (D == 2) {
+            // wgparry Segment::projectLocalPoint, then p2g_cdf.wgsl:143-158
+            const float abx = Bv.x - A.x, aby = Bv.y - A.y, apx = px - A.x, apy = py - A.y;
+            const float ab_ap = abx * apx + aby * apy, sqnab = abx * abx + aby * aby;
+            if (ab_ap <= 0.0f || ab_ap >= sqnab) continue; // projects on an end point
+            const float t = ab_ap / sqnab;
+            const float qx = A.x + abx * t, qy = A.y + aby * t;
+            if ((qx == A.x && qy == A.y) || (qx == Bv.x && qy == Bv.y)) continue;
+            const float dx = px - qx, dy = py - qy;
+            distance = sqrtf(dx * dx + dy * dy);
+            sign = (dx * -aby + dy * abx) < 0.0f;
+        } else {
+            // p2g_cdf.wgsl:160-188: projection on the face interior only
+            const V3 a = v3(A.x, A.y, A.z), b = v3(Bv.x, Bv.y, Bv.z), c = v3(C.x, C.y, C.z), pt = v3(px, py, pz);
+            const V3 ap = pt - a, bp = pt - b, cp = pt - c, ab = b - a, ac = c - a, bc = c - b;
+            const V3 nrm = cross(ab, ac);
+            const float n_length = length(nrm);
+            if (!(n_length != 0.0f && dot(cross(ab, nrm), ap) <= 0.0f && dot(cross(bc, nrm), bp) <= 0.0f &&
+                  dot(cross(ac, nrm), cp) >= 0.0f))
+                continue;
+            const float signed_dist = dot(nrm, ap) / n_length;
+            sign = signed_dist < 0.0f;
+            distance = fabsf(signed_dist);
+        }
+        uint4* cdf = d.node_cdf + node;
+        atomicOr(&cdf->z, (1u << collider) | ((uint32_t)sign << (collider + 16)));
+        atomicMin((unsigned long long*)cdf, ((unsigned long long)__float_as_uint(distance) << 32) | collider);
+        d.block_f0[hid[o]] = 1; // the block holds a coloured node (benign race: everybody stores 1)
+    }
+}
+
 // ---- update_block_particle_count (sort.wgsl:89-99), one bin per cell ---------------------------------
 __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -303,7 +441,7 @@ __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_block_prepare(DeviceData d)
             float pt[3] = {(float)(vid.x * Dim<D>::BLOCK + lx) * h, (float)(vid.y * Dim<D>::BLOCK + ly) * h,
                            (float)(vid.z * Dim<D>::BLOCK + lz) * h};
             NodeCdf c = collide<D>(d.bodies, num_bodies, h, pt);
-            d.node_cdf[b * CELLS_PER_BLOCK + t] = make_uint4(__float_as_uint(c.distance), c.affinities, c.closest_id, 0u);
+            d.node_cdf[b * CELLS_PER_BLOCK + t] = make_uint4(c.closest_id, __float_as_uint(c.distance), c.affinities, 0u);
             const int any = __syncthreads_or(c.affinities != 0u);
             if (t == 0) d.block_f0[b] = any ? 1 : 0;
         }
@@ -395,6 +533,32 @@ void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
     if (c.dim == 2) k_touch<2><<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d, cur);
     else k_touch<3><<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d, cur);
+    ++*c.launch_counter;
+}
+void launch_transform_rigid(const LaunchCfg& c, const DeviceData& d) {
+    const uint32_t n = d.num_rigid + d.num_mesh_verts;
+    if (n == 0) return;
+    if (c.dim == 2) k_transform_rigid<2><<<div_up(n, 256), 256, 0, c.stream>>>(d);
+    else k_transform_rigid<3><<<div_up(n, 256), 256, 0, c.stream>>>(d);
+    ++*c.launch_counter;
+}
+// mark + touch of the sample points' blocks; must follow launch_touch on the same stream.
+void launch_touch_rigid(const LaunchCfg& c, const DeviceData& d) {
+    if (d.num_rigid == 0) return;
+    if (c.dim == 2) {
+        k_mark_rigid<2><<<div_up(d.num_rigid, 256), 256, 0, c.stream>>>(d);
+        k_touch_rigid<2><<<div_up(d.num_rigid, 256), 256, 0, c.stream>>>(d);
+    } else {
+        k_mark_rigid<3><<<div_up(d.num_rigid, 256), 256, 0, c.stream>>>(d);
+        k_touch_rigid<3><<<div_up(d.num_rigid, 256), 256, 0, c.stream>>>(d);
+    }
+    *c.launch_counter += 2;
+}
+// Must follow launch_block_prepare (collide() initialises the node cdf) on the same stream.
+void launch_p2g_cdf(const LaunchCfg& c, const DeviceData& d) {
+    if (d.num_rigid == 0) return;
+    if (c.dim == 2) k_p2g_cdf<2><<<div_up(d.num_rigid, 128), 128, 0, c.stream>>>(d);
+    else k_p2g_cdf<3><<<div_up(d.num_rigid, 128), 128, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
 void launch_count(const LaunchCfg& c, const DeviceData& d) {

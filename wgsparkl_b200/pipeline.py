@@ -58,6 +58,7 @@ EXPORTS = (
     "b200mpm_read_grid",
     "b200mpm_read_sorted_ids",
     "b200mpm_data_status",
+    "b200mpm_data_set_rigid_particles",
     "b200mpm_prep_vertex_buffer",
     "b200mpm_data_reserve_grid",
     "b200mpm_data_set_auto_grow",
@@ -124,6 +125,7 @@ def load_library():
         getattr(L, name).argtypes = [vp, vp, sz]
     L.b200mpm_read_positions.argtypes = [vp, vp]
     L.b200mpm_data_reserve_grid.argtypes = [vp, ctypes.c_uint32]
+    L.b200mpm_data_set_rigid_particles.argtypes = [vp, vp, vp, sz, vp, vp, sz]
     L.b200mpm_prep_vertex_buffer.argtypes = [vp, vp, vp, ctypes.c_uint32]
     L.b200mpm_data_set_auto_grow.argtypes = [vp, ctypes.c_float]
     L.b200mpm_read_positions_async.argtypes = [vp, vp]
@@ -334,6 +336,15 @@ class MpmData:
         out = np.zeros(self.num_particles, dtype=abi.particle_dtype)
         _check(load_library().b200mpm_read_particles(self._h, abi.ptr(out)))
         return out
+
+    def set_rigid_particles(self, vertices, vertex_colliders, samples, ids):
+        """GpuRigidParticles::from_rapier: the sample points of the mesh colliders
+        (wgsparkl_b200.rapier.rigid_particles_to_abi builds the four arrays). Once, before stepping."""
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+        vc = np.ascontiguousarray(vertex_colliders, dtype=np.uint32)
+        sp = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1, 3)
+        ii = np.ascontiguousarray(ids, dtype=np.uint32).reshape(-1, 4)
+        _check(load_library().b200mpm_data_set_rigid_particles(self._h, abi.ptr(v), abi.ptr(vc), len(v), abi.ptr(sp), abi.ptr(ii), len(sp)))
 
     def reserve_grid(self, grid_capacity: int):
         """Grow the block capacity (the reference's stubbed resize, grid.rs:43-118)."""

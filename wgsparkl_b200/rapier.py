@@ -95,6 +95,8 @@ class Collider:
     radius: float
     density: float = 1.0
     parent: Optional[int] = None
+    vertices: Optional[np.ndarray] = None  # trimesh / polyline colliders: (nv, dim) local vertices
+    indices: Optional[np.ndarray] = None  # (nt, 3) triangles / (ns, 2) segments
 
 
 class ColliderBuilder:
@@ -116,6 +118,25 @@ class ColliderBuilder:
         return ColliderBuilder(
             Collider(abi.SHAPE_CAPSULE, np.array([0.0, -half_height, 0.0]), np.array([0.0, half_height, 0.0]), float(radius))
         )
+
+    @staticmethod
+    def trimesh(vertices, indices):
+        """3D triangle mesh (massless here: use it on fixed / kinematic bodies, like the reference's examples)."""
+        c = Collider(abi.SHAPE_TRIMESH, np.zeros(3), np.zeros(3), 0.0, density=0.0)
+        c.vertices = np.asarray(vertices, dtype=np.float32).reshape(-1, 3)
+        c.indices = np.asarray(indices, dtype=np.uint32).reshape(-1, 3)
+        return ColliderBuilder(c)
+
+    @staticmethod
+    def polyline(vertices, indices=None):
+        """2D polyline; indices default to consecutive vertices."""
+        c = Collider(abi.SHAPE_POLYLINE, np.zeros(3), np.zeros(3), 0.0, density=0.0)
+        c.vertices = np.asarray(vertices, dtype=np.float32).reshape(-1, 2)
+        if indices is None:
+            n = len(c.vertices)
+            indices = np.stack([np.arange(n - 1), np.arange(1, n)], axis=1)
+        c.indices = np.asarray(indices, dtype=np.uint32).reshape(-1, 2)
+        return ColliderBuilder(c)
 
     def density(self, d):
         self._c.density = float(d)
@@ -172,6 +193,9 @@ class ColliderSet:
 def _mass_properties(co: Collider, dim: int):
     """(mass, local_com, local inertia tensor) of a collider, as parry computes them."""
     rho = co.density
+    if co.shape_type in (abi.SHAPE_TRIMESH, abi.SHAPE_POLYLINE):
+        # parry gives a surface mesh zero mass; the reference only hangs meshes on fixed / kinematic bodies
+        return 0.0, np.zeros(3), np.eye(3 if dim == 3 else 1)
     if co.shape_type == abi.SHAPE_CUBOID:
         he = co.shape_a
         if dim == 3:
@@ -248,3 +272,126 @@ def bodies_to_abi(bodies: RigidBodySet, colliders: ColliderSet, dim: int, coupli
         o["local_com"] = com.astype(f32)
         o["two_ways"] = 1 if two_ways else 0
     return out
+
+
+# ---- rigid particles: sample points of mesh colliders (GpuRigidParticles::from_rapier) -------------------------
+_EPS = np.float32(1.0e-5)  # particle3d.rs:241
+
+
+def sample_edge(a, b, xy_spacing, triangle_id, out):
+    """particle3d.rs:300-320: points strictly after `a`, spacing / sqrt(2) apart."""
+    a, b = a.astype(f32), b.astype(f32)
+    ab = b - a
+    edge_length = f32(np.linalg.norm(ab))
+    if edge_length > _EPS:
+        edge_dir = ab / edge_length
+        spacing = f32(xy_spacing) / f32(np.sqrt(f32(2.0)))
+        nsteps = int(np.ceil(edge_length / spacing))
+        for i in range(1, nsteps):
+            out.append((a + edge_dir * (spacing * f32(i)), triangle_id))
+
+
+def sample_triangle(a, b, c, xy_spacing, triangle_id, out):
+    """particle3d.rs:336-428: a grid oriented along the longest edge (base) and the height of the triangle."""
+    a, b, c = a.astype(f32), b.astype(f32), c.astype(f32)
+    d_ab, d_bc, d_ca = f32(np.linalg.norm(b - a)), f32(np.linalg.norm(c - b)), f32(np.linalg.norm(a - c))
+    mx = max(d_ab, d_bc, d_ca)
+    if mx == d_bc:
+        a, b, c = b, c, a
+    elif mx == d_ca:
+        a, b, c = c, a, b
+    ac = c - a
+    base = b - a
+    base_length = f32(np.linalg.norm(base))
+    if not base_length > 0:
+        return
+    base_dir = base / base_length
+    spacing = f32(xy_spacing) / f32(np.sqrt(f32(2.0)))
+    base_step_count = np.ceil(base_length / spacing)
+    base_step = base_dir * spacing
+    ac_offset_length = f32(ac.dot(base_dir))
+    bc_offset_length = base_length - ac_offset_length
+    if ac_offset_length < _EPS or bc_offset_length < _EPS or base_length < _EPS:
+        return
+    height = ac - base_dir * ac_offset_length
+    height_length = f32(np.linalg.norm(height))
+    height_dir = height / height_length
+    tan_alpha = height_length / ac_offset_length
+    tan_beta = height_length / bc_offset_length
+    for i in range(1, int(base_step_count)):
+        base_position = a + f32(i) * base_step
+        height_ac = tan_alpha * f32(np.linalg.norm(base_position - a))
+        height_bc = tan_beta * f32(np.linalg.norm(base_position - b))
+        hl = min(height_ac, height_bc)
+        height_step_count = np.ceil(hl / spacing)
+        height_step = height_dir * spacing
+        for j in range(1, int(height_step_count)):
+            p = base_position + f32(j) * height_step
+            if np.all(np.isfinite(p)):
+                out.append((p.astype(f32), triangle_id))
+
+
+def sample_mesh(vertices, indices, xy_spacing):
+    """particle3d.rs:251-292: every triangle's interior, and every edge once."""
+    out, visited = [], set()
+    for tri_id, idx in enumerate(indices):
+        va, vb, vc = (vertices[int(idx[k])] for k in range(3))
+        sample_triangle(va, vb, vc, xy_spacing, tri_id, out)
+        for ia, ib in ((idx[0], idx[1]), (idx[1], idx[2]), (idx[2], idx[0])):
+            key = (max(int(ia), int(ib)), min(int(ia), int(ib)))
+            if key not in visited:
+                visited.add(key)
+                sample_edge(vertices[int(ia)], vertices[int(ib)], xy_spacing, tri_id, out)
+    return out
+
+
+def sample_polyline(vertices, indices, sampling_step):
+    """particle2d.rs:206-234 (the end points and the i = 0 sample are duplicated, as in the reference)."""
+    out = []
+    for seg_id, idx in enumerate(indices):
+        a, b = vertices[int(idx[0])].astype(f32), vertices[int(idx[1])].astype(f32)
+        out.append((a, seg_id))
+        ab = b - a
+        length = f32(np.linalg.norm(ab))
+        if length > 0:  # parry: direction() is None for a degenerate segment
+            d = ab / length
+            i = 0
+            while True:
+                shift = f32(i) * f32(sampling_step)
+                if shift > length:
+                    break
+                out.append((a + d * shift, seg_id))
+                i += 1
+            out.append((b, seg_id))
+    return out
+
+
+def rigid_particles_to_abi(bodies: RigidBodySet, colliders: ColliderSet, dim: int, cell_width: float, coupling=None):
+    """GpuRigidParticles::from_rapier (particle3d.rs:101-160, particle2d.rs:80-140) with the reference's sampling step
+    (= cell_width, pipeline.rs:140): (vertices (nv,3) f32 local, vertex_colliders (nv,) u32, samples (ns,3) f32 local,
+    ids (ns,4) u32 = vertex ids of the primitive + collider index). Collider index = position in the coupling list."""
+    if coupling is None:
+        coupling = [(co.parent, h, True) for h, co in colliders if co.parent is not None]
+    verts, vcol, samples, ids = [], [], [], []
+    for collider_id, (_, ch, _) in enumerate(coupling):
+        co = colliders[ch]
+        if co.vertices is None:
+            continue
+        base_vid = len(verts)
+        for v in co.vertices:
+            vv = np.zeros(3, dtype=f32)
+            vv[:dim] = v[:dim]
+            verts.append(vv)
+            vcol.append(collider_id)
+        if dim == 3:
+            pts = sample_mesh(co.vertices, co.indices, cell_width)
+        else:
+            pts = sample_polyline(co.vertices, co.indices, cell_width)
+        for p, prim in pts:
+            pp = np.zeros(3, dtype=f32)
+            pp[:dim] = p[:dim]
+            samples.append(pp)
+            idx = co.indices[prim]
+            ids.append([base_vid + int(idx[0]), base_vid + int(idx[1]), base_vid + int(idx[2]) if dim == 3 else 0, collider_id])
+    return (np.array(verts, dtype=f32).reshape(-1, 3), np.array(vcol, dtype=np.uint32),
+            np.array(samples, dtype=f32).reshape(-1, 3), np.array(ids, dtype=np.uint32).reshape(-1, 4))

@@ -10,6 +10,7 @@ import numpy as np
 
 from . import abi
 from .models import DruckerPrager, ElasticCoefficients
+from .rapier import rigid_particles_to_abi  # noqa: F401  (re-exported for scene users)
 from .rapier import ColliderBuilder, ColliderSet, RigidBodyBuilder, RigidBodySet, bodies_to_abi
 from .solver import F32_MAX, ParticlePhase, SimulationParams, make_particles
 
@@ -147,3 +148,43 @@ def sand_dam_3d(nx=400, ny=200, nz=200, jitter=True, seed=SEED, grid_capacity=26
                 params=SimulationParams([0.0, -9.81, 0.0], (1.0 / 60.0) / 20.0), particles=parts,
                 bodies=bodies_to_abi(bodies, colliders, 3), cell_width=h, grid_capacity=grid_capacity,
                 substeps_per_frame=20)
+
+
+def box_trimesh(half_extents):
+    """Closed, outward-oriented triangle mesh of an axis-aligned box (12 triangles)."""
+    x, y, z = half_extents
+    v = np.array([[-x, -y, -z], [x, -y, -z], [x, y, -z], [-x, y, -z], [-x, -y, z], [x, -y, z], [x, y, z], [-x, y, z]], dtype=np.float32)
+    f = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [2, 3, 7], [2, 7, 6], [1, 2, 6], [1, 6, 5],
+                  [0, 4, 7], [0, 7, 3]], dtype=np.uint32)
+    return v, f
+
+
+def elastic_cube_on_trimesh_3d(n_side=12, tilt=0.15, moving=True):
+    """an elastic cube dropped on TRIANGLE-MESH colliders (the elastic_cut3 / heightfield3 pattern):
+    a tilted fixed slab as ground and a kinematic, slowly turning bar cutting into the cube. The meshes are placed off
+    the grid lines so that no node sits exactly on a triangle edge. Returns the scene with `rigid_particles`."""
+    s = elastic_cube_3d(n_side, y_offset=-5.0, ground=False)
+    bodies, colliders = RigidBodySet(), ColliderSet()
+    rb = bodies.insert(RigidBodyBuilder.fixed().translation([0.137, -4.163, -0.071]).rotation([tilt, 0.0, 0.6 * tilt]))
+    colliders.insert_with_parent(ColliderBuilder.trimesh(*box_trimesh((9.3, 1.1, 9.7))), rb, bodies)
+    top = (n_side - 5.0) * 0.5
+    rb = bodies.insert(RigidBodyBuilder.kinematic_velocity_based().translation([0.21, top + 0.35, 0.13]).rotation([0.0, 0.3, 0.2])
+                       .linvel([0.0, -3.0 if moving else 0.0, 0.0]).angvel([0.0, 1.5 if moving else 0.0, 0.0]))
+    colliders.insert_with_parent(ColliderBuilder.trimesh(*box_trimesh((0.45, 0.6, 4.3))), rb, bodies)
+    s["bodies"] = bodies_to_abi(bodies, colliders, 3)
+    s["rigid_particles"] = rigid_particles_to_abi(bodies, colliders, 3, s["cell_width"])
+    s["name"] = "3d_elastic_cube_on_trimesh_%d" % len(s["particles"])
+    return s
+
+
+def elastic_block_on_polyline_2d(n_side=24):
+    """2D counterpart: an elastic block on a polyline ground with a kink (the elastic_cut2 pattern)."""
+    s = elastic_block_2d(n_side)
+    s["particles"]["position"][:, 1] -= 9.9
+    bodies, colliders = RigidBodySet(), ColliderSet()
+    rb = bodies.insert(RigidBodyBuilder.fixed().translation([0.013, -0.237]))
+    colliders.insert_with_parent(ColliderBuilder.polyline([[-30.0, 0.9], [-4.1, 0.23], [3.7, 0.31], [30.0, 1.4]]), rb, bodies)
+    s["bodies"] = bodies_to_abi(bodies, colliders, 2)
+    s["rigid_particles"] = rigid_particles_to_abi(bodies, colliders, 2, s["cell_width"])
+    s["name"] = "2d_elastic_block_on_polyline_%d" % len(s["particles"])
+    return s
