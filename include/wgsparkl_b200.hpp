@@ -252,6 +252,13 @@ public:
         return out;
     }
     void read_positions_async(float* out_pinned) { check(b200mpm_read_positions_async(h_, out_pinned)); }
+    // GpuRigidParticles::from_rapier (particle3d.rs:101-160): sample points of the trimesh / polyline colliders,
+    // local frames; ids = (vertex a, b, c, collider index) per sample point. Once, before stepping.
+    void set_rigid_particles(const std::vector<float>& vertices, const std::vector<uint32_t>& vertex_colliders,
+                             const std::vector<float>& samples, const std::vector<uint32_t>& sample_ids) {
+        check(b200mpm_data_set_rigid_particles(h_, vertices.data(), vertex_colliders.data(), vertex_colliders.size(),
+                                               samples.data(), sample_ids.data(), sample_ids.size() / 4));
+    }
     // The resize the reference leaves as a stub (grid.rs:43-118).
     void reserve_grid(uint32_t grid_capacity) { check(b200mpm_data_reserve_grid(h_, grid_capacity)); }
     void set_auto_grow(float max_load) { check(b200mpm_data_set_auto_grow(h_, max_load)); }

@@ -115,7 +115,12 @@ fn flatten_body(bodies: &RigidBodySet, colliders: &ColliderSet, c: &BodyCoupling
             o.shape_b[..cap.segment.b.coords.len()].copy_from_slice(cap.segment.b.coords.as_slice());
             o.radius = cap.radius;
         }
-        other => panic!("collider shape {:?} is not on the B200 path yet (SURVEY §8f row 1)", other),
+        // Mesh colliders have no analytic projection: they act through their sample points (rigid_particles()).
+        #[cfg(feature = "dim3")]
+        ShapeType::TriMesh | ShapeType::HeightField => o.shape_type = 3,
+        #[cfg(feature = "dim2")]
+        ShapeType::Polyline => o.shape_type = 4,
+        other => panic!("collider shape {:?} is not on the B200 path", other),
     }
     let pos = co.position();
     o.translation[..pos.translation.vector.len()].copy_from_slice(pos.translation.vector.as_slice());
@@ -207,6 +212,24 @@ impl MpmData {
                 &mut raw,
             )
         })?;
+        // GpuRigidParticles::from_rapier (src/solver/particle3d.rs:101-160 / particle2d.rs:80-140): the crate's own
+        // CPU sampling (sample_mesh / sample_polyline with sampling_step = cell_width, pipeline.rs:140) stays as it
+        // is; only its output is flattened - vertices + collider index per vertex, sample points + (primitive
+        // vertex ids, collider index) per sample.
+        let rp = crate::solver::sample_rigid_particles(colliders, &coupling, cell_width);
+        if !rp.samples.is_empty() {
+            check(unsafe {
+                sys::b200mpm_data_set_rigid_particles(
+                    raw,
+                    rp.vertices.as_ptr() as *const f32,
+                    rp.vertex_colliders.as_ptr(),
+                    rp.vertex_colliders.len(),
+                    rp.samples.as_ptr() as *const f32,
+                    rp.sample_ids.as_ptr() as *const u32,
+                    rp.sample_ids.len(),
+                )
+            })?;
+        }
         Ok(Self { raw, coupling })
     }
 
