@@ -97,3 +97,26 @@ def test_async_unordered_readback_of_a_slab():
         sh.pipe.sync()
         assert n == len(ref) and np.array_equal(out[:n], ref)
     grp.close()
+
+
+def test_sharded_with_mesh_colliders():
+    """Mesh colliders in a sharded run: the sample points are replicated on every slab (each applies them to the
+    blocks it holds), so two slabs must reproduce the single-GPU run on trimesh colliders."""
+    scene = scenes.elastic_cube_on_trimesh_3d(12)
+    scene["particles"]["velocity"][:, 0] = 4.0
+    n = 40
+    pipe = MpmPipeline(0, 3)
+    data = MpmData(pipe, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    data.set_rigid_particles(*scene["rigid_particles"])
+    pipe.queue_step(data, n)
+    ref = data.read_particles()
+    data.close()
+    pipe.close()
+    grp = LocalSlabs(scene, 2)
+    grp.step(n)
+    got = grp.gather_particles()
+    assert (ref["cdf_affinity"] != 0).sum() > 50
+    assert parity.field_rel_err(got["position"], ref["position"]) <= 1e-5
+    assert parity.field_rel_err(got["velocity"], ref["velocity"]) <= 2e-3
+    assert np.mean(got["cdf_affinity"] == ref["cdf_affinity"]) > 0.995
+    grp.close()

@@ -97,6 +97,9 @@ class ShardedMpm:
         cap = int(n_mine * slack) + 4 * migration_cap
         self.data = MpmData(self.pipe, scene["params"], parts[mine], scene["bodies"], scene["cell_width"], scene["grid_capacity"],
                             particle_ids=ids, particle_capacity=cap)
+        if scene.get("rigid_particles") is not None:
+            # mesh colliders are replicated: every slab holds all sample points and applies them to its own blocks
+            self.data.set_rigid_particles(*scene["rigid_particles"])
         if world > 1:
             self.data.slab_configure(lo, hi)
         self.n_global = len(parts)
