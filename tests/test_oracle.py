@@ -255,3 +255,29 @@ def test_trimesh_box_agrees_with_analytic_cuboid(oracle_mod):
         assert np.allclose(na["cdf_distance"][both], nb["cdf_distance"][both], atol=1e-5)
         assert np.array_equal(na["cdf_affinities"][both], nb["cdf_affinities"][both])
     assert n_both > 300
+
+
+def test_heightfield_collider_holds_sand(oracle_mod):
+    """heightfield3-style scene: sand dropped on a heightfield (converted to a trimesh on the host, as
+    particle3d.rs:123-132 does) comes to rest ON it: no particle ends up below the surface."""
+    from wgsparkl_b200.rapier import ColliderBuilder, ColliderSet, RigidBodyBuilder, RigidBodySet, bodies_to_abi, rigid_particles_to_abi
+
+    scene = scenes.sand_column_3d(8, 8, 8, y_offset=2.0)
+    n = 9
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    heights = 0.25 * np.sin(0.9 * ii) * np.cos(0.7 * jj)
+    bodies, colliders = RigidBodySet(), ColliderSet()
+    rb = bodies.insert(RigidBodyBuilder.fixed().translation([0.03, 0.41, -0.02]))
+    colliders.insert_with_parent(ColliderBuilder.heightfield(heights, (16.0, 1.0, 16.0)), rb, bodies)
+    scene["bodies"] = bodies_to_abi(bodies, colliders, 3)
+    rp = rigid_particles_to_abi(bodies, colliders, 3, scene["cell_width"])
+    assert len(rp[2]) > 500 and len(rp[0]) == n * n
+    sim = oracle_mod.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    sim.set_rigid_particles(*rp)
+    sim.step(400)
+    p = sim.read_particles()
+    sim.close()
+    assert np.all(np.isfinite(p["position"]))
+    assert (p["cdf_affinity"] != 0).sum() > 30, "the bottom layer must feel the heightfield"
+    assert p["position"][:, 1].min() > 0.41 - 0.25 - 0.3, "no particle falls through the surface"
+    assert np.abs(p["velocity"][:, 1]).mean() < 2.0, "the pile is held (free fall would be ~3.3 by now)"

@@ -128,6 +128,26 @@ class ColliderBuilder:
         return ColliderBuilder(c)
 
     @staticmethod
+    def heightfield(heights, scale):
+        """3D heightfield, handed to the MPM side as the triangle mesh parry's `HeightField::to_trimesh` yields
+        (particle3d.rs:123-132): heights[i, j] over a regular (rows along z, columns along x) grid centred on the
+        origin and spanning scale.x by scale.z, heights multiplied by scale.y; two triangles per cell."""
+        hgt = np.asarray(heights, dtype=np.float32)
+        nrows, ncols = hgt.shape
+        sx, sy, sz = (float(v) for v in scale)
+        xs = (np.arange(ncols, dtype=np.float32) / np.float32(ncols - 1) - np.float32(0.5)) * np.float32(sx)
+        zs = (np.arange(nrows, dtype=np.float32) / np.float32(nrows - 1) - np.float32(0.5)) * np.float32(sz)
+        verts = np.stack([np.tile(xs, nrows), (hgt * np.float32(sy)).ravel(), np.repeat(zs, ncols)], axis=1).astype(np.float32)
+        tris = []
+        for i in range(nrows - 1):
+            for j in range(ncols - 1):
+                a, b = i * ncols + j, i * ncols + j + 1
+                c, d = (i + 1) * ncols + j, (i + 1) * ncols + j + 1
+                tris.append([a, c, b])  # normals point towards +y
+                tris.append([b, c, d])
+        return ColliderBuilder.trimesh(verts, np.array(tris, dtype=np.uint32))
+
+    @staticmethod
     def polyline(vertices, indices=None):
         """2D polyline; indices default to consecutive vertices."""
         c = Collider(abi.SHAPE_POLYLINE, np.zeros(3), np.zeros(3), 0.0, density=0.0)
