@@ -38,7 +38,12 @@ def _coupled3d():
     return s
 
 
-CASES = {"elastic3d": (_elastic3d, 25), "sand3d": (_sand3d, 25), "elastic2d": (_elastic2d, 25), "coupled3d": (_coupled3d, 15)}
+def _trimesh3d():
+    return scenes.elastic_cube_on_trimesh_3d(10)  # mesh colliders: scene carries "rigid_particles"
+
+
+CASES = {"elastic3d": (_elastic3d, 25), "sand3d": (_sand3d, 25), "elastic2d": (_elastic2d, 25), "coupled3d": (_coupled3d, 15),
+         "trimesh3d": (_trimesh3d, 25)}
 
 
 def canonical_blocks(blocks):
@@ -49,6 +54,8 @@ def canonical_blocks(blocks):
 def run_case(oracle_mod, make_scene, substeps):
     s = make_scene()
     sim = oracle_mod.OracleSim(s["dim"], s["params"], s["particles"], s["bodies"], s["cell_width"], s["grid_capacity"])
+    if s.get("rigid_particles") is not None:
+        sim.set_rigid_particles(*s["rigid_particles"])
     sim.step(substeps)
     p = sim.read_particles()
     blocks, _ = sim.read_grid()
@@ -66,7 +73,10 @@ def run_case(oracle_mod, make_scene, substeps):
 if __name__ == "__main__":
     from oracle import oracle
 
+    only = sys.argv[1:]  # e.g. `python tests/golden/make_golden.py trimesh3d` adds one fixture, leaving the others alone
     for name, (mk, n) in CASES.items():
+        if only and name not in only:
+            continue
         out = run_case(oracle, mk, n)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, {k: v.shape for k, v in out.items()})

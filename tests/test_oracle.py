@@ -159,7 +159,7 @@ def test_capacity_overflow_drops_blocks_silently(oracle_mod):
     assert sim.overflowed() and sim.num_active_blocks() == 8
 
 
-@pytest.mark.parametrize("name", ["elastic3d", "sand3d", "elastic2d", "coupled3d"])
+@pytest.mark.parametrize("name", ["elastic3d", "sand3d", "elastic2d", "coupled3d", "trimesh3d"])
 def test_golden_fixtures(oracle_mod, name):
     """The oracle reproduces its committed outputs (tests/golden/make_golden.py): pins it against drift."""
     from golden.make_golden import CASES, run_case
