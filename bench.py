@@ -39,8 +39,8 @@ BYTES_P2G = 66.0
 BYTES_G2P_ELASTIC = 162.0
 BYTES_G2P_SAND = 218.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_g2p launch on the 1M-particle cube, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_full_1M_cube.md: 77.58 MB read + 62.32 MB written).
-G2P_NCU_TRAFFIC_BYTES = 139.90e6
+# `ncu --set full` capture (profiles/r01_ncu_full_1M_cube.md: 77.77 MB read + 59.39 MB written).
+G2P_NCU_TRAFFIC_BYTES = 137.16e6
 G2P_NCU_TRAFFIC_PARTICLES = 1_000_000
 
 
