@@ -224,7 +224,9 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
 }
 
 // Enqueues one substep. With `side` the independent kernels are forked onto a second stream:
-//   touch -> { block_prepare  ||  count -> scan } -> scatter -> { g2p_cdf -> p2g(cpic)  ||  p2g } -> g2p
+//   begin [-> transform_rigid] -> touch [-> mark_rigid -> touch_rigid]
+//     -> { block_prepare [-> p2g_cdf]  ||  count -> scan } -> scatter -> { g2p_cdf -> p2g(cpic)  ||  p2g } -> g2p -> integrate
+//   ([..]: only with mesh colliders)
 // phase: PHASE_ALL = the whole substep; PHASE_BEGIN = up to and including P2G; PHASE_END = from G2P on
 // (sharded runs exchange the node halo and the body impulses between the two).
 enum { PHASE_ALL = 0, PHASE_BEGIN = 1, PHASE_END = 2, PHASE_SHARDED = 3 };

@@ -7,7 +7,8 @@
 // 176-byte AoS `Dynamics` struct through memory (the velocity gradient is parked in `affine`,
 // SURVEY A.4).
 //
-// B200 design: one CTA per active block.
+// B200 design: one CTA per work item = up to 512 particles of one block (k_scatter's list:
+// blocks without particles never appear, collider-side and densely populated blocks come first).
 //   * the (BLOCK+2)^D node tile is staged in shared memory through the neighbour table; the grid
 //     update is applied while staging, so node velocities never exist in HBM;
 //   * one thread per particle of the block's contiguous sorted range: 16-byte vector loads of the

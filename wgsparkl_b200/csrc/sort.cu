@@ -10,7 +10,8 @@
 // keeps per-node linked lists for that, sort.wgsl:129-135). One histogram + one single-pass
 // decoupled-look-back scan over B*64+1 bins (B is device-resident) replace the reference's
 // capacity-length Blelloch scan; the rank returned by the histogram atomic makes the final
-// scatter atomic-free.
+// scatter atomic-free. The streaming kernels carry 4 particles per thread (memory-level parallelism).
+// Also here: the rigid-particle kernels of mesh colliders (transform, block activation, p2g_cdf as a scatter).
 #include "launch.h"
 
 namespace b2 {
