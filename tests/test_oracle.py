@@ -281,3 +281,150 @@ def test_heightfield_collider_holds_sand(oracle_mod):
     assert (p["cdf_affinity"] != 0).sum() > 30, "the bottom layer must feel the heightfield"
     assert p["position"][:, 1].min() > 0.41 - 0.25 - 0.3, "no particle falls through the surface"
     assert np.abs(p["velocity"][:, 1]).mean() < 2.0, "the pile is held (free fall would be ~3.3 by now)"
+
+
+def _numpy_mls_mpm_substep(pos, vel, F, C, mass, vol0, lam, mu, h, dt, gravity):
+    """An INDEPENDENT float64 statement of one collider-free substep, written from the formulas of SURVEY §8
+    (a1, a8, a9, a10, a13, a15, a16) with dense numpy arrays instead of blocks / tiles / lists: quadratic B-spline
+    weights around the associated cell c = round(x/h) - 1, P2G of (affine dpt + m v, m), grid velocity with gravity
+    and the +-h/dt clamp, G2P of v and grad v = inv_d sum w v_n (x) dpt, advection, F update, corotated Kirchhoff
+    stress from numpy's SVD, new affine = grad v m - tau V0 inv_d dt."""
+    n, d = pos.shape
+    inv_d = 4.0 / (h * h)
+    c = np.rint(pos / h) - 1.0  # ties-to-even, like WGSL round
+    x = (pos - c * h) / h  # in [0.5, 1.5]
+    w = np.stack([0.5 * (1.5 - x) ** 2, 0.75 - (x - 1.0) ** 2, 0.5 * (x - 0.5) ** 2], axis=0)  # [shift][particle][axis]
+    ci = c.astype(np.int64)
+    lo = ci.min(axis=0)
+    dims = ci.max(axis=0) - lo + 3
+    gm = np.zeros(tuple(dims))
+    gp = np.zeros(tuple(dims) + (d,))
+    shifts = [(i, j, k) for i in range(3) for j in range(3) for k in range(3)]
+    for s in shifts:
+        sv = np.array(s)
+        wt = w[s[0], :, 0] * w[s[1], :, 1] * w[s[2], :, 2]
+        dpt = (c + sv) * h - pos
+        contrib = np.einsum("nij,nj->ni", C, dpt) + mass[:, None] * vel
+        idx = tuple((ci + sv - lo).T)
+        np.add.at(gm, idx, wt * mass)
+        np.add.at(gp, idx, wt[:, None] * contrib)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gv = np.where(gm[..., None] > 0, (gp + gm[..., None] * gravity * dt) / gm[..., None], 0.0)
+    gv = np.clip(gv, -h / dt, h / dt)
+    v_new = np.zeros_like(vel)
+    grad = np.zeros((n, d, d))
+    for s in shifts:
+        sv = np.array(s)
+        wt = w[s[0], :, 0] * w[s[1], :, 1] * w[s[2], :, 2]
+        dpt = (c + sv) * h - pos
+        vn = gv[tuple((ci + sv - lo).T)]
+        v_new += wt[:, None] * vn
+        grad += (wt * inv_d)[:, None, None] * np.einsum("ni,nj->nij", vn, dpt)
+    speed = np.linalg.norm(v_new, axis=1)
+    v_new = np.where((speed > h / dt)[:, None], v_new / np.maximum(speed, 1e-300)[:, None] * h / dt, v_new)
+    pos_new = pos + v_new * dt
+    F_new = F + np.einsum("nij,njk->nik", grad * dt, F)
+    U, S, Vt = np.linalg.svd(F_new)
+    J = np.linalg.det(F_new)
+    R = np.einsum("nij,njk->nik", U, Vt)
+    tau = 2.0 * mu[:, None, None] * np.einsum("nij,nkj->nik", F_new - R, F_new) + (lam * (J - 1.0) * J)[:, None, None] * np.eye(d)
+    C_new = grad * mass[:, None, None] - tau * (vol0 * inv_d * dt)[:, None, None]
+    return pos_new, v_new, F_new, C_new
+
+
+def test_oracle_against_independent_numpy_mpm(oracle_mod):
+    """The C++ oracle (blocks, hash map, tiles, linked lists, f32) against a dense float64 numpy statement of the same
+    physics, 5 substeps of a falling, spinning, pre-strained elastic cube without colliders: two independent
+    transcriptions of the reference's formulas must agree to f32 accuracy."""
+    scene = scenes.elastic_cube_3d(8, y_offset=3.0, ground=False)
+    p = scene["particles"]
+    rng = np.random.default_rng(9)
+    ctr = p["position"].mean(axis=0)
+    p["velocity"][:, 0] = -3.0 * (p["position"][:, 2] - ctr[2]) + 1.0
+    p["velocity"][:, 2] = 3.0 * (p["position"][:, 0] - ctr[0])
+    p["velocity"][:, 1] = -2.0
+    p["def_grad"][:, :9] += rng.normal(0.0, 0.01, size=(len(p), 9)).astype(np.float32)
+    sim = oracle_mod.OracleSim(3, scene["params"], p, scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    h, dt = float(scene["cell_width"]), float(scene["params"].dt)
+    g = np.array(scene["params"].gravity, dtype=np.float64)
+    pos, vel = p["position"].astype(np.float64), p["velocity"].astype(np.float64)
+    F = p["def_grad"].astype(np.float64).reshape(-1, 3, 3).transpose(0, 2, 1)  # column-major storage -> [row][col]
+    C = p["affine"].astype(np.float64).reshape(-1, 3, 3).transpose(0, 2, 1)
+    for step in range(5):
+        pos, vel, F, C = _numpy_mls_mpm_substep(pos, vel, F, C, p["mass"].astype(np.float64), p["init_volume"].astype(np.float64),
+                                                p["lambda"].astype(np.float64), p["mu"].astype(np.float64), h, dt, g)
+        sim.step(1)
+        o = sim.read_particles()
+        oF = o["def_grad"].astype(np.float64).reshape(-1, 3, 3).transpose(0, 2, 1)
+        assert np.abs(o["position"] - pos).max() <= 2e-6 * np.abs(pos).max(), step
+        assert np.abs(o["velocity"] - vel).max() <= 2e-5 * np.abs(vel).max(), step
+        assert np.abs(oF - F).max() <= 1e-5, step
+    sim.close()
+
+
+def test_oracle_sand_against_independent_numpy_mpm(oracle_mod):
+    """Same cross-check with the Drucker-Prager return mapping (drucker_prager.wgsl:112-158) in the loop: a loose
+    sand block (E = 1e6 so that f32 rounding of the singular values stays small) sheared and dropped."""
+    from wgsparkl_b200.models import ElasticCoefficients
+
+    scene = scenes.sand_column_3d(8, 8, 8, y_offset=6.0)
+    scene["bodies"] = scene["bodies"][:0]
+    p = scene["particles"]
+    el = ElasticCoefficients.from_young_modulus(1.0e6, 0.2)
+    for f in ("lambda", "dp_lambda"):
+        p[f] = el.lambda_
+    for f in ("mu", "dp_mu"):
+        p[f] = el.mu
+    ctr = p["position"].mean(axis=0)
+    p["velocity"][:, 0] = 6.0 * (p["position"][:, 1] - ctr[1])  # shear: yields
+    p["velocity"][:, 1] = -1.0
+    sim = oracle_mod.OracleSim(3, scene["params"], p, scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    h, dt = float(scene["cell_width"]), float(scene["params"].dt)
+    g = np.array(scene["params"].gravity, dtype=np.float64)
+    f64 = lambda name: p[name].astype(np.float64)  # noqa: E731
+    pos, vel = f64("position"), f64("velocity")
+    F = f64("def_grad").reshape(-1, 3, 3).transpose(0, 2, 1)
+    C = f64("affine").reshape(-1, 3, 3).transpose(0, 2, 1)
+    mass, vol0, lam, mu = f64("mass"), f64("init_volume"), f64("lambda"), f64("mu")
+    h0, h1, h2, h3 = f64("dp_h0"), f64("dp_h1"), f64("dp_h2"), f64("dp_h3")
+    q, lvg = f64("plastic_hardening"), f64("plastic_log_vol_gain")
+    projected_any = 0
+    for step in range(8):
+        # gather / scatter / F update exactly as in the elastic statement, then project F and redo the stress
+        pos, vel, Ftrial, _ = _numpy_mls_mpm_substep(pos, vel, F, C, mass, vol0, lam, mu, h, dt, g)
+        # grad v * dt = (Ftrial - F) F^-1  (F update: Ftrial = F + dt grad F)
+        gradv = np.einsum("nij,njk->nik", Ftrial - F, np.linalg.inv(F)) / dt
+        U, S, Vt = np.linalg.svd(Ftrial)
+        angle = h0 + (h1 * q - h3) * np.exp(-h2 * q)
+        alpha = np.sqrt(2.0 / 3.0) * 2.0 * np.sin(angle) / (3.0 - np.sin(angle))
+        eps = np.log(S) + (lvg / 3.0)[:, None]
+        tr = eps.sum(axis=1)
+        dev = eps - (tr / 3.0)[:, None]
+        devn = np.linalg.norm(dev, axis=1)
+        tension = (tr > 0.0) | (devn == 0.0)
+        gamma = devn + (3.0 * lam + 2.0 * mu) / (2.0 * mu) * tr * alpha
+        yielding = (~tension) & (gamma > 0.0)
+        S_new = S.copy()
+        S_new[tension] = 1.0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            S_y = np.exp(eps - dev * (gamma / devn)[:, None])
+        S_new[yielding] = S_y[yielding]
+        changed = tension | yielding
+        q = q + np.where(tension, np.linalg.norm(eps, axis=1), np.where(yielding, gamma, 0.0))
+        lvg = lvg + np.where(changed, np.log(S.prod(axis=1)) - np.log(S_new.prod(axis=1)), 0.0)
+        projected_any += int(yielding.sum())
+        F = np.einsum("nij,nj,njk->nik", U, S_new, Vt)
+        Un, Sn, Vtn = np.linalg.svd(F)
+        R = np.einsum("nij,njk->nik", Un, Vtn)
+        J = np.linalg.det(F)
+        tau = 2.0 * mu[:, None, None] * np.einsum("nij,nkj->nik", F - R, F) + (lam * (J - 1.0) * J)[:, None, None] * np.eye(3)
+        C = gradv * mass[:, None, None] - tau * (vol0 * (4.0 / (h * h)) * dt)[:, None, None]
+        sim.step(1)
+        o = sim.read_particles()
+        oF = o["def_grad"].astype(np.float64).reshape(-1, 3, 3).transpose(0, 2, 1)
+        assert np.abs(o["position"] - pos).max() <= 2e-6 * np.abs(pos).max(), step
+        assert np.abs(o["velocity"] - vel).max() <= 2e-4 * np.abs(vel).max(), step
+        assert np.abs(oF - F).max() <= 2e-5, step
+        assert np.abs(o["plastic_hardening"] - q).max() <= 1e-4 * max(1.0, np.abs(q).max()), step
+    assert projected_any > 100, "the shear must drive particles onto the yield surface"
+    sim.close()
