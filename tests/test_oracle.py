@@ -428,3 +428,44 @@ def test_oracle_sand_against_independent_numpy_mpm(oracle_mod):
         assert np.abs(o["plastic_hardening"] - q).max() <= 1e-4 * max(1.0, np.abs(q).max()), step
     assert projected_any > 100, "the shear must drive particles onto the yield surface"
     sim.close()
+
+
+def test_cpic_reconstruction_recovers_plane_and_sphere(oracle_mod):
+    """g2p_cdf (g2p_cdf.wgsl:124-250) reconstructs, per particle, the collider's signed distance and normal by an
+    MLS fit through the coloured nodes. For a flat cuboid face and for a ball the exact answers are known."""
+    from wgsparkl_b200.rapier import ColliderBuilder, ColliderSet, RigidBodyBuilder, RigidBodySet, bodies_to_abi
+
+    # plane: ground cuboid with its top face at y = -3.2, particles from y = -2.25 upwards
+    scene = scenes.elastic_cube_3d(10, y_offset=-5.0)
+    scene["bodies"]["translation"][0, 1] = -4.2
+    sim = oracle_mod.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    for st in range(5):
+        sim.stage(st)
+    o = sim.read_particles()
+    sim.close()
+    near = o["cdf_affinity"] != 0
+    assert near.sum() > 150
+    assert np.all(o["cdf_normal"][near][:, 1] > 0.9999)
+    assert np.abs(o["cdf_signed_distance"][near] - (o["position"][near][:, 1] + 3.2)).max() < 1e-3
+    # ball of radius 2.3 below the block: normals are radial, distances are |x - c| - r
+    scene = scenes.elastic_cube_3d(10, y_offset=-5.0, ground=False)
+    bodies, colliders = RigidBodySet(), ColliderSet()
+    centre = np.array([0.13, -4.4, -0.21])
+    rb = bodies.insert(RigidBodyBuilder.fixed().translation(centre))
+    colliders.insert_with_parent(ColliderBuilder.ball(2.3), rb, bodies)
+    scene["bodies"] = bodies_to_abi(bodies, colliders, 3)
+    sim = oracle_mod.OracleSim(3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    for st in range(5):
+        sim.stage(st)
+    o = sim.read_particles()
+    sim.close()
+    near = o["cdf_affinity"] != 0
+    assert near.sum() > 20
+    r = o["position"][near].astype(np.float64) - centre
+    dist = np.linalg.norm(r, axis=1)
+    # a linear fit through samples of a curved distance field (second-order in h / radius), and only the nodes within
+    # 1.5 h of the surface are coloured: judge the particles whose whole stencil is supported, i.e. within one cell
+    close = (dist - 2.3) < 1.0
+    assert close.sum() > 10
+    assert np.abs(o["cdf_signed_distance"][near][close] - (dist[close] - 2.3)).max() < 0.25  # ~ h^2 / (2 r)
+    assert np.all(np.einsum("ni,ni->n", o["cdf_normal"][near][close], (r / dist[:, None])[close]) > 0.97)
