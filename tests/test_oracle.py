@@ -467,5 +467,9 @@ def test_cpic_reconstruction_recovers_plane_and_sphere(oracle_mod):
     # 1.5 h of the surface are coloured: judge the particles whose whole stencil is supported, i.e. within one cell
     close = (dist - 2.3) < 1.0
     assert close.sum() > 10
-    assert np.abs(o["cdf_signed_distance"][near][close] - (dist[close] - 2.3)).max() < 0.25  # ~ h^2 / (2 r)
-    assert np.all(np.einsum("ni,ni->n", o["cdf_normal"][near][close], (r / dist[:, None])[close]) > 0.97)
+    # the field is reconstructed RELATIVE to the particle's own colour (g2p_cdf.wgsl:205-214): a particle that starts
+    # coloured "inside" (sign bit of collider 0; decided by the weighted node signs, g2p_cdf.wgsl:160-188, so it can
+    # differ from the geometric side right at the surface) sees positive distances inside and an inward normal
+    side = np.where((o["cdf_affinity"][near] >> 16) & 1, -1.0, 1.0)
+    assert np.abs(o["cdf_signed_distance"][near][close] - (side * (dist - 2.3))[close]).max() < 0.25  # ~ h^2 / (2 r)
+    assert np.all(side[close] * np.einsum("ni,ni->n", o["cdf_normal"][near][close], (r / dist[:, None])[close]) > 0.97)
