@@ -299,10 +299,17 @@ def _numpy_mls_mpm_substep(pos, vel, F, C, mass, vol0, lam, mu, h, dt, gravity):
     dims = ci.max(axis=0) - lo + 3
     gm = np.zeros(tuple(dims))
     gp = np.zeros(tuple(dims) + (d,))
-    shifts = [(i, j, k) for i in range(3) for j in range(3) for k in range(3)]
+    import itertools
+
+    shifts = list(itertools.product(range(3), repeat=d))
+
+    def weight(s):
+        wt = w[s[0], :, 0] * w[s[1], :, 1]
+        return wt * w[s[2], :, 2] if d == 3 else wt
+
     for s in shifts:
         sv = np.array(s)
-        wt = w[s[0], :, 0] * w[s[1], :, 1] * w[s[2], :, 2]
+        wt = weight(s)
         dpt = (c + sv) * h - pos
         contrib = np.einsum("nij,nj->ni", C, dpt) + mass[:, None] * vel
         idx = tuple((ci + sv - lo).T)
@@ -315,7 +322,7 @@ def _numpy_mls_mpm_substep(pos, vel, F, C, mass, vol0, lam, mu, h, dt, gravity):
     grad = np.zeros((n, d, d))
     for s in shifts:
         sv = np.array(s)
-        wt = w[s[0], :, 0] * w[s[1], :, 1] * w[s[2], :, 2]
+        wt = weight(s)
         dpt = (c + sv) * h - pos
         vn = gv[tuple((ci + sv - lo).T)]
         v_new += wt[:, None] * vn
@@ -473,3 +480,32 @@ def test_cpic_reconstruction_recovers_plane_and_sphere(oracle_mod):
     side = np.where((o["cdf_affinity"][near] >> 16) & 1, -1.0, 1.0)
     assert np.abs(o["cdf_signed_distance"][near][close] - (side * (dist - 2.3))[close]).max() < 0.25  # ~ h^2 / (2 r)
     assert np.all(side[close] * np.einsum("ni,ni->n", o["cdf_normal"][near][close], (r / dist[:, None])[close]) > 0.97)
+
+
+def test_oracle_2d_against_independent_numpy_mpm(oracle_mod):
+    """The 2D instantiation (8x8 blocks, 10x10 tiles, svd2) against the same dense float64 statement."""
+    scene = scenes.elastic_block_2d(20)
+    scene["bodies"] = scene["bodies"][:0]
+    p = scene["particles"]
+    rng = np.random.default_rng(4)
+    ctr = p["position"].mean(axis=0)
+    p["velocity"][:, 0] = -4.0 * (p["position"][:, 1] - ctr[1]) + 0.5
+    p["velocity"][:, 1] = 4.0 * (p["position"][:, 0] - ctr[0]) - 1.0
+    Fp = p["def_grad"].reshape(len(p), -1)
+    Fp[:, :4] += rng.normal(0.0, 0.01, size=(len(p), 4)).astype(np.float32)
+    sim = oracle_mod.OracleSim(2, scene["params"], p, scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    h, dt = float(scene["cell_width"]), float(scene["params"].dt)
+    g = np.array(scene["params"].gravity, dtype=np.float64)[:2]
+    pos, vel = p["position"][:, :2].astype(np.float64), p["velocity"][:, :2].astype(np.float64)
+    F = p["def_grad"].reshape(len(p), -1)[:, :4].astype(np.float64).reshape(-1, 2, 2).transpose(0, 2, 1)
+    C = p["affine"].reshape(len(p), -1)[:, :4].astype(np.float64).reshape(-1, 2, 2).transpose(0, 2, 1)
+    for step in range(5):
+        pos, vel, F, C = _numpy_mls_mpm_substep(pos, vel, F, C, p["mass"].astype(np.float64), p["init_volume"].astype(np.float64),
+                                                p["lambda"].astype(np.float64), p["mu"].astype(np.float64), h, dt, g)
+        sim.step(1)
+        o = sim.read_particles()
+        oF = o["def_grad"].reshape(len(p), -1)[:, :4].astype(np.float64).reshape(-1, 2, 2).transpose(0, 2, 1)
+        assert np.abs(o["position"][:, :2] - pos).max() <= 2e-6 * np.abs(pos).max(), step
+        assert np.abs(o["velocity"][:, :2] - vel).max() <= 5e-5 * np.abs(vel).max(), step
+        assert np.abs(oF - F).max() <= 1e-5, step
+    sim.close()
