@@ -135,13 +135,21 @@ class ShardedMpm:
             self.p2p = False
             if p2p:
                 # NVLink peer-to-peer stores instead of NCCL send/recv: exchange CUDA-IPC handles of the arenas.
-                handles = [None] * world
-                dist.all_gather_object(handles, self.data.shard_p2p_export())
+                # (a rank that cannot export - no peer access, IPC unavailable - makes EVERY rank fall back to the
+                # NCCL send/recv transport before anybody has mapped anything)
                 try:
-                    self.data.shard_p2p_connect(handles)
-                    ok = 1
+                    mine = self.data.shard_p2p_export()
                 except Exception:
-                    ok = 0
+                    mine = None
+                handles = [None] * world
+                dist.all_gather_object(handles, mine)
+                ok = 0
+                if all(hd is not None for hd in handles):
+                    try:
+                        self.data.shard_p2p_connect(handles)
+                        ok = 1
+                    except Exception:
+                        ok = 0
                 flag = torch.tensor([ok], device="cuda:%d" % device)
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
                 self.p2p = bool(flag.item())
