@@ -22,6 +22,8 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "b200mpm.h"
@@ -161,6 +163,110 @@ struct Particle { // src/solver/particle3d.rs:53-60
         return o;
     }
 };
+
+// ---- rigid particles of mesh colliders (GpuRigidParticles::from_rapier, src/solver/particle3d.rs:101-160) --------
+// CPU sampling of triangle meshes: sample_mesh / sample_triangle / sample_edge (particle3d.rs:251-428) and of
+// polylines (particle2d.rs:206-234). The four arrays are what b200mpm_data_set_rigid_particles takes.
+struct RigidParticles {
+    std::vector<float> vertices; // 3 per collider vertex, local frame (2D: z = 0)
+    std::vector<uint32_t> vertex_colliders;
+    std::vector<float> samples; // 3 per sample point, local frame
+    std::vector<uint32_t> sample_ids; // 4 per sample point: primitive vertex ids (global) + collider index
+};
+
+namespace detail {
+struct V3f {
+    float x, y, z;
+};
+inline V3f operator+(V3f a, V3f b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3f operator-(V3f a, V3f b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3f operator*(V3f a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline float dot(V3f a, V3f b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline float norm(V3f a) { return std::sqrt(dot(a, a)); }
+constexpr float kSamplingEps = 1.0e-5f; // particle3d.rs:241
+
+template <class Emit>
+inline void sample_edge(V3f a, V3f b, float xy_spacing, Emit&& emit) { // particle3d.rs:300-320
+    const V3f ab = b - a;
+    const float edge_length = norm(ab);
+    if (edge_length > kSamplingEps) {
+        const V3f edge_dir = ab * (1.0f / edge_length);
+        const float spacing = xy_spacing / std::sqrt(2.0f);
+        const size_t nsteps = (size_t)std::ceil(edge_length / spacing);
+        for (size_t i = 1; i < nsteps; ++i) emit(a + edge_dir * (spacing * (float)i));
+    }
+}
+template <class Emit>
+inline void sample_triangle(V3f a, V3f b, V3f c, float xy_spacing, Emit&& emit) { // particle3d.rs:336-428
+    const float d_ab = norm(b - a), d_bc = norm(c - b), d_ca = norm(a - c);
+    const float mx = std::max(d_ab, std::max(d_bc, d_ca));
+    if (mx == d_bc) {
+        const V3f t = a;
+        a = b, b = c, c = t;
+    } else if (mx == d_ca) {
+        const V3f t = c;
+        c = b, b = a, a = t;
+    }
+    const V3f ac = c - a, base = b - a;
+    const float base_length = norm(base);
+    if (!(base_length > 0.0f)) return;
+    const V3f base_dir = base * (1.0f / base_length);
+    const float spacing = xy_spacing / std::sqrt(2.0f);
+    const float base_step_count = std::ceil(base_length / spacing);
+    const V3f base_step = base_dir * spacing;
+    const float ac_offset_length = dot(ac, base_dir);
+    const float bc_offset_length = base_length - ac_offset_length;
+    if (ac_offset_length < kSamplingEps || bc_offset_length < kSamplingEps || base_length < kSamplingEps) return;
+    const V3f height = ac - base_dir * ac_offset_length;
+    const float height_length = norm(height);
+    const V3f height_dir = height * (1.0f / height_length);
+    const float tan_alpha = height_length / ac_offset_length, tan_beta = height_length / bc_offset_length;
+    for (uint32_t i = 1; i < (uint32_t)base_step_count; ++i) {
+        const V3f base_position = a + base_step * (float)i;
+        const float hl = std::min(tan_alpha * norm(base_position - a), tan_beta * norm(base_position - b));
+        const float height_step_count = std::ceil(hl / spacing);
+        const V3f height_step = height_dir * spacing;
+        for (uint32_t j = 1; j < (uint32_t)height_step_count; ++j) {
+            const V3f p = base_position + height_step * (float)j;
+            if (std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z)) emit(p);
+        }
+    }
+}
+} // namespace detail
+
+// Appends the trimesh collider `collider_id` (local-frame vertices, 3 floats each; triangles, 3 indices each) with
+// the reference's sampling step (= cell_width, pipeline.rs:140).
+inline void sample_trimesh(RigidParticles& out, uint32_t collider_id, const std::vector<float>& vertices,
+                           const std::vector<uint32_t>& triangles, float sampling_step) {
+    using detail::V3f;
+    const uint32_t base_vid = (uint32_t)out.vertex_colliders.size();
+    const size_t nv = vertices.size() / 3;
+    for (size_t i = 0; i < nv; ++i) {
+        for (int k = 0; k < 3; ++k) out.vertices.push_back(vertices[3 * i + k]);
+        out.vertex_colliders.push_back(collider_id);
+    }
+    auto vtx = [&](uint32_t i) { return V3f{vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]}; };
+    std::vector<std::pair<uint32_t, uint32_t>> visited; // edges already sampled (particle3d.rs:262-270)
+    auto edge_needs_sampling = [&](uint32_t ia, uint32_t ib) {
+        if (ib > ia) std::swap(ia, ib);
+        const std::pair<uint32_t, uint32_t> key(ia, ib);
+        if (std::find(visited.begin(), visited.end(), key) != visited.end()) return false;
+        visited.push_back(key);
+        return true;
+    };
+    for (size_t t = 0; t + 2 < triangles.size(); t += 3) {
+        const uint32_t ia = triangles[t], ib = triangles[t + 1], ic = triangles[t + 2];
+        auto emit = [&](V3f p) {
+            out.samples.push_back(p.x), out.samples.push_back(p.y), out.samples.push_back(p.z);
+            out.sample_ids.push_back(base_vid + ia), out.sample_ids.push_back(base_vid + ib);
+            out.sample_ids.push_back(base_vid + ic), out.sample_ids.push_back(collider_id);
+        };
+        detail::sample_triangle(vtx(ia), vtx(ib), vtx(ic), sampling_step, emit);
+        if (edge_needs_sampling(ia, ib)) detail::sample_edge(vtx(ia), vtx(ib), sampling_step, emit);
+        if (edge_needs_sampling(ib, ic)) detail::sample_edge(vtx(ib), vtx(ic), sampling_step, emit);
+        if (edge_needs_sampling(ic, ia)) detail::sample_edge(vtx(ic), vtx(ia), sampling_step, emit);
+    }
+}
 
 } // namespace solver
 

@@ -22,6 +22,17 @@ int main() {
             }
     if (std::fabs(particles[0].dynamics.mass - 0.125f) > 1e-7f) return 2;
     if (std::fabs(models::DruckerPrager::new_(2.0e9f, 0.2f).lambda - 555555520.0f) > 64.0f) return 3;
+    {
+        // sample_trimesh (particle3d.rs:214-292) on two triangles sharing an edge; compared with the Python
+        // restatement by tests/test_abi.py
+        solver::RigidParticles rp;
+        solver::sample_trimesh(rp, 3, {0, 0, 0, 10, 0, 0, 0, 8, 0, 10, 8, 3}, {0, 1, 2, 1, 3, 2}, 1.0f);
+        double cx = 0, cy = 0, cz = 0;
+        const size_t n = rp.sample_ids.size() / 4;
+        for (size_t i = 0; i < n; ++i) cx += rp.samples[3 * i], cy += rp.samples[3 * i + 1], cz += rp.samples[3 * i + 2];
+        std::printf("samples %zu centroid %.5f %.5f %.5f vertices %zu collider %u\n", n, cx / n, cy / n, cz / n,
+                    rp.vertex_colliders.size(), rp.sample_ids[3]);
+    }
     solver::SimulationParamsT<3> params{{0.0f, -9.81f, 0.0f}, (1.0f / 60.0f) / 10.0f};
     try {
         auto pipeline = pipeline::MpmPipeline<3>::new_(0);

@@ -101,6 +101,16 @@ def test_cpp_host_mirror_compiles_and_reports_no_device(tmp_path):
         assert "stepped" in res.stdout
     else:
         assert "no device" in res.stdout
+    # the C++ mesh sampling agrees with the Python restatement of particle3d.rs:251-428
+    from wgsparkl_b200.rapier import sample_mesh
+
+    v = np.array([[0, 0, 0], [10, 0, 0], [0, 8, 0], [10, 8, 3]], dtype=np.float32)
+    pts = np.array([p for p, _ in sample_mesh(v, np.array([[0, 1, 2], [1, 3, 2]], dtype=np.uint32), 1.0)], dtype=np.float64)
+    m = re.search(r"samples (\d+) centroid (\S+) (\S+) (\S+) vertices (\d+) collider (\d+)", res.stdout)
+    assert m, res.stdout
+    assert abs(int(m.group(1)) - len(pts)) <= 2  # a ceil() on a rounding boundary may differ between float paths
+    assert np.allclose([float(m.group(k)) for k in (2, 3, 4)], pts.mean(axis=0), atol=2e-2)
+    assert int(m.group(5)) == 4 and int(m.group(6)) == 3
 
 
 def test_rust_sys_file_declares_every_symbol():
