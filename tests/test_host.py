@@ -63,3 +63,27 @@ def test_scene_sizes():
     assert np.all((s["particles"]["position"] * 2) % 1 == 0)  # every coordinate on a round() tie
     s = scenes.mixed_coupled_3d(6, 6, 6)
     assert set(np.unique(s["particles"]["model"])) == {abi.MODEL_COROTATED, abi.MODEL_NEO_HOOKEAN}
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--n-side", "12"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "particle-substeps/sec" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["unit"] == "particle-substeps/s" and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+    # ranks other than 0 of a multi-process launch print nothing and exit 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                         text=True, timeout=120, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
