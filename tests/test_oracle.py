@@ -509,3 +509,44 @@ def test_oracle_2d_against_independent_numpy_mpm(oracle_mod):
         assert np.abs(o["velocity"][:, :2] - vel).max() <= 5e-5 * np.abs(vel).max(), step
         assert np.abs(oF - F).max() <= 1e-5, step
     sim.close()
+
+
+def test_polyline_box_agrees_with_analytic_cuboid_2d(oracle_mod):
+    """2D p2g_cdf: a rectangle given as a closed polyline against the analytic cuboid of collide(). The polyline runs
+    CLOCKWISE: then (-ab.y, ab.x) points outwards and p2g_cdf.wgsl:150 sets the sign bit for interior nodes, like
+    collide() does (0x00010001 when inside). CPIC only compares particle and node signs, so the other orientation
+    is equally valid - it just puts the bit on the other side."""
+    from wgsparkl_b200.rapier import ColliderBuilder, ColliderSet, RigidBodyBuilder, RigidBodySet, bodies_to_abi, rigid_particles_to_abi
+
+    hx, hy = 6.0, 0.6
+    grids = {}
+    for mesh in (False, True):
+        scene = scenes.elastic_block_2d(30)
+        scene["particles"]["position"][:, 1] -= 9.9
+        bodies, colliders = RigidBodySet(), ColliderSet()
+        rb = bodies.insert(RigidBodyBuilder.fixed().translation([1.51, -0.73]))
+        if mesh:
+            loop = np.array([[-hx, -hy], [-hx, hy], [hx, hy], [hx, -hy], [-hx, -hy]], dtype=np.float32)
+            shape = ColliderBuilder.polyline(loop)
+        else:
+            shape = ColliderBuilder.cuboid(hx, hy)
+        colliders.insert_with_parent(shape, rb, bodies)
+        scene["bodies"] = bodies_to_abi(bodies, colliders, 2)
+        sim = oracle_mod.OracleSim(2, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+        if mesh:
+            sim.set_rigid_particles(*rigid_particles_to_abi(bodies, colliders, 2, scene["cell_width"]))
+        for st in range(4):
+            sim.stage(st)
+        blocks, nodes = sim.read_grid()
+        grids[mesh] = {tuple(b["vid"][:2]): nodes[i] for i, b in enumerate(blocks)}
+        sim.close()
+    n_both = n_same = 0
+    for vid, na in grids[False].items():
+        nb = grids[True].get(vid)
+        if nb is None:
+            continue
+        both = (na["cdf_affinities"] != 0) & (nb["cdf_affinities"] != 0)
+        n_both += int(both.sum())
+        assert np.allclose(na["cdf_distance"][both], nb["cdf_distance"][both], atol=1e-5)
+        n_same += int((na["cdf_affinities"][both] == nb["cdf_affinities"][both]).sum())
+    assert n_both > 25 and n_same == n_both, (n_both, n_same)
