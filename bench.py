@@ -387,6 +387,11 @@ def main():
                     help="auto: cube (configs[1]) at N=1, sand dam (configs[4], 2M particles per GPU) at N>1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched by hand without torchrun: re-launch as the driver does (one process per GPU, NCCL over 127.0.0.1)
+        port = os.environ.get("MASTER_PORT", "29541")
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                                   "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:])
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
