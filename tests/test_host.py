@@ -87,3 +87,23 @@ def test_bench_reference_arm_contract():
     res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                          text=True, timeout=120, env=env)
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_bench_own_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback anywhere: on a machine without an sm_100 device `bench.py` must fail, not measure something else."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("a GPU is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--n-side", "8", "--no-cpu-baseline"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0
+    assert res.stdout.strip() == "", "no JSON line may be printed"
+    assert "device" in res.stderr.lower() or "cuda" in res.stderr.lower()
