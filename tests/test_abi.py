@@ -124,3 +124,31 @@ def test_rust_sys_file_declares_every_symbol():
     declared = set(re.findall(r"\b(b200mpm_[a-z0-9_]+)\s*\(", header))
     missing = sorted(f for f in declared if ("fn %s(" % f) not in rust)
     assert not missing, missing
+
+
+def test_shared_svd_code_on_the_host(tmp_path):
+    """csrc/svd.cuh (svd2, svd3: the code the kernels fall back to, and what `prep_vertex_buffer` uses) is
+    __host__ __device__: compiled with nvcc and run on the CPU, its decompositions are checked against numpy in
+    float64 - reconstruction, proper rotations, singular values, correctly rounded ones near the identity."""
+    exe = tmp_path / "svd_host"
+    subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "cpp", "svd_host.cu")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    n3 = n2 = 0
+    for line in out.splitlines():
+        v = np.array(line.split()[1:], dtype=np.float64)
+        d = int(line[0])
+        k = d * d
+        F, U, S, V = (v[0:k].reshape(d, d).T, v[k:2 * k].reshape(d, d).T, v[2 * k:2 * k + d], v[2 * k + d:].reshape(d, d).T)  # column-major
+        assert np.abs(U @ np.diag(S) @ V.T - F).max() < 2e-6 * max(1.0, np.abs(F).max())
+        assert np.abs(U.T @ U - np.eye(d)).max() < 2e-6 and np.abs(V.T @ V - np.eye(d)).max() < 2e-6
+        assert np.linalg.det(U) > 0.99 and np.linalg.det(V) > 0.99  # proper rotations; det F < 0 goes to the last S
+        ref = np.linalg.svd(F, compute_uv=False)
+        got = np.sort(np.abs(S))[::-1]
+        assert np.abs(got - ref).max() < 2e-6
+        if np.linalg.det(F) > 0 and np.abs(F - np.eye(d)).max() < 1e-3:
+            # near the identity the returned f32 singular values are correctly rounded (the shifted iteration keeps
+            # sigma - 1 accurate relative to itself; the final 1 + (sigma - 1) costs at most one rounding)
+            assert np.abs(got - ref).max() <= 1.2e-7
+        n3 += d == 3
+        n2 += d == 2
+    assert n3 == 300 and n2 == 100
