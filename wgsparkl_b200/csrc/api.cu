@@ -153,8 +153,9 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
     if ((r = dev_alloc(d, &dev.block_flags, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.block_f0, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.cpic_list, capacity, true, L))) return r;
-    dev.g2p_list_len = capacity + d->particle_cap / G2P_ITEM + 1;
-    if ((r = dev_alloc(d, &dev.g2p_list, dev.g2p_list_len, true, L))) return r;
+    dev.g2p_items_len = capacity + d->particle_cap / G2P_ITEM + 1;
+    if ((r = dev_alloc(d, &dev.g2p_items, dev.g2p_items_len, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.p2g_list, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2, true, L))) return r;
     dev.capacity = capacity;
     return 0;

@@ -102,17 +102,28 @@ struct Counters {
     uint32_t halo_count[2]; // blocks packed for the -x / +x neighbour (sharded runs)
     uint32_t shard_seq; // substep sequence number of the peer-to-peer exchange flags
     uint32_t n_base; // live count at the start of the substep: where the immigrants are appended
+    uint32_t num_p2g_front; // entries at the FRONT of p2g_list (densely populated blocks: long items first)
+    uint32_t num_p2g_back; // entries at the BACK of p2g_list, filled downwards from the end
+    uint32_t sorted_total; // particles in the sorted range this substep (== cell_start[num_active_blocks * 64])
+    uint32_t g2p_done; // CTAs of k_g2p that have finished (the last one runs the substep's epilogue)
 };
 
-// G2P work items: a block's sorted range in parts of at most this many particles (k_scatter builds the list).
-// Bounded items keep the last scheduling round short when blocks differ a lot in population (a compressed
-// material packs 3x the seeding density into the bottom blocks), and blocks without particles are never visited.
-constexpr uint32_t G2P_ITEM = 512;
-constexpr uint32_t G2P_MAX_PARTS = 255;
-__host__ __device__ inline uint32_t g2p_parts(uint32_t n) {
-    const uint32_t p = (n + G2P_ITEM - 1) / G2P_ITEM;
-    return p < G2P_MAX_PARTS ? p : G2P_MAX_PARTS;
-}
+// G2P work items: a block's sorted range in parts of at most G2P_ITEM particles = one particle per thread of a
+// k_g2p CTA (k_scatter builds the list; blocks without particles are never visited). An item carries everything the
+// kernel needs to start fetching - slot range, collider flag, neighbour table - so that the chain
+// "work counter -> list -> cell_start -> nbr -> nodes" of dependent loads collapses into ONE 64-byte load that is
+// issued three items ahead of its use.
+constexpr uint32_t G2P_ITEM = 128;
+struct __align__(16) G2PItem {
+    uint32_t block; // header id (NONE: end of work)
+    uint32_t first; // first sorted slot
+    uint32_t count; // <= G2P_ITEM
+    uint32_t flags; // bit 0: the block's (BLOCK+2)^D tile holds a collider (block_flags)
+    uint32_t nbr[8]; // header ids of the blocks vid + {0,1}^D (2D: the first four)
+    uint32_t pad[4];
+};
+static_assert(sizeof(G2PItem) == 64, "G2PItem is fetched as 16 words by half a warp");
+__host__ __device__ inline uint32_t g2p_parts(uint32_t n) { return (n + G2P_ITEM - 1) / G2P_ITEM; }
 
 // ---- all device pointers of one MpmData --------------------------------------------------
 struct DeviceData {
@@ -158,8 +169,9 @@ struct DeviceData {
     uint8_t* block_f0; // capacity: 1 if one of the block's own nodes is near / inside a collider (k_block_prepare)
     uint32_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)
     uint32_t* cpic_list; // capacity: compact list of flagged blocks that hold particles
-    uint32_t* g2p_list; // g2p_list_len: (block | part << 24) work items of <= G2P_ITEM particles
-    uint32_t g2p_list_len; // capacity + n / G2P_ITEM + 1
+    G2PItem* g2p_items; // g2p_items_len work items of <= G2P_ITEM particles (collider-side blocks at the front)
+    uint32_t g2p_items_len; // capacity + n / G2P_ITEM + 1
+    uint32_t* p2g_list; // capacity: blocks that hold particles and whose tile holds no collider (k_p2g<.., false, ..>)
 
     BodyDev* bodies;
     // Rigid particles = sample points of trimesh / polyline colliders (GpuRigidParticles, particle3d.rs:82-88) and
@@ -288,6 +300,32 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
+// ---- mbarrier (shared-memory transaction barriers): producer / consumer pipelines without CTA-wide barriers --------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+// arrive (release): everything this thread wrote before is visible to a thread that observes the phase completion
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrive once all cp.async requests this thread has issued so far have landed (counts against the barrier's expected arrivals)
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// wait (acquire) for the completion of the phase with the given parity
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\n"
+                     : "=r"(ok)
+                     : "r"(a), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* gmem) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(gmem)); }
 __device__ __forceinline__ void prefetch_l2(const void* gmem) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gmem)); }

@@ -7,120 +7,242 @@
 // 176-byte AoS `Dynamics` struct through memory (the velocity gradient is parked in `affine`,
 // SURVEY A.4).
 //
-// B200 design: one CTA per work item = up to 512 particles of one block (k_scatter's list:
-// blocks without particles never appear, collider-side and densely populated blocks come first).
-//   * the (BLOCK+2)^D node tile is staged in shared memory through the neighbour table; the grid
-//     update is applied while staging, so node velocities never exist in HBM;
-//   * one thread per particle of the block's contiguous sorted range: 16-byte vector loads of the
-//     SoA particle arrays, the stencil gather from shared memory, the constitutive update with a
-//     single SVD, and 16-byte vector stores to the OTHER ping-pong buffer at the particle's sorted
-//     slot — the physical reordering of the particle arrays costs no extra pass.
+// B200 design: persistent CTAs of 128 threads; a work item (k_scatter's list) is <= 128
+// consecutive sorted slots of one block, one particle per thread, collider-side blocks first. The kernel is a
+// software pipeline in which no global load is ever consumed in the iteration that issued it:
+//   item i+3: four lanes request the 64-byte item descriptor (slot range, flags, neighbour table)   [cp.async]
+//   item i+2: every thread requests the id of its particle (sorted_ids, coalesced)                  [cp.async]
+//   item i+1: every thread requests its particle's 16-byte SoA records into its private shared-memory slot and,
+//             when the block changes, two nodes of the (BLOCK+2)^D tile through the item's neighbour table
+//             (two tile slots)                                                                       [cp.async]
+//   item i  : cp.async.wait_all, the grid update (grid_update.wgsl:45-64) applied in place to the nodes the thread
+//             requested itself, ONE barrier, then the stencil gather from shared memory, the constitutive update
+//             with a single decomposition, and 16-byte vector stores to the OTHER ping-pong buffer at the
+//             particle's sorted slot - the physical reordering of the particle arrays costs no extra pass.
+// Work distribution is STATIC: CTA c takes the runs {c, c + P, c + 2P, ...} of G2P_RUN consecutive items. A deep
+// prefetch pipeline and dynamic claims do not mix at this granularity (a million particles are ~11 items per
+// CTA; the items a CTA would have to claim ahead of their use are a third of its work, handed out blindly -
+// measured: 66 -> 85 us when the claims grow). Strided runs give every CTA the same number of items (+-1), deal
+// the slow collider-side items at the front of the list out evenly, and keep consecutive parts of a block on
+// one tile.
+// Registers decide this kernel (measured with the compute phase repeated 1-3x per item): 96 registers x 16 warps
+// beat 72 x 20 and 64 x 24 by 30-50 % because the spills land in the middle of the stencil gather - so the CTA
+// count follows from the register count, not the other way round, and no warp is set aside as a producer.
 #include "launch.h"
 #include "models.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 namespace b2 {
 
 constexpr int G2P_THREADS = 128;
-// CTAs per SM: 6 x 128 threads at 80 registers (elastic), 5 at 96 (plastic: the SVD + return mapping need the
-// room). Measured alternatives (tools/build_variant.py): 5 / 7 elastic and 4 / 6 plastic are all slower or equal,
-// 64- and 32-thread CTAs are 20 % / 60 % slower.
-constexpr int G2P_MIN_CTAS_ELASTIC = 6, G2P_MIN_CTAS_PLASTIC = 5;
+#ifndef G2P_CTAS_ELASTIC
+#define G2P_CTAS_ELASTIC 5
+#endif
+#ifndef G2P_CTAS_PLASTIC
+#define G2P_CTAS_PLASTIC 4
+#endif
+#ifndef G2P_RUN
+#define G2P_RUN 2u
+#endif
+constexpr int G2P_DQ = 8, G2P_IQ = 4; // look-ahead rings: descriptors 3 items ahead, ids 2 items ahead
+constexpr int G2P_SMEM_MATS = 16; // material-table entries mirrored in shared memory
 
 template <int D, bool PLASTIC, bool CPIC>
-__global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : G2P_MIN_CTAS_ELASTIC) k_g2p(DeviceData d, int cur) {
+struct __align__(16) G2PShared {
+    static constexpr int TC = Dim<D>::TILE_CELLS;
+    float4 tile_v[2][TC]; // node momentum + mass as they land; velocity + mass after the in-place grid update
+    uint2 tile_c[CPIC ? 2 : 1][CPIC ? TC : 1]; // (affinities, closest_id) of NodeCdf
+    float4 pos[2][G2P_THREADS], vel[2][G2P_THREADS], Fa[2][G2P_THREADS];
+    float4 Fb[2][D == 3 ? G2P_THREADS : 1];
+    float4 plastic[PLASTIC ? 2 : 1][PLASTIC ? G2P_THREADS : 1];
+    float4 nd[CPIC ? 2 : 1][CPIC ? G2P_THREADS : 1];
+    float Fc[2][D == 3 ? G2P_THREADS : 1];
+    uint32_t aff[CPIC ? 2 : 1][CPIC ? G2P_THREADS : 1];
+    G2PItem dq[G2P_DQ]; // item i's descriptor in slot i % G2P_DQ
+    uint32_t ids[G2P_IQ][G2P_THREADS]; // item i's particle ids in row i % G2P_IQ (each thread reads its own)
+    Material mats[G2P_SMEM_MATS];
+    float h, dt, grav[3], inv_h, inv_d, vel_limit;
+};
+
+template <int D, bool PLASTIC, bool CPIC, int CTAS>
+__global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
+    // The launch wrapper hands over the ping-pong arrays already swapped: index 0 = current, 1 = next, so that every
+    // array base is a constant-bank operand instead of a register pair.
+    constexpr int cur = 0, nxt = 1;
     constexpr int B = Dim<D>::BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
-    constexpr int NA = Dim<D>::NASSOC;
-    __shared__ float4 tile_v[TC];
-    __shared__ uint2 tile_c[CPIC ? TC : 1];
-    __shared__ uint32_t s_nbr[NA];
-    __shared__ uint32_t s_next;
+    extern __shared__ __align__(16) unsigned char g2p_smem[];
+    G2PShared<D, PLASTIC, CPIC>& sm = *reinterpret_cast<G2PShared<D, PLASTIC, CPIC>*>(g2p_smem);
 
     const int t = threadIdx.x;
-    const int nxt = cur ^ 1;
-    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-    const float h = d.sim->cell_width;
-    const float dt = d.sim->dt;
-    const float inv_h = 1.0f / h;
-    const float inv_d = 4.0f / (h * h); // kernel.wgsl:57-59
-    const float grav[3] = {d.sim->gravity[0], d.sim->gravity[1], d.sim->gravity[2]};
-    const float vel_limit = h / dt;
+    const bool mats_in_smem = d.num_materials <= (uint32_t)G2P_SMEM_MATS;
+    if (t == 0) { // simulation constants live in shared memory, not in 8 registers per thread
+        sm.h = d.sim->cell_width;
+        sm.dt = d.sim->dt;
+        sm.grav[0] = d.sim->gravity[0], sm.grav[1] = d.sim->gravity[1], sm.grav[2] = d.sim->gravity[2];
+        sm.inv_h = 1.0f / sm.h;
+        sm.inv_d = 4.0f / (sm.h * sm.h); // kernel.wgsl:57-59
+        sm.vel_limit = sm.h / sm.dt;
+    }
+    if (mats_in_smem && t < (int)(d.num_materials * 4u)) ((float4*)sm.mats)[t] = ((const float4*)d.materials)[t];
 
-    const float4* __restrict__ pos4 = d.pos4[cur];
-    const float4* __restrict__ vel4 = d.vel4[cur];
-    const float4* __restrict__ Fa = d.Fa[cur];
-    const float4* __restrict__ Fb = d.Fb[cur];
-    const float* __restrict__ Fc = d.Fc[cur];
-
-    // (block, part) items of <= G2P_ITEM particles from k_scatter: collider-side blocks first (front of the list)
+    // Logical item w lives at the front of the list for w < nfront (collider-side blocks) and at the back, counted
+    // from the end, otherwise.
     const uint32_t nfront = d.counters->num_g2p_items, nitems = nfront + d.counters->num_g2p_back;
-    while (true) {
-        __syncthreads();
-        if (t == 0) {
-            const uint32_t w = atomicAdd(&d.counters->work_g2p, 1u);
-            s_next = (w < nitems) ? d.g2p_list[w < nfront ? w : d.g2p_list_len - 1u - (w - nfront)] : NONE;
+    // Requests the descriptor of this CTA's i-th item into the ring (warp 0; an END descriptor after the last item).
+    auto request_desc = [&](uint32_t i) {
+        if (t >= 16) return;
+        const uint32_t idx = ((i / G2P_RUN) * gridDim.x + blockIdx.x) * G2P_RUN + (i % G2P_RUN);
+        uint32_t* slot = (uint32_t*)&sm.dq[i % G2P_DQ];
+        if (idx < nitems) {
+            const uint32_t phys = idx < nfront ? idx : d.g2p_items_len - 1u - (idx - nfront);
+            if (t < 4) cp_async16(slot + 4 * t, (const uint32_t*)(d.g2p_items + phys) + 4 * t);
+        } else {
+            slot[t] = (t == 0) ? NONE : 0u;
         }
-        __syncthreads();
-        const uint32_t item = s_next;
-        if (item == NONE) break;
-        const uint32_t b = item & 0xffffffu;
-        uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
-        uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
-        {
-            const uint32_t parts = g2p_parts(last - first), part = item >> 24;
-            const uint32_t per = (last - first + parts - 1) / parts;
-            first = min(first + part * per, last);
-            last = min(first + per, last);
+    };
+    // Requests the id of this thread's particle of item i (its descriptor has landed).
+    auto request_id = [&](uint32_t i) {
+        const G2PItem& it = sm.dq[i % G2P_DQ];
+        if ((uint32_t)t < it.count) cp_async4(&sm.ids[i % G2P_IQ][t], d.sorted_ids + it.first + t);
+    };
+    // Item j brings a new tile iff its block differs from item j-1's; the tile slot alternates with every new tile.
+    auto new_tile = [&](uint32_t j) -> bool {
+        return j == 0u || sm.dq[j % G2P_DQ].block != sm.dq[(j - 1u) % G2P_DQ].block;
+    };
+    int ts = 1; // slot of the current item's tile
+    // Requests item j's records of this thread's particle (its id has landed) and, on a block change, this thread's
+    // two nodes of the tile.
+    auto request_item = [&](uint32_t j) {
+        const G2PItem& it = sm.dq[j % G2P_DQ];
+        if (it.block == NONE) return;
+        const int s = (int)(j & 1u);
+        const bool any_cdf = CPIC && (it.flags & 1u);
+        if ((uint32_t)t < it.count) {
+            const uint32_t id = sm.ids[j % G2P_IQ][t];
+            cp_async16(&sm.pos[s][t], d.pos4[cur] + id);
+            cp_async16(&sm.vel[s][t], d.vel4[cur] + id);
+            cp_async16(&sm.Fa[s][t], d.Fa[cur] + id);
+            if (D == 3) {
+                cp_async16(&sm.Fb[s][t], d.Fb[cur] + id);
+                cp_async4(&sm.Fc[s][t], d.Fc[cur] + id);
+            }
+            if (PLASTIC) cp_async16(&sm.plastic[PLASTIC ? s : 0][PLASTIC ? t : 0], d.plastic[cur] + id);
+            if (any_cdf) { // this substep's particle colours, by sorted slot (k_scatter / k_g2p_cdf)
+                cp_async4(&sm.aff[CPIC ? s : 0][CPIC ? t : 0], d.cdf_aff[nxt] + it.first + t);
+                cp_async16(&sm.nd[CPIC ? s : 0][CPIC ? t : 0], d.cdf_nd + it.first + t);
+            }
         }
-        if (t < NA) s_nbr[t] = d.nbr[b * NA + t];
-        __syncthreads();
-        // Stage the tile; grid_update (grid_update.wgsl:45-64) on the fly.
-        const int any_cdf = CPIC ? (int)d.block_flags[b] : 0; // the tile holds a collider (k_scatter)
-        for (int n = t; n < TC; n += G2P_THREADS) { // g2p.wgsl:72-132
-            int x = n % T, y = (n / T) % T, z = n / (T * T);
-            int ox = x >= B, oy = y >= B, oz = z >= B;
-            uint32_t hn = s_nbr[ox + 2 * oy + 4 * oz];
-            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint2 cdf = make_uint2(0u, NONE);
-            if (hn != NONE) {
-                uint32_t node = hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B;
-                float4 mv = d.node_mv[node];
-                float mass = (D == 3) ? mv.w : mv.z;
-                float inv_mass = (mass > 0.0f) ? 1.0f / mass : 0.0f;
-                float vx = (mv.x + mass * grav[0] * dt) * inv_mass;
-                float vy = (mv.y + mass * grav[1] * dt) * inv_mass;
-                out.x = fminf(fmaxf(vx, -vel_limit), vel_limit);
-                out.y = fminf(fmaxf(vy, -vel_limit), vel_limit);
-                if (D == 3) {
-                    float vz = (mv.z + mass * grav[2] * dt) * inv_mass;
-                    out.z = fminf(fmaxf(vz, -vel_limit), vel_limit);
-                }
-                out.w = mass;
-                if (CPIC && any_cdf) {
-                    uint4 g = d.node_cdf[node];
-                    cdf = make_uint2(g.z, g.x); // (affinities, closest_id)
+        if (new_tile(j)) { // g2p.wgsl:72-132, through the item's neighbour table
+            const int u = ts ^ 1;
+            // (an opaque copy of t: the index arithmetic below is loop-invariant, and hoisted out of the main loop
+            // it would sit in registers - or in spill slots - across the whole compute phase)
+            int tt = t;
+            asm volatile("" : "+r"(tt));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int n = tt + G2P_THREADS * k;
+                if (n < TC) {
+                    const int x = n % T, y = (n / T) % T, z = n / (T * T);
+                    const int ox = x >= B, oy = y >= B, oz = z >= B;
+                    const uint32_t hn = it.nbr[ox + 2 * oy + 4 * oz];
+                    if (hn != NONE) {
+                        const uint32_t node = hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B;
+                        cp_async16(&sm.tile_v[u][n], d.node_mv + node);
+                        if (any_cdf) {
+                            const uint32_t* g = (const uint32_t*)(d.node_cdf + node);
+                            cp_async4(&sm.tile_c[CPIC ? u : 0][CPIC ? n : 0].x, g + 2); // affinities
+                            cp_async4(&sm.tile_c[CPIC ? u : 0][CPIC ? n : 0].y, g); // closest_id
+                        }
+                    } else {
+                        sm.tile_v[u][n] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (any_cdf) sm.tile_c[CPIC ? u : 0][CPIC ? n : 0] = make_uint2(0u, NONE);
+                    }
                 }
             }
-            tile_v[n] = out;
-            if (CPIC && any_cdf) tile_c[n] = cdf;
         }
-        __syncthreads();
+    };
 
-        for (uint32_t k = first + t; k < last; k += G2P_THREADS) {
-            const uint32_t id = __ldg(d.sorted_ids + k);
-            const float4 p4 = __ldg(pos4 + id);
-            const float4 v4 = __ldg(vel4 + id);
+    // ---- prologue: descriptors 0..2, ids 0..1, records of item 0 (three exposed latencies, once per CTA)
+    request_desc(0);
+    request_desc(1);
+    request_desc(2);
+    cp_async_wait_all();
+    __syncthreads();
+    request_id(0);
+    request_id(1);
+    cp_async_wait_all();
+    request_item(0);
+
+    for (uint32_t i = 0;; ++i) {
+        const bool cur_new = sm.dq[i % G2P_DQ].block != NONE && new_tile(i);
+        if (cur_new) ts ^= 1;
+        cp_async_wait_all(); // everything requested one iteration ago has landed (for this thread)
+        if (cur_new) { // grid_update (grid_update.wgsl:45-64), in place, each thread on the nodes it requested
+            const float dt = sm.dt, vel_limit = sm.vel_limit;
+            const float grav[3] = {sm.grav[0], sm.grav[1], sm.grav[2]};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int n = t + G2P_THREADS * k;
+                if (n < TC) {
+                    const float4 mv = sm.tile_v[ts][n];
+                    const float mass = (D == 3) ? mv.w : mv.z;
+                    const float inv_mass = (mass > 0.0f) ? 1.0f / mass : 0.0f;
+                    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float vx = (mv.x + mass * grav[0] * dt) * inv_mass;
+                    const float vy = (mv.y + mass * grav[1] * dt) * inv_mass;
+                    out.x = fminf(fmaxf(vx, -vel_limit), vel_limit);
+                    out.y = fminf(fmaxf(vy, -vel_limit), vel_limit);
+                    if (D == 3) {
+                        const float vz = (mv.z + mass * grav[2] * dt) * inv_mass;
+                        out.z = fminf(fmaxf(vz, -vel_limit), vel_limit);
+                    }
+                    out.w = mass;
+                    sm.tile_v[ts][n] = out;
+                }
+            }
+        }
+        __syncthreads(); // tile of item i complete; descriptors up to i+2 visible; everybody is done with item i-1
+        const G2PItem& item = sm.dq[i % G2P_DQ];
+        if (item.block == NONE) break;
+        request_item(i + 1);
+        request_id(i + 2);
+        request_desc(i + 3);
+
+        const uint32_t count = item.count;
+        const int any_cdf = CPIC ? (int)(item.flags & 1u) : 0; // the tile holds a collider (k_scatter)
+#ifdef G2P_REPEAT /* diagnostic: every item is computed and stored G2P_REPEAT times (time difference = pure compute) */
+#pragma unroll 1
+        for (int rep = 0; rep < G2P_REPEAT; ++rep) {
+        asm volatile("" ::: "memory");
+#endif
+        if ((uint32_t)t < count) {
+            const float h = sm.h, dt = sm.dt, inv_h = sm.inv_h, inv_d = sm.inv_d, vel_limit = sm.vel_limit;
+            const int s = (int)(i & 1u);
+            const uint32_t k = item.first + t;
+            const float4* __restrict__ tile_v = sm.tile_v[ts];
+            const uint2* __restrict__ tile_c = sm.tile_c[CPIC ? ts : 0];
+            const float4 p4 = sm.pos[s][t];
+            const float4 v4 = sm.vel[s][t];
             float F[D * D];
             {
-                float4 fa = __ldg(Fa + id);
+                const float4 fa = sm.Fa[s][t];
                 F[0] = fa.x, F[1] = fa.y, F[2] = fa.z, F[3] = fa.w;
                 if (D == 3) {
-                    float4 fb = __ldg(Fb + id);
+                    const float4 fb = sm.Fb[s][t];
                     F[4] = fb.x, F[5] = fb.y, F[6] = fb.z, F[7] = fb.w;
-                    F[D * D - 1] = __ldg(Fc + id);
+                    F[D * D - 1] = sm.Fc[s][t];
                 }
             }
             uint32_t mbits = __float_as_uint(p4.w);
-            const Material m = d.materials[mbits & MAT_ID_MASK];
+            Material m; // per-material constants: from the shared-memory copy when the table fits (it almost always does)
+            {
+                const uint32_t mid = mbits & MAT_ID_MASK;
+                if (mats_in_smem) m = sm.mats[mid];
+                else m = d.materials[mid];
+            }
             const float pp[3] = {p4.x, p4.y, p4.z};
             float d0[D], w[D][3];
             int tb = 0;
@@ -136,9 +258,9 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : 
             V3 normal = v3(0, 0, 0);
             float sd = 0.0f;
             if (CPIC) {
-                if (any_cdf) pa = d.cdf_aff[nxt][k];
+                if (any_cdf) pa = sm.aff[s][t];
                 if (pa != 0u) {
-                    float4 nd = d.cdf_nd[k];
+                    const float4 nd = sm.nd[s][t];
                     normal = v3(nd.x, nd.y, (D == 3) ? nd.z : 0.0f);
                     sd = nd.w;
                 }
@@ -291,7 +413,7 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : 
                     Fn[c * D + r] = F[c * D + r] + s;
                 }
             float4 plastic = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
-            if (PLASTIC) plastic = d.plastic[cur][id];
+            if (PLASTIC) plastic = sm.plastic[s][t];
             float tau[D * D];
             uint32_t flags = mbits;
             constitutive_update<D, PLASTIC>(m, flags, Fn, plastic, tau);
@@ -316,13 +438,17 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : 
                 if (pa != 0u) d.cdf_rv[k] = make_float4(rigid_vel.x, rigid_vel.y, rigid_vel.z, 0.0f);
             }
         }
+#ifdef G2P_REPEAT
+        }
+#endif
     }
+    cp_async_wait_all();
 
     // Particles of dropped blocks (capacity overflow only): carried over unchanged.
     const uint32_t dropped = d.counters->dropped_particles;
     if (dropped) {
-        const uint32_t total = d.cell_start[nb * CELLS_PER_BLOCK];
-        for (uint32_t k = total + blockIdx.x * blockDim.x + t; k < total + dropped && k < d.counters->n_live; k += gridDim.x * blockDim.x) {
+        const uint32_t total = d.counters->sorted_total;
+        for (uint32_t k = total + blockIdx.x * blockDim.x + threadIdx.x; k < total + dropped && k < d.counters->n_live; k += gridDim.x * blockDim.x) {
             const uint32_t id = d.sorted_ids[k];
             d.pos4[nxt][k] = d.pos4[cur][id];
             d.vel4[nxt][k] = d.vel4[cur][id];
@@ -340,15 +466,44 @@ __global__ void __launch_bounds__(G2P_THREADS, PLASTIC ? G2P_MIN_CTAS_PLASTIC : 
     }
 }
 
+template <int D, bool PLASTIC, bool CPIC>
+static void launch_g2p_inst(const LaunchCfg& c, const DeviceData& d, int cur) {
+    constexpr int CTAS = PLASTIC ? G2P_CTAS_PLASTIC : G2P_CTAS_ELASTIC;
+    auto kernel = k_g2p<D, PLASTIC, CPIC, CTAS>;
+    constexpr size_t smem = sizeof(G2PShared<D, PLASTIC, CPIC>);
+    static int resident = 0; // CTAs per SM (one process drives one device). The static work split needs the whole grid resident.
+    if (!resident) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, G2P_THREADS, smem) != cudaSuccess || resident < 1) resident = 1;
+        if (resident > CTAS) resident = CTAS;
+        if (getenv("B200MPM_VERBOSE"))
+            fprintf(stderr, "k_g2p<%d,%d,%d>: %zu B smem, %d CTAs/SM resident (wanted %d)\n", D, (int)PLASTIC, (int)CPIC, smem, resident, CTAS);
+    }
+    DeviceData dd = d;
+    if (cur) {
+        std::swap(dd.pos4[0], dd.pos4[1]);
+        std::swap(dd.vel4[0], dd.vel4[1]);
+        std::swap(dd.Fa[0], dd.Fa[1]);
+        std::swap(dd.Fb[0], dd.Fb[1]);
+        std::swap(dd.Fc[0], dd.Fc[1]);
+        std::swap(dd.Ca[0], dd.Ca[1]);
+        std::swap(dd.Cb[0], dd.Cb[1]);
+        std::swap(dd.Cc[0], dd.Cc[1]);
+        std::swap(dd.plastic[0], dd.plastic[1]);
+        std::swap(dd.cdf_aff[0], dd.cdf_aff[1]);
+    }
+    kernel<<<c.num_sms * resident, G2P_THREADS, smem, c.stream>>>(dd);
+}
+
 template <int D>
 static void launch_g2p_dim(const LaunchCfg& c, const DeviceData& d, int cur) {
-    const int grid = c.num_sms * 8;
     if (d.has_plastic) {
-        if (d.has_bodies) k_g2p<D, true, true><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);
-        else k_g2p<D, true, false><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);
+        if (d.has_bodies) launch_g2p_inst<D, true, true>(c, d, cur);
+        else launch_g2p_inst<D, true, false>(c, d, cur);
     } else {
-        if (d.has_bodies) k_g2p<D, false, true><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);
-        else k_g2p<D, false, false><<<grid, G2P_THREADS, 0, c.stream>>>(d, cur);
+        if (d.has_bodies) launch_g2p_inst<D, false, true>(c, d, cur);
+        else launch_g2p_inst<D, false, false>(c, d, cur);
     }
 }
 

@@ -37,6 +37,9 @@ __global__ void __launch_bounds__(256) k_begin_substep(DeviceData d) {
         c->num_cpic_blocks = 0;
         c->num_g2p_items = 0;
         c->num_g2p_back = 0;
+        c->num_p2g_front = 0;
+        c->num_p2g_back = 0;
+        c->g2p_done = 0;
         c->dropped_particles = 0;
     }
     if (id < d.sim->num_bodies) {

@@ -197,10 +197,10 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
     // A collider-side half-block is split into PARTS work items (each takes every cell's PARTS-th share of the
     // run): these blocks are few, so their latency — not throughput — is what shows up.
     constexpr uint32_t PARTS = CPIC ? 2u : 1u;
-    // CPIC = false walks the G2P item list (k_scatter: blocks that hold particles, the densely populated ones
-    // first - longest items first keeps the last scheduling round short), taking part 0 of every block.
-    const uint32_t nfront = d.counters->num_g2p_items;
-    const uint32_t nwork = (CPIC ? d.counters->num_cpic_blocks * PARTS : nfront + d.counters->num_g2p_back) * 2u;
+    // CPIC = false walks p2g_list (k_scatter: blocks that hold particles and see no collider, the densely populated
+    // ones first - longest items first keeps the last scheduling round short).
+    const uint32_t nfront = d.counters->num_p2g_front;
+    const uint32_t nwork = (CPIC ? d.counters->num_cpic_blocks * PARTS : nfront + d.counters->num_p2g_back) * 2u;
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
     uint32_t* work = CPIC ? &d.counters->work_p2g_cpic : &d.counters->work_p2g;
@@ -256,10 +256,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
             b = d.cpic_list[w / (2u * PARTS)];
         } else {
             const uint32_t e = w >> 1;
-            const uint32_t item = d.g2p_list[e < nfront ? e : d.g2p_list_len - 1u - (e - nfront)];
-            if (item >> 24) continue; // a further part of a block that was taken at its part 0
-            b = item;
-            if (d.has_bodies && d.block_flags[b] != 0) continue; // handled by the CPIC instantiation
+            b = d.p2g_list[e < nfront ? e : d.capacity - 1u - (e - nfront)];
         }
         const uint32_t cell = half * HALF + lane; // this lane's cell of the block
         const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK + half * HALF];

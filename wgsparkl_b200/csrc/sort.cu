@@ -457,43 +457,68 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
     {
         // Per-block work lists (i doubles as a block index here; the grid covers capacity blocks).
         const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-        uint32_t np = 0;
-        if (i < nb) np = d.cell_start[(i + 1) * CELLS_PER_BLOCK] - d.cell_start[i * CELLS_PER_BLOCK];
+        if (i == 0) d.counters->sorted_total = d.cell_start[nb * CELLS_PER_BLOCK];
+        uint32_t np = 0, first = 0;
+        if (i < nb) {
+            first = d.cell_start[i * CELLS_PER_BLOCK];
+            np = d.cell_start[(i + 1) * CELLS_PER_BLOCK] - first;
+        }
+        uint32_t nbr[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) nbr[o] = NONE;
         int flag = 0;
+        if (i < nb) {
+#pragma unroll
+            for (int o = 0; o < Dim<D>::NASSOC; ++o) nbr[o] = d.nbr[i * Dim<D>::NASSOC + o];
+        }
         if (d.has_bodies && i < nb) {
             // CPIC: a block runs the collider-aware paths iff one of the 2^D blocks its tile overlaps has a node
             // near / inside a collider.
 #pragma unroll
-            for (int o = 0; o < Dim<D>::NASSOC; ++o) {
-                uint32_t hn = d.nbr[i * Dim<D>::NASSOC + o];
-                if (hn != NONE) flag |= d.block_f0[hn];
-            }
+            for (int o = 0; o < Dim<D>::NASSOC; ++o)
+                if (nbr[o] != NONE) flag |= d.block_f0[nbr[o]];
             d.block_flags[i] = (uint32_t)flag;
             if (flag && np != 0u) d.cpic_list[atomicAdd(&d.counters->num_cpic_blocks, 1u)] = i;
         }
-        // G2P items: blocks that hold particles, in parts of <= G2P_ITEM particles. Collider-side blocks cost
-        // several times more per particle (ghost-velocity gather), so they go to the FRONT of the list and are
-        // scheduled first; everything else fills the list from the back. One atomic per warp and list end.
-        const uint32_t parts = g2p_parts(np);
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const bool slow = (flag != 0) || np > G2P_ITEM + G2P_ITEM / 4; // collider-side, or densely populated
-            const uint32_t mine = (slow == (side == 0)) ? parts : 0u;
+        // Two-ended lists, one atomic per warp and list end: positions [0, front) grow upwards, the back grows
+        // downwards from the end; the consumers walk front first, then the back from the end - slow items first.
+        const uint32_t lane = threadIdx.x & 31;
+        auto reserve = [&](uint32_t mine, uint32_t* counter) -> uint32_t {
             uint32_t incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)(threadIdx.x & 31) >= o) incl += v;
+                if ((int)lane >= o) incl += v;
             }
             const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-            if (warp_total == 0u) continue; // (warp-uniform)
             uint32_t base = 0;
-            if ((threadIdx.x & 31) == 31)
-                base = atomicAdd(side == 0 ? &d.counters->num_g2p_items : &d.counters->num_g2p_back, warp_total);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-            for (uint32_t p = 0; p < mine; ++p)
-                d.g2p_list[side == 0 ? base + p : d.g2p_list_len - 1u - (base + p)] = i | (p << 24);
+            if (warp_total != 0u && lane == 31) base = atomicAdd(counter, warp_total);
+            return __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+        };
+        // G2P items: blocks that hold particles, in parts of <= G2P_ITEM particles (one per thread of a k_g2p CTA).
+        // Collider-side blocks cost more per particle (ghost-velocity gather), so they go to the FRONT of the
+        // list and are scheduled first; everything else fills the list from the back.
+        const uint32_t parts = g2p_parts(np);
+        const bool slow = flag != 0;
+        const uint32_t base_f = reserve(slow ? parts : 0u, &d.counters->num_g2p_items);
+        const uint32_t base_b = reserve(slow ? 0u : parts, &d.counters->num_g2p_back);
+        if (parts) {
+            const uint32_t per = (np + parts - 1) / parts;
+            for (uint32_t p = 0; p < parts; ++p) {
+                const uint32_t pos = slow ? base_f + p : d.g2p_items_len - 1u - (base_b + p);
+                uint4* dst = (uint4*)(d.g2p_items + pos);
+                dst[0] = make_uint4(i, first + p * per, min(per, np - p * per), (uint32_t)flag);
+                dst[1] = make_uint4(nbr[0], nbr[1], nbr[2], nbr[3]);
+                dst[2] = make_uint4(nbr[4], nbr[5], nbr[6], nbr[7]);
+            }
         }
+        // P2G list (k_p2g without CPIC): blocks that hold particles and whose tile holds no collider; the densely
+        // populated ones (longest items) first.
+        const bool p2g_mine = np != 0u && flag == 0;
+        const bool dense = np > 5u * G2P_ITEM;
+        const uint32_t pf = reserve((p2g_mine && dense) ? 1u : 0u, &d.counters->num_p2g_front);
+        const uint32_t pb = reserve((p2g_mine && !dense) ? 1u : 0u, &d.counters->num_p2g_back);
+        if (p2g_mine) d.p2g_list[dense ? pf : d.capacity - 1u - pb] = i;
     }
     // particles: SORT_ITEMS per thread, see k_touch
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
