@@ -156,6 +156,9 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
     dev.g2p_items_len = capacity + d->particle_cap / G2P_ITEM + 1;
     if ((r = dev_alloc(d, &dev.g2p_items, dev.g2p_items_len, true, L))) return r;
     if ((r = dev_alloc(d, &dev.p2g_list, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.half_max, 2u * (size_t)capacity, true, L))) return r;
+    dev.p2g_stages_cap = d->particle_cap / P2G_K + 2u * capacity + 1u;
+    if ((r = dev_alloc(d, &dev.p2g_stages, dev.p2g_stages_cap, true, L))) return r;
     if ((r = dev_alloc(d, &dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2, true, L))) return r;
     dev.capacity = capacity;
     return 0;

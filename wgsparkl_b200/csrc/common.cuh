@@ -106,6 +106,7 @@ struct Counters {
     uint32_t num_p2g_back; // entries at the BACK of p2g_list, filled downwards from the end
     uint32_t sorted_total; // particles in the sorted range this substep (== cell_start[num_active_blocks * 64])
     uint32_t g2p_done; // CTAs of k_g2p that have finished (the last one runs the substep's epilogue)
+    uint32_t num_p2g_stages; // entries of p2g_stages this substep
 };
 
 // G2P work items: a block's sorted range in parts of at most G2P_ITEM particles = one particle per thread of a
@@ -114,6 +115,7 @@ struct Counters {
 // "work counter -> list -> cell_start -> nbr -> nodes" of dependent loads collapses into ONE 64-byte load that is
 // issued three items ahead of its use.
 constexpr uint32_t G2P_ITEM = 128;
+constexpr uint32_t P2G_K = 4; // particles per cell that one P2G stage takes (half the reference's seeding density)
 struct __align__(16) G2PItem {
     uint32_t block; // header id (NONE: end of work)
     uint32_t first; // first sorted slot
@@ -171,6 +173,12 @@ struct DeviceData {
     uint32_t* cpic_list; // capacity: compact list of flagged blocks that hold particles
     G2PItem* g2p_items; // g2p_items_len work items of <= G2P_ITEM particles (collider-side blocks at the front)
     uint32_t g2p_items_len; // capacity + n / G2P_ITEM + 1
+    // P2G work table of k_p2g_fast (k_scatter): one entry per STAGE = one half block (32 cells, one lane per cell) x up
+    // to P2G_K particles per cell; .x = block | half << 31, .y = stage | stages of the half block << 16. The stages of
+    // a half block are consecutive; the workers take equal contiguous shares of the table.
+    uint32_t* half_max; // 2 * capacity: longest cell run of every half block (k_scan)
+    uint2* p2g_stages;
+    uint32_t p2g_stages_cap; // particle capacity / P2G_K + 2 * block capacity: cannot overflow
     uint32_t* p2g_list; // capacity: blocks that hold particles and whose tile holds no collider (k_p2g<.., false, ..>)
 
     BodyDev* bodies;
@@ -295,6 +303,10 @@ __device__ __forceinline__ int flt2int(float f) {
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -61,7 +61,8 @@ struct __align__(16) G2PShared {
     float4 nd[CPIC ? 2 : 1][CPIC ? G2P_THREADS : 1];
     float Fc[2][D == 3 ? G2P_THREADS : 1];
     uint32_t aff[CPIC ? 2 : 1][CPIC ? G2P_THREADS : 1];
-    G2PItem dq[G2P_DQ]; // item i's descriptor in slot i % G2P_DQ
+    G2PItem dq[G2P_THREADS / 32][G2P_DQ]; // per warp: item i's descriptor in slot i % G2P_DQ (every warp keeps its own
+                                          // copy, so that descriptors never need a CTA barrier)
     uint32_t ids[G2P_IQ][G2P_THREADS]; // item i's particle ids in row i % G2P_IQ (each thread reads its own)
     Material mats[G2P_SMEM_MATS];
     float h, dt, grav[3], inv_h, inv_d, vel_limit;
@@ -91,32 +92,34 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     // Logical item w lives at the front of the list for w < nfront (collider-side blocks) and at the back, counted
     // from the end, otherwise.
     const uint32_t nfront = d.counters->num_g2p_items, nitems = nfront + d.counters->num_g2p_back;
-    // Requests the descriptor of this CTA's i-th item into the ring (warp 0; an END descriptor after the last item).
+    // Requests the descriptor of this CTA's i-th item into the warp's ring (an END descriptor after the last item).
+    const int lane = t & 31;
+    G2PItem* const dq = sm.dq[t >> 5];
     auto request_desc = [&](uint32_t i) {
-        if (t >= 16) return;
+        if (lane >= 16) return;
         const uint32_t idx = ((i / G2P_RUN) * gridDim.x + blockIdx.x) * G2P_RUN + (i % G2P_RUN);
-        uint32_t* slot = (uint32_t*)&sm.dq[i % G2P_DQ];
+        uint32_t* slot = (uint32_t*)&dq[i % G2P_DQ];
         if (idx < nitems) {
             const uint32_t phys = idx < nfront ? idx : d.g2p_items_len - 1u - (idx - nfront);
-            if (t < 4) cp_async16(slot + 4 * t, (const uint32_t*)(d.g2p_items + phys) + 4 * t);
+            if (lane < 4) cp_async16(slot + 4 * lane, (const uint32_t*)(d.g2p_items + phys) + 4 * lane);
         } else {
-            slot[t] = (t == 0) ? NONE : 0u;
+            slot[lane] = (lane == 0) ? NONE : 0u;
         }
     };
     // Requests the id of this thread's particle of item i (its descriptor has landed).
     auto request_id = [&](uint32_t i) {
-        const G2PItem& it = sm.dq[i % G2P_DQ];
+        const G2PItem& it = dq[i % G2P_DQ];
         if ((uint32_t)t < it.count) cp_async4(&sm.ids[i % G2P_IQ][t], d.sorted_ids + it.first + t);
     };
     // Item j brings a new tile iff its block differs from item j-1's; the tile slot alternates with every new tile.
     auto new_tile = [&](uint32_t j) -> bool {
-        return j == 0u || sm.dq[j % G2P_DQ].block != sm.dq[(j - 1u) % G2P_DQ].block;
+        return j == 0u || dq[j % G2P_DQ].block != dq[(j - 1u) % G2P_DQ].block;
     };
     int ts = 1; // slot of the current item's tile
     // Requests item j's records of this thread's particle (its id has landed) and, on a block change, this thread's
     // two nodes of the tile.
     auto request_item = [&](uint32_t j) {
-        const G2PItem& it = sm.dq[j % G2P_DQ];
+        const G2PItem& it = dq[j % G2P_DQ];
         if (it.block == NONE) return;
         const int s = (int)(j & 1u);
         const bool any_cdf = CPIC && (it.flags & 1u);
@@ -170,14 +173,14 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     request_desc(1);
     request_desc(2);
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads(); // (also: the constants and the material table)
     request_id(0);
     request_id(1);
     cp_async_wait_all();
     request_item(0);
 
     for (uint32_t i = 0;; ++i) {
-        const bool cur_new = sm.dq[i % G2P_DQ].block != NONE && new_tile(i);
+        const bool cur_new = dq[i % G2P_DQ].block != NONE && new_tile(i);
         if (cur_new) ts ^= 1;
         cp_async_wait_all(); // everything requested one iteration ago has landed (for this thread)
         if (cur_new) { // grid_update (grid_update.wgsl:45-64), in place, each thread on the nodes it requested
@@ -204,8 +207,12 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
                 }
             }
         }
-        __syncthreads(); // tile of item i complete; descriptors up to i+2 visible; everybody is done with item i-1
-        const G2PItem& item = sm.dq[i % G2P_DQ];
+        // A CTA barrier only where the warps share something: a freshly updated tile. (It also keeps the tile slots
+        // safe: nobody requests the tile after next before everybody is done with the previous one.) Records and
+        // ids are thread-private, descriptors warp-private: between block changes the warps drift freely.
+        if (cur_new) __syncthreads();
+        else __syncwarp();
+        const G2PItem& item = dq[i % G2P_DQ];
         if (item.block == NONE) break;
         request_item(i + 1);
         request_id(i + 2);

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) k_begin_substep(DeviceData d) {
         c->num_p2g_front = 0;
         c->num_p2g_back = 0;
         c->g2p_done = 0;
+        c->num_p2g_stages = 0;
         c->dropped_particles = 0;
     }
     if (id < d.sim->num_bodies) {

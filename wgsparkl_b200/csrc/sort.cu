@@ -341,9 +341,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
 
 // ---- exclusive scan, single pass with decoupled look-back (replaces prefix_sum.wgsl) -----------------
 // Same result as WgPrefixSum::eval_cpu (prefix_sum.rs:71-83): out[i] = sum_{j<i} in[j].
+// group_max (optional): the largest input value of every aligned group of 32 inputs = the longest cell run of every half
+// block, which sizes the P2G stage table (k_scatter) - the inputs are in registers here anyway.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t len_value,
                                                        const Counters* __restrict__ counters, uint32_t capacity,
-                                                       uint64_t* state, uint32_t* ticket) {
+                                                       uint64_t* state, uint32_t* ticket, uint32_t* __restrict__ group_max) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_prefix;
@@ -366,6 +368,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
     }
     // inclusive warp scan of the per-thread sums
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (group_max) { // 4 consecutive threads hold one group of 32 inputs (SCAN_ITEMS == 8)
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) m = max(m, v[j]);
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        if ((lane & 3u) == 0u && t0 + 31u < len) group_max[t0 >> 5] = m;
+    }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -519,6 +529,19 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
         const uint32_t pf = reserve((p2g_mine && dense) ? 1u : 0u, &d.counters->num_p2g_front);
         const uint32_t pb = reserve((p2g_mine && !dense) ? 1u : 0u, &d.counters->num_p2g_back);
         if (p2g_mine) d.p2g_list[dense ? pf : d.capacity - 1u - pb] = i;
+        // P2G stage table (k_p2g_fast): a half block needs ceil(longest cell run / P2G_K) stages (k_scan left the
+        // longest run of every half block in half_max).
+        if (p2g_mine) {
+#pragma unroll
+            for (uint32_t half = 0; half < 2u; ++half) {
+                const uint32_t nst = (d.half_max[2u * i + half] + P2G_K - 1u) / P2G_K;
+                if (nst) {
+                    const uint32_t base = atomicAdd(&d.counters->num_p2g_stages, nst);
+                    for (uint32_t st = 0; st < nst && base + st < d.p2g_stages_cap; ++st)
+                        d.p2g_stages[base + st] = make_uint2(i | (half << 31), st | (nst << 16));
+                }
+            }
+        }
     }
     // particles: SORT_ITEMS per thread, see k_touch
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -597,8 +620,9 @@ void launch_scan_cells(const LaunchCfg& c, const DeviceData& d) {
     uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
     if (max_blocks > d.capacity) max_blocks = d.capacity;
     uint32_t tiles = scan_num_tiles(max_blocks * CELLS_PER_BLOCK + 1);
+    static_assert(SCAN_ITEMS == 8, "k_scan derives the per-half-block maxima from groups of 4 threads");
     k_scan<<<tiles, SCAN_THREADS, 0, c.stream>>>(d.cell_start, 0u, d.counters, d.capacity, d.scan_state,
-                                                  &d.counters->scan_ticket);
+                                                  &d.counters->scan_ticket, d.half_max);
     ++*c.launch_counter;
 }
 void launch_block_prepare(const LaunchCfg& c, const DeviceData& d) {
@@ -625,7 +649,7 @@ void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len,
     uint32_t tiles = scan_num_tiles(len);
     cudaMemsetAsync(scan_state, 0, sizeof(uint64_t) * (tiles + 1), c.stream);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c.stream);
-    k_scan<<<tiles, SCAN_THREADS, 0, c.stream>>>(data, len, nullptr, 0u, scan_state, ticket);
+    k_scan<<<tiles, SCAN_THREADS, 0, c.stream>>>(data, len, nullptr, 0u, scan_state, ticket, nullptr);
     ++*c.launch_counter;
 }
 
