@@ -156,6 +156,24 @@ enum {
     B200MPM_NUM_PASSES = 10
 };
 
+/* Kernel-level timers of this implementation (b200mpm_get_kernel_timings): finer than the reference's pass names,
+ * e.g. the two P2G instantiations, which the "p2g" pass sums. Used by bench.py's per-kernel roofline. */
+enum {
+    B200MPM_KERNEL_TOUCH = 0,
+    B200MPM_KERNEL_COUNT = 1,
+    B200MPM_KERNEL_SCAN = 2,
+    B200MPM_KERNEL_BLOCK_PREPARE = 3,
+    B200MPM_KERNEL_SCATTER = 4,
+    B200MPM_KERNEL_G2P_CDF = 5,
+    B200MPM_KERNEL_P2G_CPIC = 6, /* blocks next to a collider */
+    B200MPM_KERNEL_P2G = 7, /* all other blocks */
+    B200MPM_KERNEL_BEGIN = 8, /* reset_hmap for the next substep */
+    B200MPM_KERNEL_G2P = 9, /* grid_update + g2p + particles_update */
+    B200MPM_KERNEL_INTEGRATE_BODIES = 10,
+    B200MPM_KERNEL_RIGID = 11, /* mesh-collider kernels (transform, mark / touch, p2g_cdf) */
+    B200MPM_NUM_KERNELS = 12
+};
+
 typedef struct b200mpm_pipeline b200mpm_pipeline; /* MpmPipeline (src/pipeline.rs:24-39) */
 typedef struct b200mpm_data b200mpm_data; /* MpmData (src/pipeline.rs:84-95) */
 
@@ -197,6 +215,12 @@ int b200mpm_sync(b200mpm_pipeline* p);
 int b200mpm_set_timestamps(b200mpm_pipeline* p, int enabled);
 /* Accumulated ms per reference pass since the last call (src_testbed/step.rs:219-254). Syncs. */
 int b200mpm_get_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_PASSES]);
+/* The same accumulation per kernel of this implementation (no reference counterpart; timestamps mode only). Syncs. */
+int b200mpm_get_kernel_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_KERNELS]);
+/* Debug: [2k] earliest start / [2k+1] latest end (GPU %globaltimer, ns) of kernel k since the last call, then reset.
+ * Only libraries built with -DB200MPM_TIMELINE record anything (tools/timeline.py); otherwise the reset values
+ * (all ones / zero) come back. Syncs. */
+int b200mpm_debug_timeline(b200mpm_data* d, uint64_t ns[2 * B200MPM_NUM_KERNELS]);
 
 /* ---- per-frame host writes / reads (src_testbed/step.rs:79-119,175-176, ui.rs:98-103) -- */
 int b200mpm_write_sim_params(b200mpm_data* d, const b200mpm_sim_params* params);

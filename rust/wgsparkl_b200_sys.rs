@@ -132,6 +132,8 @@ extern "C" {
     pub fn b200mpm_sync(p: *mut b200mpm_pipeline) -> c_int;
     pub fn b200mpm_set_timestamps(p: *mut b200mpm_pipeline, enabled: c_int) -> c_int;
     pub fn b200mpm_get_timings(p: *mut b200mpm_pipeline, ms: *mut f64) -> c_int;
+    pub fn b200mpm_get_kernel_timings(p: *mut b200mpm_pipeline, ms: *mut f64) -> c_int;
+    pub fn b200mpm_debug_timeline(d: *mut b200mpm_data, ns: *mut u64) -> c_int;
     pub fn b200mpm_write_sim_params(d: *mut b200mpm_data, params: *const b200mpm_sim_params) -> c_int;
     pub fn b200mpm_write_body_poses(d: *mut b200mpm_data, poses: *const b200mpm_pose, n: usize) -> c_int;
     pub fn b200mpm_write_body_vels(d: *mut b200mpm_data, vels: *const b200mpm_velocity, n: usize) -> c_int;

@@ -112,3 +112,60 @@ def test_sharded_equals_unsharded_1m(cube1m):
     assert np.abs(got["velocity"].astype(np.float64) - ref["velocity"]).max() <= 1e-4 * np.abs(ref["velocity"]).max()
     assert np.array_equal(got["cdf_affinity"], ref["cdf_affinity"])
     grp.close()
+
+
+# ---- one-substep parity against the oracle AT SIZE (the oracle does ~0.5 s per million particles and substep) ------
+def _parity_one_substep_from_gpu_state(pipe3, oracle_mod, scene, develop):
+    """Develops the scene on the GPU (`develop` substeps: compression / contact / plastic flow at the real block
+    populations), reads the full particle state back, and then advances THAT state by one substep on both sides."""
+    import parity
+    from wgsparkl_b200.pipeline import MpmData
+
+    data = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    pipe3.queue_step(data, develop)
+    pipe3.sync()
+    state = data.read_particles()
+    nb, overflow = data.status()
+    assert not overflow
+    data.close()
+    assert np.isfinite(state["position"]).all()
+    data = MpmData(pipe3, scene["params"], state, scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    sim = oracle_mod.OracleSim(scene["dim"], scene["params"], state, scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    pipe3.queue_step(data, 1)
+    pipe3.sync()
+    sim.step(1)
+    g, o = data.read_particles(), sim.read_particles()
+    gb, gn = data.read_grid()
+    ob, on = sim.read_grid()
+    # indexing: bit-exact after canonicalisation (SURVEY 8c)
+    parity.assert_sort_equal(gb, data.read_sorted_ids(), ob, sim.read_sorted_ids())
+    parity.assert_grid_close(gb, gn, ob, on, 1e-5)
+    assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
+    data.close()
+    sim.close()
+    return state, g, o, nb
+
+
+def test_one_substep_parity_cube_1m(pipe3, oracle_mod, cube1m):
+    """BASELINE configs[1] at full size: the 1M cube after 60 substeps of compression on the ground (multi-part G2P
+    items, densely populated bottom blocks, CPIC contact layer), one substep CUDA vs oracle from the same state."""
+    import parity
+
+    state, g, o, nb = _parity_one_substep_from_gpu_state(pipe3, oracle_mod, cube1m, 60)
+    assert (state["cdf_affinity"] != 0).sum() > 10_000, "the developed state must exercise CPIC"
+    parity.assert_particles_close(g, o, 1e-5, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 3, cube1m["cell_width"], float(cube1m["params"].dt))
+    assert 2000 < nb < 4500
+
+
+def test_one_substep_parity_dam_slab_2m(pipe3, oracle_mod):
+    """One GPU's share of BASELINE configs[4]: the 2M-particle Drucker-Prager dam slab after 40 substeps."""
+    import parity
+
+    scene = scenes.sand_dam_3d(50, 200, 200, grid_capacity=65536)
+    state, g, o, nb = _parity_one_substep_from_gpu_state(pipe3, oracle_mod, scene, 40)
+    # stiff sand (E = 2e9): one substep from an identical state stays at the one-substep bounds of the small scenes
+    parity.assert_particles_close(g, o, 1e-5, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 3, scene["cell_width"], float(scene["params"].dt))
+    for f in ("plastic_det", "plastic_hardening"):
+        assert parity.field_rel_err(g[f], o[f]) <= 1e-5, f

@@ -50,6 +50,7 @@ struct b200mpm_pipeline {
     std::vector<EventPair> events;
     std::vector<cudaEvent_t> event_pool;
     double pass_ms[B200MPM_NUM_PASSES] = {0};
+    double kernel_ms[B200MPM_NUM_KERNELS] = {0};
     std::vector<b200mpm_data*> children; // data objects created on this pipeline (orphaned, not freed, on destroy)
     // scratch for b200mpm_prefix_sum_u32
     LaunchCfg cfg() { return LaunchCfg{dim, num_sms, stream, &launches}; }
@@ -61,6 +62,10 @@ struct b200mpm_data {
     DeviceData dev{};
     int cur = 0;
     bool sorted_indirect = true; // sorted_ids is an indirection into `cur` (no full substep since the last sort)
+    // The hash map / per-cell bins still hold a sort (after creation, a grid reallocation or b200mpm_sort_only): the
+    // next substep has to launch k_begin_substep itself. A complete substep leaves the grid clean (its graph runs the
+    // clearing beside k_g2p).
+    bool grid_dirty = true;
     uint32_t num_bodies = 0;
     std::vector<void*> allocs;
     std::vector<void*> grid_allocs; // the capacity-sized arrays (replaced by b200mpm_data_reserve_grid)
@@ -94,7 +99,7 @@ struct b200mpm_data {
     uint32_t n_live_host = 0; // host mirror of counters->n_live (sharded runs track it)
     bool sharded = false;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // Asynchronous position readback (b200mpm_read_positions_async): two device staging slots, a copy stream.
     cudaStream_t copy_stream = nullptr;
     float4* pos_stage[2] = {nullptr, nullptr};
@@ -156,9 +161,7 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
     dev.g2p_items_len = capacity + d->particle_cap / G2P_ITEM + 1;
     if ((r = dev_alloc(d, &dev.g2p_items, dev.g2p_items_len, true, L))) return r;
     if ((r = dev_alloc(d, &dev.p2g_list, capacity, true, L))) return r;
-    if ((r = dev_alloc(d, &dev.half_max, 2u * (size_t)capacity, true, L))) return r;
-    dev.p2g_stages_cap = d->particle_cap / P2G_K + 2u * capacity + 1u;
-    if ((r = dev_alloc(d, &dev.p2g_stages, dev.p2g_stages_cap, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.block_range, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2, true, L))) return r;
     dev.capacity = capacity;
     return 0;
@@ -167,7 +170,7 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
 struct PassTimer { // queue.compute_pass(name, add_timestamps) (src/pipeline.rs:201)
     b200mpm_pipeline* p;
     cudaEvent_t a = nullptr;
-    int pass;
+    int pass; // pass id, or B200MPM_NUM_PASSES + kernel id for the kernel-level timers
     PassTimer(b200mpm_pipeline* pipe, int pass_id) : p(pipe), pass(pass_id) {
         if (!p->timestamps) return;
         a = take();
@@ -197,7 +200,8 @@ void fold_events(b200mpm_pipeline* p) {
     for (auto& e : p->events) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, e.a, e.b);
-        p->pass_ms[e.pass] += ms;
+        if (e.pass < B200MPM_NUM_PASSES) p->pass_ms[e.pass] += ms;
+        else p->kernel_ms[e.pass - B200MPM_NUM_PASSES] += ms;
         p->event_pool.push_back(e.a);
         p->event_pool.push_back(e.b);
     }
@@ -206,23 +210,39 @@ void fold_events(b200mpm_pipeline* p) {
 
 void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
     LaunchCfg c = p->cfg();
+    constexpr int K = B200MPM_NUM_PASSES; // kernel-level timers nest inside the reference's pass timers
     {
         PassTimer t(p, B200MPM_PASS_GRID_SORT);
-        launch_touch(c, d->dev, d->cur);
-        launch_touch_rigid(c, d->dev);
-        launch_count(c, d->dev);
-        launch_scan_cells(c, d->dev);
+        {
+            PassTimer k(p, K + B200MPM_KERNEL_TOUCH);
+            launch_touch(c, d->dev, d->cur);
+        }
+        {
+            PassTimer k(p, K + B200MPM_KERNEL_RIGID);
+            launch_touch_rigid(c, d->dev);
+        }
+        {
+            PassTimer k(p, K + B200MPM_KERNEL_COUNT);
+            launch_count(c, d->dev);
+        }
+        {
+            PassTimer k(p, K + B200MPM_KERNEL_SCAN);
+            launch_scan_cells(c, d->dev);
+        }
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_UPDATE_CDF);
+        PassTimer k(p, K + B200MPM_KERNEL_BLOCK_PREPARE);
         launch_block_prepare(c, d->dev);
     }
     {
         PassTimer t(p, B200MPM_PASS_P2G_CDF);
+        PassTimer k(p, K + B200MPM_KERNEL_RIGID);
         launch_p2g_cdf(c, d->dev);
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_SORT);
+        PassTimer k(p, K + B200MPM_KERNEL_SCATTER);
         launch_scatter(c, d->dev, d->cur);
     }
 }
@@ -240,6 +260,23 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
     LaunchCfg c{p->dim, p->num_sms, main, counter};
     LaunchCfg cs{p->dim, p->num_sms, side ? side : main, counter};
     const DeviceData& dev = d->dev;
+    // From G2P on: nothing reads the hash map or the per-cell bins any more, so the clearing for the NEXT substep
+    // (k_begin_substep) runs beside k_g2p instead of at the top of the critical path.
+    // The body integration (<= 16 bodies, one warp: a pure latency chain of ~7 us) is DEFERRED in the single-GPU
+    // graph: it opens the side branch of the next substep, in front of k_block_prepare (the first kernel that looks
+    // at the poses again) and beside touch / count / scan; b200mpm_step flushes the last one.
+    const bool defer_integrate = side && phase == PHASE_ALL && dev.num_rigid == 0; // (mesh colliders: k_transform_rigid needs the poses first)
+    auto finish_substep = [&]() {
+        if (side) {
+            cudaEventRecord(d->ev[4], main);
+            cudaStreamWaitEvent(side, d->ev[4], 0);
+        }
+        launch_begin_substep(cs, dev);
+        if (side) cudaEventRecord(d->ev[5], side);
+        launch_g2p_update(c, dev, d->cur);
+        if (side) cudaStreamWaitEvent(main, d->ev[5], 0);
+        if (!defer_integrate) launch_integrate_bodies(c, dev);
+    };
     if (phase == PHASE_SHARDED) {
         // One whole substep of a slab: migration and node-halo exchanges are NCCL send/recv groups on the same
         // stream (and inside the same captured graph) as the kernels.
@@ -288,8 +325,7 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
                 launch_impulses_io(c, dev, d->imp_buf, 1);
             }
             // (the dead tail of this substep is dropped by the next k_shard_tick)
-            launch_g2p_update(c, dev, d->cur);
-            launch_integrate_bodies(c, dev);
+            finish_substep();
             return;
         } else {
             launch_emigrate(c, dev, d->cur, d->mig_send[0], d->mig_send[1], d->mig_cap);
@@ -311,12 +347,15 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
         return;
     }
     if (phase == PHASE_END) {
-        launch_g2p_update(c, dev, d->cur);
-        launch_integrate_bodies(c, dev);
+        finish_substep();
         launch_drop_dead_tail(c, dev);
         return;
     }
-    launch_begin_substep(c, dev);
+    if (defer_integrate) { // the previous substep's integration (no-op on the very first substep)
+        cudaEventRecord(d->ev[4], main);
+        cudaStreamWaitEvent(side, d->ev[4], 0);
+        launch_integrate_bodies(cs, dev);
+    }
     launch_transform_rigid(c, dev);
     launch_touch(c, dev, d->cur);
     launch_touch_rigid(c, dev);
@@ -341,8 +380,14 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
     launch_p2g(c, dev, d->cur);
     if (side && dev.has_bodies) cudaStreamWaitEvent(main, d->ev[3], 0);
     if (phase == PHASE_BEGIN) return;
-    launch_g2p_update(c, dev, d->cur);
-    launch_integrate_bodies(c, dev);
+    finish_substep();
+}
+
+// The sparse grid must be clear before a sort starts (see b200mpm_data::grid_dirty).
+void ensure_clean_grid(b200mpm_pipeline* p, b200mpm_data* d) {
+    if (!d->grid_dirty) return;
+    launch_begin_substep(p->cfg(), d->dev);
+    d->grid_dirty = false;
 }
 
 // Captures the substep for the current parity into a graph (once), then replays it.
@@ -374,8 +419,10 @@ bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
         }
         d->graph_launches[par][phase] = count;
     }
+    if (phase != PHASE_END) ensure_clean_grid(p, d);
     if (cudaGraphLaunch(d->graph_exec[par][phase], p->stream) != cudaSuccess) return false;
     p->launches += d->graph_launches[par][phase];
+    d->grid_dirty = (phase == PHASE_BEGIN); // every other phase ends with the clearing for the next substep
     if (phase != PHASE_BEGIN) {
         d->cur ^= 1;
         d->sorted_indirect = false;
@@ -386,7 +433,9 @@ bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
 // One phase of a substep without timestamps: graph replay, or plain launches when graphs are disabled.
 void run_phase(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
     if (p->use_graphs && run_substep_graph(p, d, phase)) return;
+    if (phase != PHASE_END) ensure_clean_grid(p, d);
     enqueue_substep(p, d, p->stream, nullptr, &p->launches, phase);
+    d->grid_dirty = (phase == PHASE_BEGIN);
     if (phase != PHASE_BEGIN) {
         d->cur ^= 1;
         d->sorted_indirect = false;
@@ -398,25 +447,40 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
     LaunchCfg c = p->cfg();
     {
         PassTimer t(p, B200MPM_PASS_UPDATE_RIGID_PARTICLES);
-        launch_begin_substep(c, d->dev);
+        ensure_clean_grid(p, d);
         launch_transform_rigid(c, d->dev);
     }
     run_sort(p, d);
+    constexpr int K = B200MPM_NUM_PASSES;
     {
         PassTimer t(p, B200MPM_PASS_G2P_CDF);
+        PassTimer k(p, K + B200MPM_KERNEL_G2P_CDF);
         launch_g2p_cdf(c, d->dev, d->cur);
     }
     {
         PassTimer t(p, B200MPM_PASS_P2G);
-        launch_p2g_cpic(c, d->dev, d->cur);
-        launch_p2g(c, d->dev, d->cur);
+        {
+            PassTimer k(p, K + B200MPM_KERNEL_P2G_CPIC);
+            launch_p2g_cpic(c, d->dev, d->cur);
+        }
+        {
+            PassTimer k(p, K + B200MPM_KERNEL_P2G);
+            launch_p2g(c, d->dev, d->cur);
+        }
+    }
+    {
+        PassTimer t(p, B200MPM_PASS_GRID_SORT); // reset_hmap for the next substep (beside k_g2p in the graph)
+        PassTimer k(p, K + B200MPM_KERNEL_BEGIN);
+        launch_begin_substep(c, d->dev);
     }
     {
         PassTimer t(p, B200MPM_PASS_G2P); // grid_update + g2p + particles_update are one kernel here
+        PassTimer k(p, K + B200MPM_KERNEL_G2P);
         launch_g2p_update(c, d->dev, d->cur);
     }
     {
         PassTimer t(p, B200MPM_PASS_INTEGRATE_BODIES);
+        PassTimer k(p, K + B200MPM_KERNEL_INTEGRATE_BODIES);
         launch_integrate_bodies(c, d->dev);
     }
     d->cur ^= 1;
@@ -664,6 +728,7 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
     ALLOC(dev.bodies, B200MPM_MAX_BODIES);
     ALLOC(dev.sim, 1);
     ALLOC(dev.counters, 1);
+    ALLOC(dev.timeline, 2 * B200MPM_NUM_KERNELS);
 
     UPLOAD(dev.pos4[0], pos4);
     UPLOAD(dev.vel4[0], vel4);
@@ -742,6 +807,7 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
     UPLOAD(dev.counters, hc);
 #undef ALLOC
 #undef UPLOAD
+    if (num_bodies) launch_refresh_bodies(p->cfg(), dev); // world-space mass properties (rigid_impulses.wgsl:139-150)
     cudaError_t e = cudaStreamSynchronize(p->stream); // host vectors go out of scope
     if (e != cudaSuccess) {
         b200mpm_data_destroy(d);
@@ -871,10 +937,19 @@ int b200mpm_data_reserve_grid(b200mpm_data* d, uint32_t grid_capacity) {
                 cudaGraphExecDestroy(g);
                 g = nullptr;
             }
-    for (void* q : d->grid_allocs) cudaFree(q);
-    d->grid_allocs.clear();
+    // Allocate the new arrays first; the old grid is only given up once every allocation has succeeded.
+    const DeviceData old_dev = d->dev;
+    std::vector<void*> old_allocs;
+    old_allocs.swap(d->grid_allocs);
     int r = alloc_grid(d, capacity);
-    if (r) return r;
+    if (r) {
+        for (void* q : d->grid_allocs) cudaFree(q);
+        d->grid_allocs.swap(old_allocs);
+        d->dev = old_dev;
+        return r;
+    }
+    for (void* q : old_allocs) cudaFree(q);
+    d->grid_dirty = true; // the new hash map is zero-filled, not cleared
     // Nothing of the old grid has to be cleared by the next k_begin_substep, and the (sticky) overflow flag is
     // about the capacity that was just replaced.
     const uint32_t zero = 0;
@@ -897,7 +972,7 @@ namespace {
 int maybe_grow_grid(b200mpm_pipeline* p, b200mpm_data* d) {
     if (!(d->auto_grow_load > 0.0f)) return B200MPM_OK;
     uint32_t nb = 0;
-    CU_TRY(cudaMemcpyAsync(&nb, &d->dev.counters->num_active_blocks, sizeof(nb), cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaMemcpyAsync(&nb, &d->dev.counters->prev_active_blocks, sizeof(nb), cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
     uint64_t want = d->dev.capacity;
     while ((double)nb > (double)d->auto_grow_load * (double)want && want < (1ull << 24)) want <<= 1;
@@ -914,6 +989,7 @@ int b200mpm_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_substeps) {
         if (r) return r;
     }
     for (uint32_t s = 0; s < num_substeps; ++s) run_substep(p, d);
+    launch_integrate_bodies(p->cfg(), d->dev); // flushes the integration the last graph replay deferred (else a no-op)
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;
 }
@@ -922,9 +998,10 @@ int b200mpm_sort_only(b200mpm_pipeline* p, b200mpm_data* d) {
     if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
     CU_TRY(cudaSetDevice(p->device));
     LaunchCfg c = p->cfg();
-    launch_begin_substep(c, d->dev);
+    ensure_clean_grid(p, d);
     launch_transform_rigid(c, d->dev);
     run_sort(p, d);
+    d->grid_dirty = true;
     d->sorted_indirect = true;
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;
@@ -943,6 +1020,31 @@ int b200mpm_set_timestamps(b200mpm_pipeline* p, int enabled) {
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null pipeline");
     if (!enabled) fold_events(p);
     p->timestamps = enabled != 0;
+    return B200MPM_OK;
+}
+
+int b200mpm_debug_timeline(b200mpm_data* d, uint64_t ns[2 * B200MPM_NUM_KERNELS]) {
+    if (!d || !ns) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    b200mpm_pipeline* p = d->pipe;
+    if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaMemcpyAsync(ns, d->dev.timeline, sizeof(uint64_t) * 2 * B200MPM_NUM_KERNELS, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    uint64_t init[2 * B200MPM_NUM_KERNELS];
+    for (int k = 0; k < B200MPM_NUM_KERNELS; ++k) init[2 * k] = ~0ull, init[2 * k + 1] = 0ull;
+    CU_TRY(cudaMemcpyAsync(d->dev.timeline, init, sizeof(init), cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return B200MPM_OK;
+}
+
+int b200mpm_get_kernel_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_KERNELS]) {
+    if (!p || !ms) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    fold_events(p);
+    for (int i = 0; i < B200MPM_NUM_KERNELS; ++i) {
+        ms[i] = p->kernel_ms[i];
+        p->kernel_ms[i] = 0.0;
+    }
     return B200MPM_OK;
 }
 
@@ -1192,10 +1294,13 @@ int b200mpm_data_status(b200mpm_data* d, uint32_t* num_active_blocks) {
     Counters c;
     CU_TRY(cudaMemcpyAsync(&c, d->dev.counters, sizeof(c), cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
-    if (num_active_blocks) *num_active_blocks = std::min(c.num_active_blocks, d->dev.capacity);
-    if (c.overflow == 1) return fail(B200MPM_ERR_GRID_OVERFLOW, "grid block capacity exceeded: blocks were dropped");
-    if (c.overflow == 2) return fail(B200MPM_ERR_GRID_OVERFLOW, "a shard exchange buffer was too small");
-    if (c.overflow == 3) return fail(B200MPM_ERR_GRID_OVERFLOW, "particle_capacity exceeded by immigrants: particles were lost");
+    if (num_active_blocks) *num_active_blocks = std::min(c.prev_active_blocks, d->dev.capacity);
+    // (bit 2: live particles were left without a block; codes 1..3 in the low bits)
+    if ((c.overflow & 4u) && d->sharded)
+        return fail(B200MPM_ERR_GRID_OVERFLOW, "grid block capacity exceeded: blocks were dropped and their particles lost (sharded run)");
+    if ((c.overflow & 3u) == 1 || c.overflow == 4u) return fail(B200MPM_ERR_GRID_OVERFLOW, "grid block capacity exceeded: blocks were dropped");
+    if ((c.overflow & 3u) == 2) return fail(B200MPM_ERR_GRID_OVERFLOW, "a shard exchange buffer was too small");
+    if ((c.overflow & 3u) == 3) return fail(B200MPM_ERR_GRID_OVERFLOW, "particle_capacity exceeded by immigrants: particles were lost");
     return B200MPM_OK;
 }
 

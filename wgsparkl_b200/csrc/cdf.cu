@@ -10,7 +10,12 @@
 
 namespace b2 {
 
-constexpr int CDF_THREADS = 256;
+// Work item = a quarter of a collider-side block (<= ~128 particles) on a CTA of 128 threads: the flagged blocks are
+// few (the contact layer), so the kernel is a latency chain per item - more, shorter items finish sooner.
+#ifndef CDF_PARTS
+#define CDF_PARTS 4u
+#endif
+constexpr int CDF_THREADS = 128;
 
 template <int Q>
 struct SmallMat {
@@ -87,6 +92,7 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
     __shared__ uint32_t s_nbr[NA];
     __shared__ uint32_t s_next;
     const int t = threadIdx.x;
+    TL_BEGIN(d, B200MPM_KERNEL_G2P_CDF);
     const uint32_t ncpic = d.counters->num_cpic_blocks;
     const uint32_t num_bodies = d.sim->num_bodies;
     const float h = d.sim->cell_width;
@@ -99,10 +105,18 @@ __global__ void __launch_bounds__(CDF_THREADS) k_g2p_cdf(DeviceData d, int cur) 
         __syncthreads();
         if (t == 0) s_next = atomicAdd(&d.counters->work_cdf, 1u);
         __syncthreads();
-        if (s_next >= ncpic) break;
-        const uint32_t b = d.cpic_list[s_next];
-        const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
-        const uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
+        if (s_next >= ncpic * CDF_PARTS) {
+            TL_END(d, B200MPM_KERNEL_G2P_CDF);
+            break;
+        }
+        const uint32_t b = d.cpic_list[s_next / CDF_PARTS], part = s_next % CDF_PARTS;
+        uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
+        uint32_t last = d.cell_start[(b + 1) * CELLS_PER_BLOCK];
+        {
+            const uint32_t per = (last - first + CDF_PARTS - 1u) / CDF_PARTS;
+            first = min(first + part * per, last);
+            last = min(first + per, last);
+        }
         if (first == last) continue;
         if (t < NA) s_nbr[t] = d.nbr[b * NA + t];
         __syncthreads();

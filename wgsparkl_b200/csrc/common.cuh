@@ -86,7 +86,9 @@ struct SimState {
 // ---- device-resident counters --------------------------------------------------------------
 struct Counters {
     uint32_t num_active_blocks; // Grid.num_active_blocks (grid.wgsl:223)
-    uint32_t prev_active_blocks; // active count of the previous substep (what has to be cleared)
+    uint32_t prev_active_blocks; // active count of the last sort (published by k_scatter): what the host reads, and
+                                 // what k_begin_substep has to clear - num_active_blocks itself is already back
+                                 // to zero when a substep ends
     uint32_t overflow; // sticky: the block capacity / hash map was exceeded at least once
     uint32_t scan_ticket; // dynamic tile id for the single-pass scan
     uint32_t work_p2g; // dynamic block schedulers
@@ -105,8 +107,7 @@ struct Counters {
     uint32_t num_p2g_front; // entries at the FRONT of p2g_list (densely populated blocks: long items first)
     uint32_t num_p2g_back; // entries at the BACK of p2g_list, filled downwards from the end
     uint32_t sorted_total; // particles in the sorted range this substep (== cell_start[num_active_blocks * 64])
-    uint32_t g2p_done; // CTAs of k_g2p that have finished (the last one runs the substep's epilogue)
-    uint32_t num_p2g_stages; // entries of p2g_stages this substep
+    uint32_t integrate_pending; // a substep ran since the last k_integrate_bodies (which may be deferred, api.cu)
 };
 
 // G2P work items: a block's sorted range in parts of at most G2P_ITEM particles = one particle per thread of a
@@ -115,7 +116,6 @@ struct Counters {
 // "work counter -> list -> cell_start -> nbr -> nodes" of dependent loads collapses into ONE 64-byte load that is
 // issued three items ahead of its use.
 constexpr uint32_t G2P_ITEM = 128;
-constexpr uint32_t P2G_K = 4; // particles per cell that one P2G stage takes (half the reference's seeding density)
 struct __align__(16) G2PItem {
     uint32_t block; // header id (NONE: end of work)
     uint32_t first; // first sorted slot
@@ -173,12 +173,7 @@ struct DeviceData {
     uint32_t* cpic_list; // capacity: compact list of flagged blocks that hold particles
     G2PItem* g2p_items; // g2p_items_len work items of <= G2P_ITEM particles (collider-side blocks at the front)
     uint32_t g2p_items_len; // capacity + n / G2P_ITEM + 1
-    // P2G work table of k_p2g_fast (k_scatter): one entry per STAGE = one half block (32 cells, one lane per cell) x up
-    // to P2G_K particles per cell; .x = block | half << 31, .y = stage | stages of the half block << 16. The stages of
-    // a half block are consecutive; the workers take equal contiguous shares of the table.
-    uint32_t* half_max; // 2 * capacity: longest cell run of every half block (k_scan)
-    uint2* p2g_stages;
-    uint32_t p2g_stages_cap; // particle capacity / P2G_K + 2 * block capacity: cannot overflow
+    uint2* block_range; // capacity: (first sorted slot, particle count) of every block (k_scatter; read-back helpers)
     uint32_t* p2g_list; // capacity: blocks that hold particles and whose tile holds no collider (k_p2g<.., false, ..>)
 
     BodyDev* bodies;
@@ -194,6 +189,9 @@ struct DeviceData {
     uint32_t* mv_body;
     SimState* sim;
     Counters* counters;
+    // Debug timeline (builds with -DB200MPM_TIMELINE only): [2k] = earliest start, [2k+1] = latest end of kernel k
+    // (B200MPM_KERNEL_*) in %globaltimer nanoseconds; read and reset by b200mpm_debug_timeline.
+    unsigned long long* timeline;
 };
 
 // ---- small math --------------------------------------------------------------------------
@@ -259,6 +257,17 @@ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y 
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
 __device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
 
+// Contraction-free variants (every product and sum rounded on its own, like WGSL without fused multiply-add and
+// like the oracle's -ffp-contract=off): for code whose RESULT IS AN INTEGER DECISION - the affinity / sign bits of
+// the mesh-collider colouring must match bit for bit, and one fused multiply-add next to a triangle edge flips them.
+__device__ __forceinline__ float dot_rn(V3 a, V3 b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ V3 cross_rn(V3 a, V3 b) {
+    return V3{__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+              __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x))};
+}
+
 // project_velocity (grid.wgsl:390-404). For 2D pass z = 0.
 __device__ __forceinline__ V3 project_velocity(V3 vel, V3 n) {
     float normal_vel = dot(vel, n);
@@ -299,6 +308,18 @@ __device__ __forceinline__ int flt2int(float f) {
 }
 
 #if defined(__CUDACC__)
+#ifdef B200MPM_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_BEGIN(d, k) do { if (threadIdx.x == 0) atomicMin((d).timeline + 2 * (k), tl_now()); } while (0)
+#define TL_END(d, k) do { if (threadIdx.x == 0) atomicMax((d).timeline + 2 * (k) + 1, tl_now()); } while (0)
+#else
+#define TL_BEGIN(d, k) do { } while (0)
+#define TL_END(d, k) do { } while (0)
+#endif
 // ---- cp.async (LDGSTS): global -> shared without register staging -------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     extern __shared__ __align__(16) unsigned char g2p_smem[];
     G2PShared<D, PLASTIC, CPIC>& sm = *reinterpret_cast<G2PShared<D, PLASTIC, CPIC>*>(g2p_smem);
 
+    pdl_start();
+    TL_BEGIN(d, B200MPM_KERNEL_G2P);
     const int t = threadIdx.x;
     const bool mats_in_smem = d.num_materials <= (uint32_t)G2P_SMEM_MATS;
     if (t == 0) { // simulation constants live in shared memory, not in 8 registers per thread
@@ -450,6 +452,7 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
 #endif
     }
     cp_async_wait_all();
+    TL_END(d, B200MPM_KERNEL_G2P);
 
     // Particles of dropped blocks (capacity overflow only): carried over unchanged.
     const uint32_t dropped = d.counters->dropped_particles;
@@ -500,7 +503,7 @@ static void launch_g2p_inst(const LaunchCfg& c, const DeviceData& d, int cur) {
         std::swap(dd.plastic[0], dd.plastic[1]);
         std::swap(dd.cdf_aff[0], dd.cdf_aff[1]);
     }
-    kernel<<<c.num_sms * resident, G2P_THREADS, smem, c.stream>>>(dd);
+    launch_pdl(kernel, c.num_sms * resident, G2P_THREADS, smem, c.stream, dd);
 }
 
 template <int D>

@@ -5,6 +5,33 @@
 
 namespace b2 {
 
+// Programmatic dependent launch for the kernels of the substep's critical path (touch -> count -> scan -> scatter ->
+// p2g -> g2p -> integrate): the dependent kernel is launched while its predecessor drains and parks at
+// pdl_wait() (griddepcontrol.wait: full completion + memory flush of the predecessor), so the ~2-3 us of launch
+// latency per graph edge overlap the predecessor's tail. Every such kernel starts with pdl_start().
+// B200MPM_NO_PDL=1 switches the attribute off (plain stream order; the device-side instructions are then no-ops).
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_start() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); // (the dependents park at their own wait)
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+#endif
+
 struct LaunchCfg {
     int dim;
     int num_sms;
@@ -12,8 +39,10 @@ struct LaunchCfg {
     uint64_t* launch_counter; // incremented once per kernel launch (b200mpm_pipeline_launch_count)
 };
 
-// "update rigid particles" pass + per-substep counter reset.
+// reset_hmap + bin clearing: leaves the sparse grid ready for the next k_touch (runs beside k_g2p, see api.cu).
 void launch_begin_substep(const LaunchCfg& c, const DeviceData& d);
+// update_world_mass_properties for all bodies (after data creation; pose / velocity writers refresh on their own).
+void launch_refresh_bodies(const LaunchCfg& c, const DeviceData& d);
 // "grid sort" pass (WgGrid::queue_sort, src/grid/grid.rs:30-207).
 void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur);
 void launch_count(const LaunchCfg& c, const DeviceData& d);

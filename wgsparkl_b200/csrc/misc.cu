@@ -1,90 +1,80 @@
 // Rigid-body kernels ("update rigid particles" and "integrate_bodies" passes), per-substep counter
 // bookkeeping, and the readback / host-write helpers behind the C ABI.
 #include "launch.h"
+
+#include <cstdlib>
 #include "svd.cuh"
 
 namespace b2 {
 
-// ---- update_world_mass_properties (rigid_impulses.wgsl:139-150) + counter reset ----------------------
-// wgrapier Body::updateMprops: com = pose * local_com,
-// inv_inertia_world = R I^-1 R^T.
-// + reset_hmap (grid.wgsl:186-203) and the clearing of last substep's per-cell bins / scan descriptors, spread
-// over the whole grid of this kernel; the rigid-body part runs on the first warp of CTA 0.
+// ---- update_world_mass_properties (rigid_impulses.wgsl:139-150) -------------------------------------------------
+// wgrapier Body::updateMprops: com = pose * local_com, inv_inertia_world = R I^-1 R^T; plus the
+// needs_impulse flag. The reference recomputes them at the top of every substep; here whoever CHANGES a pose or a
+// velocity (k_integrate_bodies, the host writes, data creation) refreshes them, so no kernel of the substep's
+// critical path is spent on <= 16 bodies.
 template <int D>
-__global__ void __launch_bounds__(256) k_begin_substep(DeviceData d) {
+__device__ inline void refresh_body(BodyDev& b) {
     {
-        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-        const uint32_t stride = gridDim.x * blockDim.x;
-        for (uint32_t i = tid; i < d.capacity; i += stride) d.hkeys[i] = NONE;
-        // prev_active_blocks was published by the last k_scatter (0 before the first substep: the arrays are
-        // zero-initialised at creation)
-        const uint32_t prev = min(d.counters->prev_active_blocks, d.capacity);
-        const uint32_t nbins = prev * CELLS_PER_BLOCK + 1;
-        for (uint32_t i = tid; i < nbins; i += stride) d.cell_start[i] = 0;
-        const uint32_t ntiles = (nbins + 2047u) / 2048u;
-        for (uint32_t i = tid; i < ntiles + 1; i += stride) d.scan_state[i] = 0ull;
+        float any = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) any += fabsf(b.local_inv_mass[k]) + fabsf(b.linvel[k]) + fabsf(b.angvel[k]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) any += fabsf(b.local_inv_inertia[k]);
+        b.needs_impulse = (any != 0.0f || any != any) ? 1u : 0u;
     }
-    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-    const uint32_t id = threadIdx.x;
-    if (id == 0) {
-        Counters* c = d.counters;
-        c->num_active_blocks = 0;
-        c->scan_ticket = 0;
-        c->work_p2g = 0;
-        c->work_p2g_cpic = 0;
-        c->work_g2p = 0;
-        c->work_cdf = 0;
-        c->num_cpic_blocks = 0;
-        c->num_g2p_items = 0;
-        c->num_g2p_back = 0;
-        c->num_p2g_front = 0;
-        c->num_p2g_back = 0;
-        c->g2p_done = 0;
-        c->num_p2g_stages = 0;
-        c->dropped_particles = 0;
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        float s = b.rot[r] * b.local_com[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) s = s + b.rot[k * D + r] * b.local_com[k];
+        b.com[r] = s + b.trans[r];
     }
-    if (id < d.sim->num_bodies) {
-        BodyDev& b = d.bodies[id];
-        {
-            float any = 0.0f;
+    if (D == 2) {
+        b.inv_inertia[0] = b.local_inv_inertia[0];
+    } else {
+        // W = R * I * R^T (all column-major 3x3)
+        float RI[9];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) any += fabsf(b.local_inv_mass[k]) + fabsf(b.linvel[k]) + fabsf(b.angvel[k]);
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) any += fabsf(b.local_inv_inertia[k]);
-            b.needs_impulse = (any != 0.0f || any != any) ? 1u : 0u;
-        }
+            for (int r = 0; r < 3; ++r) {
+                float s = 0.0f;
 #pragma unroll
-        for (int r = 0; r < D; ++r) {
-            float s = b.rot[r] * b.local_com[0];
+                for (int k = 0; k < 3; ++k) s += b.rot[k * 3 + r] * b.local_inv_inertia[c * 3 + k];
+                RI[c * 3 + r] = s;
+            }
 #pragma unroll
-            for (int k = 1; k < D; ++k) s = s + b.rot[k * D + r] * b.local_com[k];
-            b.com[r] = s + b.trans[r];
-        }
-        if (D == 2) {
-            b.inv_inertia[0] = b.local_inv_inertia[0];
-        } else {
-            // W = R * I * R^T (all column-major 3x3)
-            float RI[9];
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) {
+                float s = 0.0f;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    float s = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) s += b.rot[k * 3 + r] * b.local_inv_inertia[c * 3 + k];
-                    RI[c * 3 + r] = s;
-                }
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    float s = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) s += RI[k * 3 + r] * b.rot[k * 3 + c]; // R^T[k][c] = R[c][k]
-                    b.inv_inertia[c * 3 + r] = s;
-                }
-        }
+                for (int k = 0; k < 3; ++k) s += RI[k * 3 + r] * b.rot[k * 3 + c]; // R^T[k][c] = R[c][k]
+                b.inv_inertia[c * 3 + r] = s;
+            }
     }
+}
+template <int D>
+__global__ void k_refresh_bodies(DeviceData d) {
+    if (threadIdx.x < d.sim->num_bodies) refresh_body<D>(d.bodies[threadIdx.x]);
+}
+
+// ---- reset_hmap (grid.wgsl:186-203) + clearing of the last sort's per-cell bins -------------------------------------
+// Leaves the sparse grid ready for the next k_touch. It does not sit at the top of a substep: nothing after P2G (and
+// the halo exchange of sharded runs) reads the hash map or the bins any more - G2P works from its item list - so the
+// substep graph runs it on a side branch next to k_g2p, off the critical path (api.cu, finish_substep).
+__global__ void __launch_bounds__(256) k_begin_substep(DeviceData d) {
+    TL_BEGIN(d, B200MPM_KERNEL_BEGIN);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < d.capacity; i += stride) d.hkeys[i] = NONE;
+    // prev_active_blocks was published by the last k_scatter (0 before the first sort: the arrays are
+    // zero-initialised at creation)
+    const uint32_t prev = min(d.counters->prev_active_blocks, d.capacity);
+    const uint32_t nbins = prev * CELLS_PER_BLOCK + 1;
+    for (uint32_t i = tid; i < nbins; i += stride) d.cell_start[i] = 0;
+    if (tid == 0) d.counters->num_active_blocks = 0;
+    TL_END(d, B200MPM_KERNEL_BEGIN);
 }
 
 __device__ inline void quat_to_rot(const float* q, float* R) { // column-major
@@ -109,8 +99,15 @@ __device__ inline void complex_to_rot(const float* c, float* R) {
 // ---- update (rigid_impulses.wgsl:94-137) ---------------------------------------------------------------
 template <int D>
 __global__ void k_integrate_bodies(DeviceData d) {
+    pdl_start();
+    TL_BEGIN(d, B200MPM_KERNEL_INTEGRATE_BODIES);
     const uint32_t id = threadIdx.x;
-    if (id >= d.sim->num_bodies) return;
+    // Runs once per substep - at its end, or (single-GPU graph) deferred to the start of the next one, beside the
+    // sort - and is a no-op when nothing is pending (the flush at the end of b200mpm_step after an in-place integrate).
+    const bool pending = d.counters->integrate_pending != 0u;
+    __syncwarp();
+    if (id == 0) d.counters->integrate_pending = 0u;
+    if (!pending || id >= d.sim->num_bodies) return;
     BodyDev& b = d.bodies[id];
     const float dt = d.sim->dt, h = d.sim->cell_width;
     float il[3] = {0, 0, 0}, ia[3] = {0, 0, 0};
@@ -228,6 +225,8 @@ __global__ void k_integrate_bodies(DeviceData d) {
         b.linvel[k] = lin[k];
         b.angvel[k] = ang[k];
     }
+    refresh_body<D>(b); // world-space mass properties of the new pose, for the next substep
+    TL_END(d, B200MPM_KERNEL_INTEGRATE_BODIES);
 }
 
 // ---- host writes / reads of body state (src_testbed/step.rs:79-119,175-176) ------------------------------
@@ -240,7 +239,9 @@ __global__ void k_write_poses(DeviceData d, const b200mpm_pose* poses, uint32_t 
     for (int k = 0; k < 4; ++k) b.rot_raw[k] = poses[id].rotation[k];
     if (D == 2) complex_to_rot(b.rot_raw, b.rot);
     else quat_to_rot(b.rot_raw, b.rot);
+    refresh_body<D>(b);
 }
+template <int D>
 __global__ void k_write_vels(DeviceData d, const b200mpm_velocity* vels, uint32_t n) {
     uint32_t id = threadIdx.x;
     if (id >= n || id >= d.sim->num_bodies) return;
@@ -249,6 +250,7 @@ __global__ void k_write_vels(DeviceData d, const b200mpm_velocity* vels, uint32_
         b.linvel[k] = vels[id].linear[k];
         b.angvel[k] = vels[id].angular[k];
     }
+    refresh_body<D>(b);
 }
 __global__ void k_read_poses(DeviceData d, b200mpm_pose* poses, b200mpm_velocity* vels, uint32_t n) {
     uint32_t id = threadIdx.x;
@@ -414,16 +416,16 @@ __global__ void k_gather_sorted_ids(DeviceData d, int cur, int indirect, uint32_
 // Grid in reference form: velocities after the grid update (grid_update.wgsl:20-64) + node cdf.
 template <int D>
 __global__ void k_gather_grid(DeviceData d, b200mpm_block_info* blocks, b200mpm_node* nodes, uint32_t max_blocks) {
-    const uint32_t nb = min(min(d.counters->num_active_blocks, d.capacity), max_blocks);
+    const uint32_t nb = min(min(d.counters->prev_active_blocks, d.capacity), max_blocks);
     const uint32_t t = threadIdx.x;
     const float dt = d.sim->dt, h = d.sim->cell_width;
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
         if (t == 0) {
             int4 vid = d.block_vid[b];
             blocks[b].vid[0] = vid.x, blocks[b].vid[1] = vid.y, blocks[b].vid[2] = vid.z;
-            uint32_t first = d.cell_start[b * CELLS_PER_BLOCK];
-            blocks[b].first_particle = first;
-            blocks[b].num_particles = d.cell_start[(b + 1) * CELLS_PER_BLOCK] - first;
+            const uint2 range = d.block_range[b];
+            blocks[b].first_particle = range.x;
+            blocks[b].num_particles = range.y;
         }
         float4 mv = d.node_mv[b * CELLS_PER_BLOCK + t];
         float mass = (D == 3) ? mv.w : mv.z;
@@ -454,15 +456,27 @@ __global__ void k_gather_grid(DeviceData d, b200mpm_block_info* blocks, b200mpm_
 // ---- launch wrappers ------------------------------------------------------------------------------------------
 static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
 
+bool pdl_enabled() {
+    static const bool on = []() {
+        const char* e = getenv("B200MPM_NO_PDL");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
+}
+
 void launch_begin_substep(const LaunchCfg& c, const DeviceData& d) {
-    if (c.dim == 2) k_begin_substep<2><<<c.num_sms * 2, 256, 0, c.stream>>>(d);
-    else k_begin_substep<3><<<c.num_sms * 2, 256, 0, c.stream>>>(d);
+    k_begin_substep<<<c.num_sms * 2, 256, 0, c.stream>>>(d);
+    ++*c.launch_counter;
+}
+void launch_refresh_bodies(const LaunchCfg& c, const DeviceData& d) {
+    if (c.dim == 2) k_refresh_bodies<2><<<1, 32, 0, c.stream>>>(d);
+    else k_refresh_bodies<3><<<1, 32, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
 void launch_integrate_bodies(const LaunchCfg& c, const DeviceData& d) {
     if (!d.has_bodies) return;
-    if (c.dim == 2) k_integrate_bodies<2><<<1, 32, 0, c.stream>>>(d);
-    else k_integrate_bodies<3><<<1, 32, 0, c.stream>>>(d);
+    if (c.dim == 2) launch_pdl(k_integrate_bodies<2>, 1, 32, 0, c.stream, d);
+    else launch_pdl(k_integrate_bodies<3>, 1, 32, 0, c.stream, d);
     ++*c.launch_counter;
 }
 void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, float4* out, int unordered) {
@@ -499,7 +513,8 @@ void launch_write_poses(const LaunchCfg& c, const DeviceData& d, const b200mpm_p
     ++*c.launch_counter;
 }
 void launch_write_vels(const LaunchCfg& c, const DeviceData& d, const b200mpm_velocity* vels, uint32_t n) {
-    k_write_vels<<<1, 32, 0, c.stream>>>(d, vels, n);
+    if (c.dim == 2) k_write_vels<2><<<1, 32, 0, c.stream>>>(d, vels, n);
+    else k_write_vels<3><<<1, 32, 0, c.stream>>>(d, vels, n);
     ++*c.launch_counter;
 }
 void launch_read_poses(const LaunchCfg& c, const DeviceData& d, b200mpm_pose* poses, b200mpm_velocity* vels, uint32_t n) {

@@ -129,10 +129,9 @@ __global__ void k_write_headers(Counters* c, void* left, void* right, uint32_t c
 // resets the pack counters, snapshots the live count (immigrants are appended there) and advances the sequence.
 __global__ void k_shard_tick(DeviceData d) {
     Counters* c = d.counters;
-    if (c->shard_seq > 0u) {
-        const uint32_t nb = min(c->num_active_blocks, d.capacity);
-        c->n_live = d.cell_start[nb * CELLS_PER_BLOCK];
-    }
+    // (the sorted total comes from its own counter, not from the bins: a grid reallocation between two substeps
+    // replaces the bins, and k_begin_substep has cleared them by now anyway)
+    if (c->shard_seq > 0u) c->n_live = c->sorted_total;
     c->send_count[0] = c->send_count[1] = 0;
     c->halo_count[0] = c->halo_count[1] = 0;
     c->n_base = c->n_live;
@@ -210,8 +209,7 @@ __global__ void k_wait(const Counters* c, const uint32_t* from_left, const uint3
 // After a substep the next buffer holds the sorted live particles in [0, total) and the parked (dead) ones after:
 // dropping the tail removes the emigrants.
 __global__ void k_drop_dead_tail(DeviceData d) {
-    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-    d.counters->n_live = d.cell_start[nb * CELLS_PER_BLOCK];
+    d.counters->n_live = d.counters->sorted_total;
 }
 
 // Packs the node momenta of the active blocks of the shared columns (x == slab_lo -> buffer 0, x == slab_hi ->

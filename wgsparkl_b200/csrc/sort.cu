@@ -17,8 +17,10 @@
 namespace b2 {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+// Large tiles: the scan covers ~200 k bins per million particles, so with 8192-bin tiles every tile finds all its
+// predecessors in ONE look-back round of 32 (the kernel is a latency chain, not a bandwidth problem).
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 uint32_t scan_num_tiles(uint64_t len) { return (uint32_t)((len + SCAN_TILE - 1) / SCAN_TILE); }
@@ -75,6 +77,8 @@ constexpr int SORT_PER_CTA = SORT_THREADS * SORT_ITEMS;
 
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
+    pdl_start();
+    TL_BEGIN(d, B200MPM_KERNEL_TOUCH);
     constexpr int NA = Dim<D>::NASSOC, WARPS = SORT_THREADS / 32, PER_ROUND = 32 / NA;
     __shared__ int4 s_lead[WARPS][SORT_PER_WARP]; // run leaders of a warp: block (x, y, z), then the slot in .w
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
             d.pkey[i] = pk;
         }
     }
-
+    TL_END(d, B200MPM_KERNEL_TOUCH);
 }
 
 // ---- rigid particles (sample points of trimesh / polyline colliders) ---------------------------------------
@@ -171,11 +175,11 @@ __global__ void k_transform_rigid(DeviceData d) {
     const float lp[3] = {l.x, l.y, l.z};
     float w[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < D; ++r) {
-        float s = b.rot[r] * lp[0];
+    for (int r = 0; r < D; ++r) { // (contraction-free: the vertices feed the integer-valued colouring of k_p2g_cdf)
+        float s = __fmul_rn(b.rot[r], lp[0]);
 #pragma unroll
-        for (int k = 1; k < D; ++k) s = s + b.rot[k * D + r] * lp[k];
-        w[r] = s + b.trans[r];
+        for (int k = 1; k < D; ++k) s = __fadd_rn(s, __fmul_rn(b.rot[k * D + r], lp[k]));
+        w[r] = __fadd_rn(s, b.trans[r]);
     }
     (vertex ? d.mv_world : d.rp_world)[j] = make_float4(w[0], w[1], w[2], 0.f);
 }
@@ -266,25 +270,28 @@ __global__ void k_p2g_cdf(DeviceData d) {
         bool sign;
         if (D == 2) {
             // wgparry Segment::projectLocalPoint, then p2g_cdf.wgsl:143-158
+            // (contraction-free arithmetic: the outcome is a set of affinity / sign BITS)
             const float abx = Bv.x - A.x, aby = Bv.y - A.y, apx = px - A.x, apy = py - A.y;
-            const float ab_ap = abx * apx + aby * apy, sqnab = abx * abx + aby * aby;
+            const float ab_ap = __fadd_rn(__fmul_rn(abx, apx), __fmul_rn(aby, apy));
+            const float sqnab = __fadd_rn(__fmul_rn(abx, abx), __fmul_rn(aby, aby));
             if (ab_ap <= 0.0f || ab_ap >= sqnab) continue; // projects on an end point
-            const float t = ab_ap / sqnab;
-            const float qx = A.x + abx * t, qy = A.y + aby * t;
+            const float t = __fdiv_rn(ab_ap, sqnab);
+            const float qx = __fadd_rn(A.x, __fmul_rn(abx, t)), qy = __fadd_rn(A.y, __fmul_rn(aby, t));
             if ((qx == A.x && qy == A.y) || (qx == Bv.x && qy == Bv.y)) continue;
             const float dx = px - qx, dy = py - qy;
-            distance = sqrtf(dx * dx + dy * dy);
-            sign = (dx * -aby + dy * abx) < 0.0f;
+            distance = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+            sign = __fadd_rn(__fmul_rn(dx, -aby), __fmul_rn(dy, abx)) < 0.0f;
         } else {
             // p2g_cdf.wgsl:160-188: projection on the face interior only
             const V3 a = v3(A.x, A.y, A.z), b = v3(Bv.x, Bv.y, Bv.z), c = v3(C.x, C.y, C.z), pt = v3(px, py, pz);
             const V3 ap = pt - a, bp = pt - b, cp = pt - c, ab = b - a, ac = c - a, bc = c - b;
-            const V3 nrm = cross(ab, ac);
-            const float n_length = length(nrm);
-            if (!(n_length != 0.0f && dot(cross(ab, nrm), ap) <= 0.0f && dot(cross(bc, nrm), bp) <= 0.0f &&
-                  dot(cross(ac, nrm), cp) >= 0.0f))
+            // (contraction-free arithmetic: the outcome is a set of affinity / sign BITS)
+            const V3 nrm = cross_rn(ab, ac);
+            const float n_length = sqrtf(dot_rn(nrm, nrm));
+            if (!(n_length != 0.0f && dot_rn(cross_rn(ab, nrm), ap) <= 0.0f && dot_rn(cross_rn(bc, nrm), bp) <= 0.0f &&
+                  dot_rn(cross_rn(ac, nrm), cp) >= 0.0f))
                 continue;
-            const float signed_dist = dot(nrm, ap) / n_length;
+            const float signed_dist = __fdiv_rn(dot_rn(nrm, ap), n_length);
             sign = signed_dist < 0.0f;
             distance = fabsf(signed_dist);
         }
@@ -297,6 +304,30 @@ __global__ void k_p2g_cdf(DeviceData d) {
 
 // ---- update_block_particle_count (sort.wgsl:89-99), one bin per cell ---------------------------------
 __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
+    pdl_start();
+    TL_BEGIN(d, B200MPM_KERNEL_COUNT);
+    {
+        // Housekeeping for the kernels that follow (nobody reads these before k_scan / k_scatter, and the readers of
+        // the last substep are long done): the work-list counters and the scan's tile descriptors.
+        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+        if (tid == 0) {
+            Counters* c = d.counters;
+            c->scan_ticket = 0;
+            c->work_p2g = 0;
+            c->work_p2g_cpic = 0;
+            c->work_g2p = 0;
+            c->work_cdf = 0;
+            c->num_cpic_blocks = 0;
+            c->num_g2p_items = 0;
+            c->num_g2p_back = 0;
+            c->num_p2g_front = 0;
+            c->num_p2g_back = 0;
+            c->dropped_particles = 0;
+        }
+        const uint32_t nbins = min(d.counters->num_active_blocks, d.capacity) * CELLS_PER_BLOCK + 1;
+        const uint32_t ntiles = (nbins + SCAN_TILE - 1u) / SCAN_TILE;
+        for (uint32_t i = tid; i < ntiles + 1u; i += gridDim.x * blockDim.x) d.scan_state[i] = 0ull;
+    }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SORT_PER_WARP;
     const uint32_t n_live = d.counters->n_live;
@@ -337,18 +368,18 @@ __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
             d.rank[i] = b + (lane - (uint32_t)lead[j]);
         }
     }
+    TL_END(d, B200MPM_KERNEL_COUNT);
 }
 
 // ---- exclusive scan, single pass with decoupled look-back (replaces prefix_sum.wgsl) -----------------
 // Same result as WgPrefixSum::eval_cpu (prefix_sum.rs:71-83): out[i] = sum_{j<i} in[j].
-// group_max (optional): the largest input value of every aligned group of 32 inputs = the longest cell run of every half
-// block, which sizes the P2G stage table (k_scatter) - the inputs are in registers here anyway.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t len_value,
                                                        const Counters* __restrict__ counters, uint32_t capacity,
-                                                       uint64_t* state, uint32_t* ticket, uint32_t* __restrict__ group_max) {
+                                                       uint64_t* state, uint32_t* ticket) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_prefix;
+    pdl_start();
     const uint32_t len = counters ? (min(counters->num_active_blocks, capacity) * CELLS_PER_BLOCK + 1) : len_value;
     // The grid is sized for the worst case (capacity); CTAs beyond the live tiles leave without a ticket, so
     // the tickets handed out are exactly 0 .. ntiles-1 and the same-address atomic stays cheap.
@@ -361,21 +392,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
     const uint32_t t0 = base + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t sum = 0;
+    if (t0 + SCAN_ITEMS <= len && (reinterpret_cast<uintptr_t>(data) & 15u) == 0u) { // (t0 is a multiple of SCAN_ITEMS)
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        v[j] = (t0 + j < len) ? data[t0 + j] : 0u;
-        sum += v[j];
+        for (int j = 0; j < SCAN_ITEMS; j += 4) {
+            const uint4 q = *reinterpret_cast<const uint4*>(data + t0 + j);
+            v[j] = q.x, v[j + 1] = q.y, v[j + 2] = q.z, v[j + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (t0 + j < len) ? data[t0 + j] : 0u;
     }
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) sum += v[j];
     // inclusive warp scan of the per-thread sums
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (group_max) { // 4 consecutive threads hold one group of 32 inputs (SCAN_ITEMS == 8)
-        uint32_t m = 0;
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) m = max(m, v[j]);
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        if ((lane & 3u) == 0u && t0 + 31u < len) group_max[t0 >> 5] = m;
-    }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -420,10 +450,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
     }
     __syncthreads();
     uint32_t excl = s_prefix + warp_off + (inc - sum);
+    if (t0 + SCAN_ITEMS <= len && (reinterpret_cast<uintptr_t>(data) & 15u) == 0u) {
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        if (t0 + j < len) data[t0 + j] = excl;
-        excl += v[j];
+        for (int j = 0; j < SCAN_ITEMS; j += 4) {
+            uint4 q;
+            q.x = excl, excl += v[j];
+            q.y = excl, excl += v[j + 1];
+            q.z = excl, excl += v[j + 2];
+            q.w = excl, excl += v[j + 3];
+            *reinterpret_cast<uint4*>(data + t0 + j) = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            if (t0 + j < len) data[t0 + j] = excl;
+            excl += v[j];
+        }
     }
 }
 
@@ -434,6 +476,7 @@ namespace b2 {
 
 template <int D>
 __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_block_prepare(DeviceData d) {
+    TL_BEGIN(d, B200MPM_KERNEL_BLOCK_PREPARE);
     const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
     const uint32_t t = threadIdx.x;
     const float h = d.sim->cell_width;
@@ -457,13 +500,19 @@ __global__ void __launch_bounds__(CELLS_PER_BLOCK) k_block_prepare(DeviceData d)
             if (t == 0) d.block_f0[b] = any ? 1 : 0;
         }
     }
+    TL_END(d, B200MPM_KERNEL_BLOCK_PREPARE);
 }
 
 // ---- finalize_particles_sort (sort.wgsl:117-137): atomic-free scatter ------------------------------
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur) {
+    pdl_start();
+    TL_BEGIN(d, B200MPM_KERNEL_SCATTER);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) d.counters->prev_active_blocks = min(d.counters->num_active_blocks, d.capacity); // for the next clear
+    if (i == 0) {
+        d.counters->prev_active_blocks = min(d.counters->num_active_blocks, d.capacity); // for the host and the next clear
+        d.counters->integrate_pending = 1u; // this substep's body impulses / poses are still to be integrated
+    }
     {
         // Per-block work lists (i doubles as a block index here; the grid covers capacity blocks).
         const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
@@ -472,6 +521,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
         if (i < nb) {
             first = d.cell_start[i * CELLS_PER_BLOCK];
             np = d.cell_start[(i + 1) * CELLS_PER_BLOCK] - first;
+            d.block_range[i] = make_uint2(first, np);
         }
         uint32_t nbr[8];
 #pragma unroll
@@ -529,25 +579,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
         const uint32_t pf = reserve((p2g_mine && dense) ? 1u : 0u, &d.counters->num_p2g_front);
         const uint32_t pb = reserve((p2g_mine && !dense) ? 1u : 0u, &d.counters->num_p2g_back);
         if (p2g_mine) d.p2g_list[dense ? pf : d.capacity - 1u - pb] = i;
-        // P2G stage table (k_p2g_fast): a half block needs ceil(longest cell run / P2G_K) stages (k_scan left the
-        // longest run of every half block in half_max).
-        if (p2g_mine) {
-#pragma unroll
-            for (uint32_t half = 0; half < 2u; ++half) {
-                const uint32_t nst = (d.half_max[2u * i + half] + P2G_K - 1u) / P2G_K;
-                if (nst) {
-                    const uint32_t base = atomicAdd(&d.counters->num_p2g_stages, nst);
-                    for (uint32_t st = 0; st < nst && base + st < d.p2g_stages_cap; ++st)
-                        d.p2g_stages[base + st] = make_uint2(i | (half << 31), st | (nst << 16));
-                }
-            }
-        }
     }
     // particles: SORT_ITEMS per thread, see k_touch
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SORT_PER_WARP;
     const uint32_t n_live = d.counters->n_live;
-    if (warp_base >= n_live) return;
+    if (warp_base >= n_live) {
+        TL_END(d, B200MPM_KERNEL_SCATTER);
+        return;
+    }
     uint32_t ck[SORT_ITEMS], rk[SORT_ITEMS], dest[SORT_ITEMS];
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS; ++j) {
@@ -571,8 +611,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
             uint32_t total = d.cell_start[nb * CELLS_PER_BLOCK];
             uint32_t k = atomicAdd(&d.counters->dropped_particles, 1u);
             d.sorted_ids[total + k] = p;
+            // a LIVE particle without a block (capacity / hash overflow): sharded runs compact the parked tail away
+            // together with the emigrants, so the loss is reported (bit 2 of the overflow word)
+            if ((__float_as_uint(d.pos4[cur][p].w) & FLAG_DEAD) == 0u) atomicOr(&d.counters->overflow, 4u);
         }
     }
+    TL_END(d, B200MPM_KERNEL_SCATTER);
 }
 
 // ---- launch wrappers ------------------------------------------------------------------------------------
@@ -580,8 +624,8 @@ static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b)
 
 void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
-    if (c.dim == 2) k_touch<2><<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d, cur);
-    else k_touch<3><<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d, cur);
+    if (c.dim == 2) launch_pdl(k_touch<2>, div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream, d, cur);
+    else launch_pdl(k_touch<3>, div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream, d, cur);
     ++*c.launch_counter;
 }
 void launch_transform_rigid(const LaunchCfg& c, const DeviceData& d) {
@@ -612,7 +656,7 @@ void launch_p2g_cdf(const LaunchCfg& c, const DeviceData& d) {
 }
 void launch_count(const LaunchCfg& c, const DeviceData& d) {
     if (d.n == 0) return;
-    k_count<<<div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream>>>(d);
+    launch_pdl(k_count, div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream, d);
     ++*c.launch_counter;
 }
 void launch_scan_cells(const LaunchCfg& c, const DeviceData& d) {
@@ -620,9 +664,8 @@ void launch_scan_cells(const LaunchCfg& c, const DeviceData& d) {
     uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
     if (max_blocks > d.capacity) max_blocks = d.capacity;
     uint32_t tiles = scan_num_tiles(max_blocks * CELLS_PER_BLOCK + 1);
-    static_assert(SCAN_ITEMS == 8, "k_scan derives the per-half-block maxima from groups of 4 threads");
-    k_scan<<<tiles, SCAN_THREADS, 0, c.stream>>>(d.cell_start, 0u, d.counters, d.capacity, d.scan_state,
-                                                  &d.counters->scan_ticket, d.half_max);
+    launch_pdl(k_scan, tiles, SCAN_THREADS, 0, c.stream, d.cell_start, 0u, (const Counters*)d.counters, d.capacity, d.scan_state,
+               &d.counters->scan_ticket);
     ++*c.launch_counter;
 }
 void launch_block_prepare(const LaunchCfg& c, const DeviceData& d) {
@@ -639,8 +682,8 @@ void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (max_blocks > d.capacity) max_blocks = d.capacity;
     uint64_t ctas_p = div_up(d.n, SORT_PER_CTA), ctas_b = div_up(max_blocks, SORT_THREADS);
     int ctas = (int)(ctas_p > ctas_b ? ctas_p : ctas_b);
-    if (c.dim == 2) k_scatter<2><<<ctas, SORT_THREADS, 0, c.stream>>>(d, cur);
-    else k_scatter<3><<<ctas, SORT_THREADS, 0, c.stream>>>(d, cur);
+    if (c.dim == 2) launch_pdl(k_scatter<2>, ctas, SORT_THREADS, 0, c.stream, d, cur);
+    else launch_pdl(k_scatter<3>, ctas, SORT_THREADS, 0, c.stream, d, cur);
     ++*c.launch_counter;
 }
 void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len, uint64_t* scan_state,
@@ -649,7 +692,7 @@ void launch_exclusive_scan_u32(const LaunchCfg& c, uint32_t* data, uint32_t len,
     uint32_t tiles = scan_num_tiles(len);
     cudaMemsetAsync(scan_state, 0, sizeof(uint64_t) * (tiles + 1), c.stream);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), c.stream);
-    k_scan<<<tiles, SCAN_THREADS, 0, c.stream>>>(data, len, nullptr, 0u, scan_state, ticket, nullptr);
+    k_scan<<<tiles, SCAN_THREADS, 0, c.stream>>>(data, len, nullptr, 0u, scan_state, ticket);
     ++*c.launch_counter;
 }
 

@@ -47,6 +47,8 @@ EXPORTS = (
     "b200mpm_sync",
     "b200mpm_set_timestamps",
     "b200mpm_get_timings",
+    "b200mpm_get_kernel_timings",
+    "b200mpm_debug_timeline",
     "b200mpm_write_sim_params",
     "b200mpm_write_body_poses",
     "b200mpm_write_body_vels",
@@ -119,6 +121,8 @@ def load_library():
     L.b200mpm_sync.argtypes = [vp]
     L.b200mpm_set_timestamps.argtypes = [vp, i32]
     L.b200mpm_get_timings.argtypes = [vp, vp]
+    L.b200mpm_get_kernel_timings.argtypes = [vp, vp]
+    L.b200mpm_debug_timeline.argtypes = [vp, vp]
     L.b200mpm_write_sim_params.argtypes = [vp, vp]
     for name in ("b200mpm_write_body_poses", "b200mpm_write_body_vels", "b200mpm_read_body_poses",
                  "b200mpm_read_body_vels"):
@@ -229,6 +233,12 @@ class MpmPipeline:
         out = np.zeros(len(abi.PASS_NAMES), dtype=np.float64)
         _check(load_library().b200mpm_get_timings(self._h, abi.ptr(out)))
         return dict(zip(abi.PASS_NAMES, out.tolist()))
+
+    def kernel_timings_ms(self):
+        """Accumulated milliseconds per kernel of this implementation (timestamps mode; abi.KERNEL_NAMES)."""
+        out = np.zeros(len(abi.KERNEL_NAMES), dtype=np.float64)
+        _check(load_library().b200mpm_get_kernel_timings(self._h, abi.ptr(out)))
+        return dict(zip(abi.KERNEL_NAMES, out.tolist()))
 
     def launch_count(self) -> int:
         return int(load_library().b200mpm_pipeline_launch_count(self._h))
@@ -361,6 +371,17 @@ class MpmData:
         if code not in (OK, ERR_GRID_OVERFLOW):
             _check(code)
         return int(nb.value), code == ERR_GRID_OVERFLOW
+
+    def debug_timeline(self):
+        """{kernel: (first start, last end)} in GPU nanoseconds since the last call (libraries built with
+        -DB200MPM_TIMELINE only; None for kernels that did not run)."""
+        raw = np.zeros(2 * len(abi.KERNEL_NAMES), dtype=np.uint64)
+        _check(load_library().b200mpm_debug_timeline(self._h, abi.ptr(raw)))
+        out = {}
+        for k, name in enumerate(abi.KERNEL_NAMES):
+            a, b = int(raw[2 * k]), int(raw[2 * k + 1])
+            out[name] = None if b == 0 else (a, b)
+        return out
 
     def read_grid(self):
         nb, _ = self.status()
