@@ -17,8 +17,8 @@ column, the mixed scene and one 2M dam slab alone (the like-for-like base of the
 `scaling_base` (one dam slab alone on rank 0's GPU) and `also.dam_strong` (the 16M dam over the same N GPUs).
 
 Particle state is resident in HBM when a timed region starts (it lives there in the reference too: src/pipeline.rs:
-130-168 uploads once). K steps are timed `repeats` times (>= 5, more until >= 1 s has been timed); `value` is the
-MEDIAN region. `e2e` times the same frames through the C ABI with HOST buffers: per frame the body poses and
+130-168 uploads once). K steps are timed five times (at N = 1 every region restarts the scene, so all five cover the same frames);
+`value` is the MEDIAN region. `e2e` times the same frames through the C ABI with HOST buffers: per frame the body poses and
 velocities are uploaded from host memory (src_testbed/step.rs:79-119) and the body poses plus all particle positions
 are read back into pinned host memory.
 
@@ -248,13 +248,7 @@ def make_timer(torch, dist, world, stream):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    def timed_median(fn, steps, finish=None, min_repeats=5, min_total_ms=1000.0, max_repeats=25):
-        samples = []
-        while len(samples) < min_repeats or (sum(samples) < min_total_ms and len(samples) < max_repeats):
-            samples.append(timed(fn, steps, finish))
-        return float(np.median(samples)), samples
-
-    return timed, timed_median
+    return timed, None
 
 
 def kernel_roofline(runner, workload, hbm_peak, peak_kind, frames):
@@ -369,26 +363,37 @@ def run_ours(args):
             data.read_positions_unordered_async(host_pos[e2e_slot[0]])  # this rank's slab, same pattern
         e2e_slot[0] ^= 1
 
-    for _ in range(args.warmup):
-        runner.frame()
+    # The cost of a frame depends on the state (the cube's substep costs 2.4x more at peak compression than in the first
+    # frames of contact), so at N = 1 every timed region covers the SAME frames of the same trajectory: the data object
+    # is rebuilt from the scene, W warm-up frames, then the K timed frames (frames W .. W+K, as in round 1) - five
+    # times, median. A sharded run (expensive to rebuild, and the dam barely changes within 5 K frames) continues.
+    REPEATS = 5
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = pipe.launch_count()
-    ms, samples = timed_median(runner.frame, args.steps)
-    launches = (pipe.launch_count() - l0) // len(samples)
+    samples, samples_e2e, launches = [], [], 0
+    for r in range(REPEATS):
+        if runner.sharded is None and r > 0:
+            runner.rebuild()
+        if r == 0 or runner.sharded is None:
+            for _ in range(args.warmup):
+                runner.frame()
+        l0 = pipe.launch_count()
+        samples.append(timed(runner.frame, args.steps))
+        launches = pipe.launch_count() - l0
+    ms = float(np.median(samples))
     value = n_total * spf * args.steps / (ms * 1e-3)
 
-    # End-to-end through the C ABI with host buffers, over the same kind of frames (at N = 1 the data object is rebuilt
-    # from the scene and warmed up again so that the trajectory starts over; a sharded run continues from where it is).
-    if runner.sharded is None:
-        runner.rebuild()
-        for _ in range(args.warmup):
-            frame_e2e()
-    else:
-        frame_e2e()
-    ms_e2e, samples_e2e = timed_median(frame_e2e, args.steps, finish=pipe.sync)
-    clocks = sampler.stop() if rank == 0 else None  # sampled (100 ms period) over both timed regions
+    # End-to-end through the C ABI with host buffers, over the same frames (same restart rule).
+    for r in range(REPEATS):
+        if runner.sharded is None:
+            runner.rebuild()
+        if r == 0 or runner.sharded is None:
+            for _ in range(args.warmup if runner.sharded is None else 1):
+                frame_e2e()
+        samples_e2e.append(timed(frame_e2e, args.steps, finish=pipe.sync))
+    ms_e2e = float(np.median(samples_e2e))
+    clocks = sampler.stop() if rank == 0 else None  # sampled (100 ms period) over all timed regions
     e2e_value = n_total * spf * args.steps / (ms_e2e * 1e-3)
     nb = len(scene["bodies"])
     h2d = nb * (poses.dtype.itemsize + vels.dtype.itemsize)
@@ -410,8 +415,9 @@ def run_ours(args):
                    "parallelism": "1 GPU" if world == 1 else
                    "%d slabs along x (particle migration + node-halo exchange over NVLink peer stores, body "
                    "impulses all-reduced over NCCL, every substep)" % world,
-                   "timing": "median of %d regions of %d steps each (CUDA events on the launching stream, max over ranks)"
-                             % (len(samples), args.steps),
+                   "timing": "median of %d regions of %d steps each (CUDA events on the launching stream, max over ranks)%s"
+                             % (len(samples), args.steps, "; every region restarts the scene and times frames %d..%d"
+                                % (args.warmup, args.warmup + args.steps) if world == 1 else ""),
                    "timed_regions_ms": samples, "timed_regions_e2e_ms": samples_e2e,
                    "l2": "inputs larger than L2 (%.0f MB of particle state per GPU)" % (n_total // world * 220 / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -426,6 +432,15 @@ def run_ours(args):
     extras = args.workload == "auto" and not args.no_extras
     if extras and world == 1:
         also = {}
+        try:  # cost profile of the cube along its trajectory (drop, compression, rebound): ms per 10 frames
+            tr = Runner(scene, 0, 1, local_rank, stream, shard=False)
+            prof = [timed(tr.frame, 10) for _ in range(16)]
+            tr.close()
+            also["cube_trajectory"] = {"ms_per_10_frames": prof, "substeps": 16 * 10 * spf,
+                                       "value_whole_trajectory": n_total * spf * 160 / (sum(prof) * 1e-3), "unit": UNIT,
+                                       "note": "160 frames from the initial state; the peak is the cube at maximal compression"}
+        except Exception as e:
+            also["cube_trajectory"] = {"error": repr(e)}
         for name, wl, warm, frames, blocks in (("column", "column", 0, 100, True), ("mixed", "mixed", 5, 10, False),
                                                ("dam_slab", "dam", 3, 10, False)):
             try:

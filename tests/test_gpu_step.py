@@ -401,3 +401,35 @@ def test_sixteen_colliders_of_every_shape(pipe3, oracle_mod):
     assert parity.field_rel_err(data.read_body_poses()["translation"], sim.read_body_poses()["translation"]) <= 1e-5
     assert parity.field_rel_err(data.read_body_vels()["linear"], sim.read_body_vels()["linear"]) <= 2e-3
     data.close()
+
+
+def test_2d_sand_with_ball_and_capsule_colliders(pipe2, oracle_mod):
+    """The reference's 2D sand scene at test size (sand2.rs:28-156): 2D Drucker-Prager (svd2 + the 2D return mapping,
+    drucker_prager.wgsl:43-64) next to kinematic BALL and CAPSULE colliders, a rotating cuboid and a dynamic cuboid."""
+    scene = scenes.sand_2d(60, 60)
+    parts, poses, vels = developed_state(oracle_mod, scene, 120)  # the block has fallen onto the colliders
+    assert (parts["cdf_affinity"] & 0b0110).any(), "the developed state must touch the ball and the capsule"
+    bodies = scene["bodies"].copy()
+    bodies["translation"] = poses["translation"]
+    bodies["rotation"] = poses["rotation"]
+    bodies["linvel"] = vels["linear"]
+    bodies["angvel"] = vels["angular"]
+    scene2 = dict(scene)
+    scene2["bodies"] = bodies
+    data, sim = one_substep_both(oracle_mod, pipe2, scene2, parts)
+    g, o = data.read_particles(), sim.read_particles()
+    gb, gn = data.read_grid()
+    ob, on = sim.read_grid()
+    parity.assert_grid_close(gb, gn, ob, on, TOL)
+    parity.assert_particles_close(g, o, TOL, fields=("position", "velocity", "def_grad"), tols={"position": 2e-6})
+    parity.assert_affine_close(g, o, 2, scene["cell_width"], float(scene["params"].dt))
+    assert np.array_equal(g["cdf_affinity"], o["cdf_affinity"])
+    for f in ("plastic_det", "plastic_hardening"):
+        assert parity.field_rel_err(g[f], o[f]) <= 1e-5, f
+    assert parity.field_rel_err(data.read_body_poses()["translation"], sim.read_body_poses()["translation"]) <= 1e-6
+    data.close()
+    # and 40 more substeps: positions stay within the sand bound
+    data, sim = one_substep_both(oracle_mod, pipe2, scene2, parts, n=40)
+    g, o = data.read_particles(), sim.read_particles()
+    assert parity.field_rel_err(g["position"], o["position"]) <= 1e-4
+    data.close()

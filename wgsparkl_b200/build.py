@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libb200mpm.so")
-SOURCES = ["api.cu", "sort.cu", "misc.cu", "cdf.cu", "p2g.cu", "g2p.cu", "shard.cu"]
+SOURCES = ["api.cu", "sort.cu", "misc.cu", "p2g.cu", "g2p.cu", "shard.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -98,6 +98,9 @@ struct b200mpm_data {
     bool bodies_react = false; // some body can react to an impulse (mass or motion): the impulse all-reduce is needed
     uint32_t n_live_host = 0; // host mirror of counters->n_live (sharded runs track it)
     bool sharded = false;
+    // The ORDERED read-backs scatter by original particle id into a buffer of num_particles entries: only valid when
+    // the ids are the default 0..n-1 and there is no spare capacity (b200mpm_data_create_ex may break both).
+    bool ordered_readback_ok = true;
     cudaStream_t side = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // Asynchronous position readback (b200mpm_read_positions_async): two device staging slots, a copy stream.
@@ -160,7 +163,7 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
     if ((r = dev_alloc(d, &dev.cpic_list, capacity, true, L))) return r;
     dev.g2p_items_len = capacity + d->particle_cap / G2P_ITEM + 1;
     if ((r = dev_alloc(d, &dev.g2p_items, dev.g2p_items_len, true, L))) return r;
-    if ((r = dev_alloc(d, &dev.p2g_list, capacity, true, L))) return r;
+    if ((r = dev_alloc(d, &dev.p2g_list, (size_t)P2G_BUCKETS * capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.block_range, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.scan_state, scan_num_tiles((uint64_t)capacity * CELLS_PER_BLOCK + 1) + 2, true, L))) return r;
     dev.capacity = capacity;
@@ -370,15 +373,7 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
     launch_scan_cells(c, dev);
     if (side) cudaStreamWaitEvent(main, d->ev[1], 0);
     launch_scatter(c, dev, d->cur);
-    if (side && dev.has_bodies) {
-        cudaEventRecord(d->ev[2], main);
-        cudaStreamWaitEvent(side, d->ev[2], 0);
-    }
-    launch_g2p_cdf(cs, dev, d->cur);
-    launch_p2g_cpic(cs, dev, d->cur);
-    if (side && dev.has_bodies) cudaEventRecord(d->ev[3], side);
-    launch_p2g(c, dev, d->cur);
-    if (side && dev.has_bodies) cudaStreamWaitEvent(main, d->ev[3], 0);
+    launch_p2g(c, dev, d->cur); // (with bodies: particle colouring "g2p_cdf" + collider-side blocks + all others, one kernel)
     if (phase == PHASE_BEGIN) return;
     finish_substep();
 }
@@ -453,20 +448,10 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
     run_sort(p, d);
     constexpr int K = B200MPM_NUM_PASSES;
     {
-        PassTimer t(p, B200MPM_PASS_G2P_CDF);
-        PassTimer k(p, K + B200MPM_KERNEL_G2P_CDF);
-        launch_g2p_cdf(c, d->dev, d->cur);
-    }
-    {
+        // (the "g2p_cdf" pass runs inside the P2G kernel, on the particles of collider-side blocks while they are staged)
         PassTimer t(p, B200MPM_PASS_P2G);
-        {
-            PassTimer k(p, K + B200MPM_KERNEL_P2G_CPIC);
-            launch_p2g_cpic(c, d->dev, d->cur);
-        }
-        {
-            PassTimer k(p, K + B200MPM_KERNEL_P2G);
-            launch_p2g(c, d->dev, d->cur);
-        }
+        PassTimer k(p, K + B200MPM_KERNEL_P2G);
+        launch_p2g(c, d->dev, d->cur);
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_SORT); // reset_hmap for the next substep (beside k_g2p in the graph)
@@ -595,6 +580,7 @@ int b200mpm_data_create_ex(b200mpm_pipeline* p, const b200mpm_sim_params* params
     dev.n = ncap;
     dev.capacity = capacity;
     d->n_live_host = n;
+    d->ordered_readback_ok = (particle_ids == nullptr) && (particle_capacity == num_particles);
     dev.has_bodies = num_bodies > 0;
 
     // ---- material table (dedup of the per-particle model buffers) + SoA staging on the host
@@ -1172,6 +1158,7 @@ int b200mpm_read_positions(b200mpm_data* d, float* out) {
     int r = ensure_staging(d, bytes);
     if (r) return r;
     if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_particles_unordered");
+    if (!d->ordered_readback_ok) return fail(B200MPM_ERR_INVALID_ARGUMENT, "created with custom particle ids or spare capacity: use the unordered read-backs");
     launch_gather_positions(p->cfg(), d->dev, d->cur, (float4*)d->staging);
     CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
@@ -1211,6 +1198,7 @@ int b200mpm_read_positions_async(b200mpm_data* d, float* out) {
     b200mpm_pipeline* p = d->pipe;
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_positions_unordered_async");
+    if (!d->ordered_readback_ok) return fail(B200MPM_ERR_INVALID_ARGUMENT, "created with custom particle ids or spare capacity: use the unordered read-backs");
     CU_TRY(cudaSetDevice(p->device));
     int r = ensure_async_readback(d);
     if (r) return r;
@@ -1238,7 +1226,8 @@ int b200mpm_prep_vertex_buffer(b200mpm_pipeline* p, b200mpm_data* d, b200mpm_ins
     if (!p || !d || d->pipe != p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "pipeline/data mismatch");
     if (!dev_instances && d->dev.n) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null instance buffer");
     if (mode > B200MPM_RENDER_CDF_SIGNS) return fail(B200MPM_ERR_INVALID_ARGUMENT, "unknown render mode");
-    if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data holds a changing subset of the particles");
+    if (d->sharded || !d->ordered_readback_ok)
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data / custom particle ids / spare capacity: the instance buffer is indexed by the default particle ids");
     CU_TRY(cudaSetDevice(p->device));
     cudaPointerAttributes attr{};
     if (d->dev.n && (cudaPointerGetAttributes(&attr, dev_instances) != cudaSuccess ||
@@ -1280,6 +1269,7 @@ int b200mpm_read_particles(b200mpm_data* d, b200mpm_particle* out) {
     int r = ensure_staging(d, bytes);
     if (r) return r;
     if (d->sharded) return fail(B200MPM_ERR_INVALID_ARGUMENT, "sharded data: use b200mpm_read_particles_unordered");
+    if (!d->ordered_readback_ok) return fail(B200MPM_ERR_INVALID_ARGUMENT, "created with custom particle ids or spare capacity: use the unordered read-backs");
     launch_gather_particles(p->cfg(), d->dev, d->cur, (b200mpm_particle*)d->staging, nullptr);
     CU_TRY(cudaMemcpyAsync(out, d->staging, bytes, cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
@@ -1336,6 +1326,8 @@ int b200mpm_read_sorted_ids(b200mpm_data* d, uint32_t* out) {
     b200mpm_pipeline* p = d->pipe;
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
+    if (!d->ordered_readback_ok || d->sharded)
+        return fail(B200MPM_ERR_INVALID_ARGUMENT, "created with custom particle ids or spare capacity: the sorted-id read-back needs the default layout");
     size_t bytes = (size_t)d->dev.n * sizeof(uint32_t);
     int r = ensure_staging(d, bytes);
     if (r) return r;

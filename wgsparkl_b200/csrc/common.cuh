@@ -83,6 +83,15 @@ struct SimState {
     int slab_lo, slab_hi; // this rank owns particles whose block x-index is in [slab_lo, slab_hi) (sharded runs)
 };
 
+// P2G work list: the blocks are bucketed by population (bucket 0: >= 7 * 96 particles ... bucket 7: < 96) and the
+// persistent warps walk the buckets in order - longest items first, so that the last scheduling round (a warp gets
+// ~3 half blocks per million particles) consists of the cheapest items instead of arbitrary ones.
+constexpr uint32_t P2G_BUCKETS = 8, P2G_BUCKET_STEP = 96;
+__host__ __device__ inline uint32_t p2g_bucket(uint32_t np) {
+    const uint32_t q = np / P2G_BUCKET_STEP;
+    return q >= P2G_BUCKETS - 1u ? 0u : P2G_BUCKETS - 1u - q;
+}
+
 // ---- device-resident counters --------------------------------------------------------------
 struct Counters {
     uint32_t num_active_blocks; // Grid.num_active_blocks (grid.wgsl:223)
@@ -104,8 +113,7 @@ struct Counters {
     uint32_t halo_count[2]; // blocks packed for the -x / +x neighbour (sharded runs)
     uint32_t shard_seq; // substep sequence number of the peer-to-peer exchange flags
     uint32_t n_base; // live count at the start of the substep: where the immigrants are appended
-    uint32_t num_p2g_front; // entries at the FRONT of p2g_list (densely populated blocks: long items first)
-    uint32_t num_p2g_back; // entries at the BACK of p2g_list, filled downwards from the end
+    uint32_t num_p2g[P2G_BUCKETS]; // entries of every population bucket of p2g_list (bucket 0 = most particles)
     uint32_t sorted_total; // particles in the sorted range this substep (== cell_start[num_active_blocks * 64])
     uint32_t integrate_pending; // a substep ran since the last k_integrate_bodies (which may be deferred, api.cu)
 };
@@ -174,7 +182,7 @@ struct DeviceData {
     G2PItem* g2p_items; // g2p_items_len work items of <= G2P_ITEM particles (collider-side blocks at the front)
     uint32_t g2p_items_len; // capacity + n / G2P_ITEM + 1
     uint2* block_range; // capacity: (first sorted slot, particle count) of every block (k_scatter; read-back helpers)
-    uint32_t* p2g_list; // capacity: blocks that hold particles and whose tile holds no collider (k_p2g<.., false, ..>)
+    uint32_t* p2g_list; // P2G_BUCKETS x capacity: blocks that hold particles and whose tile holds no collider, by bucket
 
     BodyDev* bodies;
     // Rigid particles = sample points of trimesh / polyline colliders (GpuRigidParticles, particle3d.rs:82-88) and

@@ -49,11 +49,9 @@ void launch_count(const LaunchCfg& c, const DeviceData& d);
 void launch_scan_cells(const LaunchCfg& c, const DeviceData& d);
 void launch_block_prepare(const LaunchCfg& c, const DeviceData& d); // + "grid_update_cdf" pass
 void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur);
-// "g2p_cdf" pass.
-void launch_g2p_cdf(const LaunchCfg& c, const DeviceData& d, int cur);
 // "p2g" pass.
+// "g2p_cdf" + "p2g" passes (the particle colouring runs inside the P2G kernel, p2g.cu).
 void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur);
-void launch_p2g_cpic(const LaunchCfg& c, const DeviceData& d, int cur);
 // "grid_update" + "g2p" + "particles_update" passes (fused).
 void launch_g2p_update(const LaunchCfg& c, const DeviceData& d, int cur);
 // "integrate_bodies" pass.

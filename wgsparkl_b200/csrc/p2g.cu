@@ -23,13 +23,11 @@
 // impulses exactly like p2g.wgsl:201-226; only the blocks whose tile holds a collider run that
 // instantiation (a second pass over the staged particles accumulates the per-node impulses with
 // the same register/phase scheme, so the impulse path has no floating-point atomics either).
+#include "cdf.cuh"
 #include "launch.h"
 
 namespace b2 {
 
-#ifndef P2G_CPIC_PARTS
-#define P2G_CPIC_PARTS 4u
-#endif
 constexpr int P2G_CHUNK = 256; // particles staged per pass and warp: 32 cells x 8 (the reference's seeding density)
 
 enum { P2G_FAST = 0, P2G_CPIC_MOMENTUM = 1, P2G_CPIC_IMPULSE = 2 };
@@ -46,7 +44,7 @@ struct P2GAcc {
 };
 
 // Staged particle record in shared memory (SoA of float4, 64 bytes per particle):
-//   sp = (x, y, z, mass)   sv = (vx, vy, vz, -)   sa = C[0..3]   sb = C[4..7]   sc = C[8]
+//   sp = (x, y, z, mass)   sv = (vx, vy, vz, CPIC affinity word of this substep)   sa = C[0..3]   sb = C[4..7]   sc = C[8]
 // Slot i is stored at i ^ ((i >> 3) & 7): a cell's run starts at ~8 t for thread t, so consecutive lanes
 // would otherwise hit the same bank group on every 16-byte load (8-way conflict).
 __device__ __forceinline__ int p2g_swz(int i) { return i ^ ((i >> 3) & 7); }
@@ -57,7 +55,7 @@ __device__ __forceinline__ int p2g_swz(int i) { return i ^ ((i >> 3) & 7); }
 template <int D, int MODE, int W>
 __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uint32_t base, int lo, int hi,
                                                const float4* sp, const float4* sv, const float4* sa, const float4* sb,
-                                               const float* sc, const uint32_t* s_aff, const float* cellpos, float h, float inv_h, int tb,
+                                               const float* sc, const float* cellpos, float h, float inv_h, int tb,
                                                const uint2* tcdf, P2GAcc<Dim<D>::NBH, W>& acc) {
     constexpr int T = Dim<D>::TILE;
     bool any_incompatible = false;
@@ -94,7 +92,7 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
         uint32_t pa = 0;
         V3 normal = v3(0, 0, 0);
         if (MODE != P2G_FAST) {
-            pa = s_aff[s];
+            pa = __float_as_uint(v4.w); // this substep's colour of the particle (the colouring phase left it here)
             if (MODE == P2G_CPIC_IMPULSE && pa == 0u) continue; // compatible with every node: no impulse
             if (MODE == P2G_CPIC_IMPULSE) {
                 float4 nd = d.cdf_nd[base + (uint32_t)i];
@@ -175,8 +173,14 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
 // One WARP owns half a block (32 cells, one lane per cell) and is an independent worker: its own staging
 // buffers, its own (BLOCK+2)^D tile, its own dynamic work queue position — there is no CTA-wide barrier anywhere
 // in the kernel (a CTA is a single warp), so some warps stage while others compute.
-//   CPIC = false: blocks whose tile holds no collider (block_flags == 0, or no bodies at all).
-//   CPIC = true : the few blocks next to a collider (compact list), further split into PARTS work items.
+//   CPIC = false: scenes without bodies - every block takes the plain path.
+//   CPIC = true : scenes with bodies - ONE kernel for all blocks. The collider-side blocks (k_scatter's compact list)
+//     come FIRST in the work queue (they cost several times more per particle); for them the warp also runs the
+//     "g2p_cdf" pass on the staged particles (cdf.cuh: colour = affinity / sign bits + MLS normal and distance, one
+//     lane per particle) before it scatters them with the compatibility tests. All other blocks take the plain path.
+//     Running both kinds in one persistent kernel matters: as separate kernels on a second stream the collider-side
+//     work only got SM slots when the plain kernel's warps retired, i.e. it ran AFTER it (timeline: +21 us per substep
+//     on the 1M cube, +120 us on the 2M dam slab with its four walls).
 //   IMP (with CPIC): some body can react to impulses (DeviceData::bodies_react) - without it the per-node impulse
 //   accumulators (27 x 6 registers, 5 KB of shared memory) and the second pass are compiled out.
 template <int D, bool CPIC, bool IMP>
@@ -191,24 +195,35 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
     __shared__ float4 sb[D == 3 ? CHUNK : 1];
     __shared__ float sc[D == 3 ? CHUNK : 1];
     __shared__ uint32_t s_ids[CHUNK];
-    __shared__ uint32_t s_aff[CPIC ? CHUNK : 1]; // this substep's particle affinities (k_g2p_cdf, by sorted slot)
     __shared__ uint32_t s_nbr[NA];
-    __shared__ uint2 tcdf[CPIC ? TC : 1];
+    __shared__ uint2 tcdf[CPIC ? TC : 1]; // node (affinities, closest_id) of the tile
+    __shared__ float tdist[CPIC ? TC : 1]; // node distance
     __shared__ float timp[IMP ? TC * WI : 1];
 
     pdl_start();
-    TL_BEGIN(d, CPIC ? B200MPM_KERNEL_P2G_CPIC : B200MPM_KERNEL_P2G);
+    TL_BEGIN(d, B200MPM_KERNEL_P2G);
     const int lane = threadIdx.x;
-    // A collider-side half-block is split into PARTS work items (each takes every cell's PARTS-th share of the
-    // run): these blocks are few, so their latency — not throughput — is what shows up.
-    constexpr uint32_t PARTS = CPIC ? P2G_CPIC_PARTS : 1u;
-    // CPIC = false walks p2g_list (k_scatter: blocks that hold particles and see no collider, the densely populated
-    // ones first - longest items first keeps the last scheduling round short).
-    const uint32_t nfront = d.counters->num_p2g_front;
-    const uint32_t nwork = (CPIC ? d.counters->num_cpic_blocks * PARTS : nfront + d.counters->num_p2g_back) * 2u;
+    // Work queue: the collider-side half blocks (cpic_list) first, then p2g_list bucket by bucket (k_scatter: blocks that
+    // hold particles and see no collider, by decreasing population - longest items first keeps the last round short).
+    __shared__ uint32_t s_cum[P2G_BUCKETS + 1]; // first work index of every bucket
+    __shared__ float s_mass[16]; // masses of the first 16 materials (saves a dependent global load per staged chunk)
+    const bool mass_in_smem = d.num_materials <= 16u;
+    if (mass_in_smem && lane < (int)d.num_materials) s_mass[lane] = d.materials[lane].mass;
+    const uint32_t ncpic = CPIC ? d.counters->num_cpic_blocks * 2u : 0u;
+    if (lane == 0) {
+        uint32_t c = ncpic;
+        for (uint32_t k = 0; k < P2G_BUCKETS; ++k) {
+            s_cum[k] = c;
+            c += d.counters->num_p2g[k] * 2u;
+        }
+        s_cum[P2G_BUCKETS] = c;
+    }
+    __syncwarp();
+    const uint32_t nwork = s_cum[P2G_BUCKETS];
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
-    uint32_t* work = CPIC ? &d.counters->work_p2g_cpic : &d.counters->work_p2g;
+    const uint32_t num_bodies = d.sim->num_bodies;
+    uint32_t* work = &d.counters->work_p2g;
     const float4* __restrict__ pos4 = d.pos4[cur];
     const float4* __restrict__ vel4 = d.vel4[cur];
     const float4* __restrict__ Ca = d.Ca[cur];
@@ -217,7 +232,9 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
 
     // Stage one chunk of the sorted range into shared memory (gather through sorted_ids, a
     // near-identity permutation of the current buffers).
-    auto stage = [&](uint32_t base, int cn) {
+    // reload_colour: second (impulse) pass over a half block of several chunks - the colours come back from
+    // cdf_aff[next], where the first pass left them.
+    auto stage = [&](uint32_t base, int cn, bool reload_colour) {
         // ids go through shared memory so that the request loop below stays rolled (few live registers
         // next to the 108 accumulators); each lane only reads back the ids it wrote itself.
 #pragma unroll
@@ -236,7 +253,6 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
                 cp_async16(sb + s, Cb + id);
                 cp_async4(sc + s, Cc + id);
             }
-            if (CPIC) cp_async4(s_aff + s, d.cdf_aff[cur ^ 1] + base + i);
         }
         cp_async_wait_all();
         // (x, y, z, material bits) -> (x, y, z, mass)
@@ -244,7 +260,56 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
         for (int i = lane; i < cn; i += 32) {
             const int s = p2g_swz(i);
             const uint32_t mbits = __float_as_uint(sp[s].w);
-            sp[s].w = __ldg(&d.materials[mbits & MAT_ID_MASK].mass);
+            sp[s].w = mass_in_smem ? s_mass[mbits & MAT_ID_MASK] : __ldg(&d.materials[mbits & MAT_ID_MASK].mass);
+            if (CPIC && reload_colour) sv[s].w = __uint_as_float(d.cdf_aff[cur ^ 1][base + i]);
+        }
+        __syncwarp();
+    };
+    // "g2p_cdf" pass (g2p_cdf.wgsl:39-63) on the staged chunk, one lane per particle: the colour goes to sv[].w for
+    // the scatter below and, if it is not the default, to cdf_aff[next] / cdf_nd (by sorted slot) for G2P.
+    auto colour = [&](uint32_t base, int cn, bool any_cdf) {
+        // Two phases, because the full colouring (sign votes + a 4x4 MLS solve, ~1.5 k instructions) only concerns the
+        // particles within reach of a collider: first every particle checks its stencil (27 loads) and the ones that
+        // see a collider are COMPACTED into a list, then the warp works through the list with all lanes busy.
+        uint32_t* const s_list = s_ids; // compacted chunk indices; reuses the id buffer (the requests have been issued,
+                                        // and phase 2 re-reads the few ids it needs from sorted_ids)
+        int count = 0;
+        const auto aff_tile = [&](int n) { return tcdf[n].x; };
+#pragma unroll 1
+        for (int i0 = 0; i0 < cn; i0 += 32) {
+            const int i = i0 + lane;
+            bool near = false;
+            if (i < cn) {
+                const int s = p2g_swz(i);
+                if (any_cdf) {
+                    const float4 p4 = sp[s];
+                    const float pp[3] = {p4.x, p4.y, p4.z};
+                    near = cdf_stencil_affinity<D>(pp, h, inv_h, aff_tile) != 0u;
+                }
+                if (!near) sv[s].w = __uint_as_float(0u);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, near);
+            if (near) s_list[count + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+            count += __popc(m);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int j0 = 0; j0 < count; j0 += 32) {
+            const int j = j0 + lane;
+            if (j < count) {
+                const int i = (int)s_list[j];
+                const int s = p2g_swz(i);
+                const float4 p4 = sp[s];
+                const float pp[3] = {p4.x, p4.y, p4.z};
+                float4 nd;
+                const uint32_t prev = d.cdf_aff[cur][__ldg(d.sorted_ids + base + i)];
+                const uint32_t aff = cdf_colour_particle<D>(pp, prev, num_bodies, h, inv_h, aff_tile, [&](int n) { return tdist[n]; }, nd);
+                if (aff != 0u) {
+                    d.cdf_aff[cur ^ 1][base + i] = aff; // (k_scatter wrote the default, 0)
+                    d.cdf_nd[base + i] = nd;
+                }
+                sv[s].w = __uint_as_float(aff);
+            }
         }
         __syncwarp();
     };
@@ -254,51 +319,54 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
         if (lane == 0) w = atomicAdd(work, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= nwork) {
-            TL_END(d, CPIC ? B200MPM_KERNEL_P2G_CPIC : B200MPM_KERNEL_P2G);
+            TL_END(d, B200MPM_KERNEL_P2G);
             break;
         }
-        const uint32_t half = w & 1u;
-        const uint32_t part = (w >> 1) % PARTS;
+        const uint32_t half = w & 1u; // (ncpic is even)
+        const bool cpic_item = CPIC && w < ncpic; // (warp-uniform)
         uint32_t b;
-        if (CPIC) {
-            b = d.cpic_list[w / (2u * PARTS)];
+        if (cpic_item) {
+            b = d.cpic_list[w >> 1];
         } else {
-            const uint32_t e = w >> 1;
-            b = d.p2g_list[e < nfront ? e : d.capacity - 1u - (e - nfront)];
+            uint32_t k = 0;
+#pragma unroll
+            for (uint32_t q = 1; q < P2G_BUCKETS; ++q) k += (w >= s_cum[q]) ? 1u : 0u;
+            b = d.p2g_list[(size_t)k * d.capacity + ((w - s_cum[k]) >> 1)];
         }
         const uint32_t cell = half * HALF + lane; // this lane's cell of the block
         const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK + half * HALF];
         const uint32_t last = d.cell_start[b * CELLS_PER_BLOCK + half * HALF + HALF];
         if (first == last) continue; // nothing to scatter from this half
-        uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + cell];
-        uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + cell + 1];
-        if (PARTS > 1) {
-            const uint32_t len = end - start;
-            end = start + (len * (part + 1)) / PARTS;
-            start = start + (len * part) / PARTS;
-        }
+        const uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + cell];
+        const uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + cell + 1];
         const int lx = cell & (B - 1), ly = (cell >> LB) & (B - 1), lz = (D == 3) ? (cell >> (2 * LB)) : 0;
         const int tb = lx + T * ly + T * T * lz;
         __syncwarp(); // the previous work item's tile / s_nbr are no longer read
         if (lane < NA) s_nbr[lane] = d.nbr[b * NA + lane];
         for (int n = lane; n < TC; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
-        if (CPIC) {
+        bool any_cdf = false; // the tile holds a coloured node
+        if (cpic_item) {
             for (int n = lane; n < TC; n += 32) {
                 int x = n % T, y = (n / T) % T, z = n / (T * T);
                 int ox = x >= B, oy = y >= B, oz = z >= B;
                 uint32_t hn = s_nbr[ox + 2 * oy + 4 * oz];
                 uint2 c = make_uint2(0u, NONE);
+                float dist = 0.0f;
                 if (hn != NONE) {
                     uint4 g = d.node_cdf[hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B];
                     c = make_uint2(g.z, g.x); // (affinities, closest_id)
+                    dist = __uint_as_float(g.y);
                 }
                 tcdf[n] = c;
+                tdist[n] = dist;
+                any_cdf = any_cdf || (c.x != 0u);
                 if (IMP) {
 #pragma unroll
                     for (int k = 0; k < WI; ++k) timp[n * WI + k] = 0.0f;
                 }
             }
+            any_cdf = __any_sync(0xffffffffu, any_cdf);
             __syncwarp();
         }
 
@@ -307,15 +375,29 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
         bool incompatible = false;
         {
             P2GAcc<NBH, D + 1> acc;
-            acc.clear();
-            for (uint32_t base = first; base < last; base += CHUNK) {
+            // One chunk: stage, colour (collider side only), scatter into the register accumulators. The first chunk -
+            // for all but overfull half blocks the only one - is peeled so that the 3^D x (D+1) accumulators are not
+            // live yet while the colouring (a 4x4 solve per particle) runs.
+            auto scatter_chunk = [&](uint32_t base) {
                 const int cn = (int)min((uint32_t)CHUNK, last - base);
-                __syncwarp(); // the previous chunk is no longer in use
-                stage(base, cn);
                 const int lo = (int)(max(start, base) - base);
                 const int hi = (int)(min(end, base + (uint32_t)cn) - base);
-                incompatible |= p2g_accumulate<D, CPIC ? P2G_CPIC_MOMENTUM : P2G_FAST, D + 1>(
-                    d, cur, base, lo, hi, sp, sv, sa, sb, sc, s_aff, cellpos, h, inv_h, tb, tcdf, acc);
+                if (cpic_item && any_cdf)
+                    incompatible |= p2g_accumulate<D, P2G_CPIC_MOMENTUM, D + 1>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, cellpos, h,
+                                                                               inv_h, tb, tcdf, acc);
+                else // no coloured node in reach: every particle keeps the default colour k_scatter wrote
+                    p2g_accumulate<D, P2G_FAST, D + 1>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, cellpos, h, inv_h, tb, tcdf, acc);
+            };
+            stage(first, (int)min((uint32_t)CHUNK, last - first), false);
+            if (cpic_item && any_cdf) colour(first, (int)min((uint32_t)CHUNK, last - first), true);
+            acc.clear();
+            scatter_chunk(first);
+            for (uint32_t base = first + CHUNK; base < last; base += CHUNK) {
+                const int cn = (int)min((uint32_t)CHUNK, last - base);
+                __syncwarp(); // the previous chunk is no longer in use
+                stage(base, cn, false);
+                if (cpic_item && any_cdf) colour(base, cn, true);
+                scatter_chunk(base);
             }
             // Merge the per-cell stencils into the tile: 3^D conflict-free phases (within a phase the 32 lanes
             // add to 32 distinct nodes).
@@ -336,7 +418,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
                         __syncwarp();
                     }
         }
-        if (IMP) {
+        if (IMP && cpic_item) {
             // Second pass, only if some particle/node pair of this work item is CPIC-incompatible with a collider
             // that can react: per-node body impulses (p2g.wgsl:201-226).
             if (__any_sync(0xffffffffu, incompatible)) {
@@ -347,11 +429,11 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
                     const int cn = (int)min((uint32_t)CHUNK, last - base);
                     if (!single_chunk) {
                         __syncwarp();
-                        stage(base, cn);
+                        stage(base, cn, true);
                     }
                     const int lo = (int)(max(start, base) - base);
                     const int hi = (int)(min(end, base + (uint32_t)cn) - base);
-                    p2g_accumulate<D, P2G_CPIC_IMPULSE, WI>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, s_aff, cellpos, h, inv_h, tb, tcdf, imp);
+                    p2g_accumulate<D, P2G_CPIC_IMPULSE, WI>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, cellpos, h, inv_h, tb, tcdf, imp);
                 }
 #pragma unroll
                 for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz)
@@ -378,7 +460,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
             float4 c = tile[n];
             if (D == 2) c.w = 0.0f; // 2D stores (px, py, mass, 0)
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f) atomicAdd(d.node_mv + node, c);
-            if (IMP) {
+            if (IMP && cpic_item) {
                 uint32_t cid = tcdf[n].y;
                 if (cid != NONE) { // p2g.wgsl:142-155: integer atomics, i32(x * 1e5)
                     BodyDev& body = d.bodies[cid];
@@ -400,24 +482,20 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
 
 void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.n == 0) return;
-    const int grid = c.num_sms * 10; // 10 single-warp CTAs per SM (shared memory: 22 KB each)
-    if (c.dim == 2) launch_pdl(k_p2g<2, false, false>, grid, 32, 0, c.stream, d, cur);
-    else launch_pdl(k_p2g<3, false, false>, grid, 32, 0, c.stream, d, cur);
-    ++*c.launch_counter;
-}
-
-// The blocks next to a collider (compact list built by k_scatter). Independent of launch_p2g: the two
-// instantiations touch disjoint blocks and meet only in the commutative node reductions.
-void launch_p2g_cpic(const LaunchCfg& c, const DeviceData& d, int cur) {
-    if (d.n == 0 || !d.has_bodies) return;
-    if (d.bodies_react) {
+    // single-warp CTAs, as many per SM as the shared memory allows (22 KB each without bodies, 24.5 KB with, 29.6 KB
+    // with impulse accumulators)
+    if (!d.has_bodies) {
+        const int grid = c.num_sms * 10;
+        if (c.dim == 2) launch_pdl(k_p2g<2, false, false>, grid, 32, 0, c.stream, d, cur);
+        else launch_pdl(k_p2g<3, false, false>, grid, 32, 0, c.stream, d, cur);
+    } else if (d.bodies_react) {
         const int grid = c.num_sms * 7;
-        if (c.dim == 2) k_p2g<2, true, true><<<grid, 32, 0, c.stream>>>(d, cur);
-        else k_p2g<3, true, true><<<grid, 32, 0, c.stream>>>(d, cur);
+        if (c.dim == 2) launch_pdl(k_p2g<2, true, true>, grid, 32, 0, c.stream, d, cur);
+        else launch_pdl(k_p2g<3, true, true>, grid, 32, 0, c.stream, d, cur);
     } else { // every body is immovable and at rest: no impulse can have an effect (rigid_impulses.wgsl:94-137)
         const int grid = c.num_sms * 9;
-        if (c.dim == 2) k_p2g<2, true, false><<<grid, 32, 0, c.stream>>>(d, cur);
-        else k_p2g<3, true, false><<<grid, 32, 0, c.stream>>>(d, cur);
+        if (c.dim == 2) launch_pdl(k_p2g<2, true, false>, grid, 32, 0, c.stream, d, cur);
+        else launch_pdl(k_p2g<3, true, false>, grid, 32, 0, c.stream, d, cur);
     }
     ++*c.launch_counter;
 }

@@ -320,8 +320,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
             c->num_cpic_blocks = 0;
             c->num_g2p_items = 0;
             c->num_g2p_back = 0;
-            c->num_p2g_front = 0;
-            c->num_p2g_back = 0;
+            for (uint32_t k = 0; k < P2G_BUCKETS; ++k) c->num_p2g[k] = 0;
             c->dropped_particles = 0;
         }
         const uint32_t nbins = min(d.counters->num_active_blocks, d.capacity) * CELLS_PER_BLOCK + 1;
@@ -572,13 +571,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
                 dst[2] = make_uint4(nbr[4], nbr[5], nbr[6], nbr[7]);
             }
         }
-        // P2G list (k_p2g without CPIC): blocks that hold particles and whose tile holds no collider; the densely
-        // populated ones (longest items) first.
+        // P2G list: blocks that hold particles and whose tile holds no collider, bucketed by population (common.cuh).
         const bool p2g_mine = np != 0u && flag == 0;
-        const bool dense = np > 5u * G2P_ITEM;
-        const uint32_t pf = reserve((p2g_mine && dense) ? 1u : 0u, &d.counters->num_p2g_front);
-        const uint32_t pb = reserve((p2g_mine && !dense) ? 1u : 0u, &d.counters->num_p2g_back);
-        if (p2g_mine) d.p2g_list[dense ? pf : d.capacity - 1u - pb] = i;
+        const uint32_t my_bucket = p2g_bucket(np);
+#pragma unroll
+        for (uint32_t k = 0; k < P2G_BUCKETS; ++k) {
+            const bool in = p2g_mine && my_bucket == k;
+            if (!__any_sync(0xffffffffu, in)) continue; // (warp-uniform)
+            const uint32_t pos = reserve(in ? 1u : 0u, &d.counters->num_p2g[k]);
+            if (in) d.p2g_list[(size_t)k * d.capacity + pos] = i;
+        }
     }
     // particles: SORT_ITEMS per thread, see k_touch
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -188,3 +188,32 @@ def elastic_block_on_polyline_2d(n_side=24):
     s["rigid_particles"] = rigid_particles_to_abi(bodies, colliders, 2, s["cell_width"])
     s["name"] = "2d_elastic_block_on_polyline_%d" % len(s["particles"])
     return s
+
+
+def sand_2d(nx=60, ny=60, jitter=True, seed=SEED, n_dynamic=1):
+    """The reference's 2D sand scene (crates/wgsparkl2d/examples/sand2.rs:28-156) at test size: Drucker-Prager sand
+    (phase None: plasticity on) falling on a static platform, past kinematic rotating colliders of the three analytic
+    shapes - cuboid, BALL and CAPSULE (sand2.rs:124-136) - and under dynamic cuboids (sand2.rs:149-156)."""
+    h = 0.2
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    pos = np.stack([i.ravel() + 0.5, j.ravel() + 0.5], axis=1) * (h / 2.0) + np.array([0.0, 2.0])
+    pos = _jitter(pos, h, jitter, seed)
+    parts = make_particles(pos, 2, h / 4.0, 1000.0, ElasticCoefficients.from_young_modulus(10_000_000.0, 0.2),
+                           plasticity=DruckerPrager.new(10_000_000.0, 0.2), phase=None)
+    bodies, colliders = RigidBodySet(), ColliderSet()
+    w = nx * h / 2.0
+    rb = bodies.insert(RigidBodyBuilder.fixed().translation([w / 2.0, -1.0]))
+    colliders.insert_with_parent(ColliderBuilder.cuboid(42.0, 1.0), rb, bodies)
+    rb = bodies.insert(RigidBodyBuilder.kinematic_velocity_based().translation([0.25 * w, 1.2]).angvel(-1.0))
+    colliders.insert_with_parent(ColliderBuilder.ball(0.7), rb, bodies)
+    rb = bodies.insert(RigidBodyBuilder.kinematic_velocity_based().translation([0.75 * w, 1.2]).angvel(-1.0))
+    colliders.insert_with_parent(ColliderBuilder.capsule_y(0.5, 0.3), rb, bodies)
+    rb = bodies.insert(RigidBodyBuilder.kinematic_velocity_based().translation([0.5 * w, 1.0]).angvel(1.0))
+    colliders.insert_with_parent(ColliderBuilder.cuboid(0.1, 0.8), rb, bodies)
+    top = 2.0 + ny * h / 2.0
+    for k in range(n_dynamic):
+        rb = bodies.insert(RigidBodyBuilder.dynamic().translation([0.5 * w + 0.6 * k, top + 0.4]))
+        colliders.insert_with_parent(ColliderBuilder.cuboid(0.5, 0.1).density(10.0 + 100.0 * k), rb, bodies)
+    return dict(name="2d_sand_%d" % (nx * ny), dim=2, params=SimulationParams([0.0, -9.81], (1.0 / 60.0) / 10.0),
+                particles=parts, bodies=bodies_to_abi(bodies, colliders, 2), cell_width=h, grid_capacity=60_000,
+                substeps_per_frame=10)
