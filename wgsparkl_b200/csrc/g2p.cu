@@ -77,8 +77,7 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     extern __shared__ __align__(16) unsigned char g2p_smem[];
     G2PShared<D, PLASTIC, CPIC>& sm = *reinterpret_cast<G2PShared<D, PLASTIC, CPIC>*>(g2p_smem);
 
-    pdl_start();
-    TL_BEGIN(d, B200MPM_KERNEL_G2P);
+    // (pdl_wait() comes later: the prologue below only reads what k_scatter and the previous substep left)
     const int t = threadIdx.x;
     const bool mats_in_smem = d.num_materials <= (uint32_t)G2P_SMEM_MATS;
     if (t == 0) { // simulation constants live in shared memory, not in 8 registers per thread
@@ -118,13 +117,11 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
         return j == 0u || dq[j % G2P_DQ].block != dq[(j - 1u) % G2P_DQ].block;
     };
     int ts = 1; // slot of the current item's tile
-    // Requests item j's records of this thread's particle (its id has landed) and, on a block change, this thread's
-    // two nodes of the tile.
-    auto request_item = [&](uint32_t j) {
+    // Requests item j's records of this thread's particle (its id has landed) ...
+    auto request_records = [&](uint32_t j) {
         const G2PItem& it = dq[j % G2P_DQ];
         if (it.block == NONE) return;
         const int s = (int)(j & 1u);
-        const bool any_cdf = CPIC && (it.flags & 1u);
         if ((uint32_t)t < it.count) {
             const uint32_t id = sm.ids[j % G2P_IQ][t];
             cp_async16(&sm.pos[s][t], d.pos4[cur] + id);
@@ -135,10 +132,18 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
                 cp_async4(&sm.Fc[s][t], d.Fc[cur] + id);
             }
             if (PLASTIC) cp_async16(&sm.plastic[PLASTIC ? s : 0][PLASTIC ? t : 0], d.plastic[cur] + id);
-            if (any_cdf) { // this substep's particle colours, by sorted slot (k_scatter / k_g2p_cdf)
-                cp_async4(&sm.aff[CPIC ? s : 0][CPIC ? t : 0], d.cdf_aff[nxt] + it.first + t);
-                cp_async16(&sm.nd[CPIC ? s : 0][CPIC ? t : 0], d.cdf_nd + it.first + t);
-            }
+        }
+    };
+    // ... and what THIS substep's P2G produced: the particle's colour (collider-side blocks) and, on a block change,
+    // this thread's two nodes of the tile.
+    auto request_grid = [&](uint32_t j) {
+        const G2PItem& it = dq[j % G2P_DQ];
+        if (it.block == NONE) return;
+        const int s = (int)(j & 1u);
+        const bool any_cdf = CPIC && (it.flags & 1u);
+        if (any_cdf && (uint32_t)t < it.count) { // by sorted slot (k_scatter's default / k_p2g's colouring)
+            cp_async4(&sm.aff[CPIC ? s : 0][CPIC ? t : 0], d.cdf_aff[nxt] + it.first + t);
+            cp_async16(&sm.nd[CPIC ? s : 0][CPIC ? t : 0], d.cdf_nd + it.first + t);
         }
         if (new_tile(j)) { // g2p.wgsl:72-132, through the item's neighbour table
             const int u = ts ^ 1;
@@ -179,7 +184,11 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     request_id(0);
     request_id(1);
     cp_async_wait_all();
-    request_item(0);
+    request_records(0);
+    pdl_wait(); // k_p2g is complete: node momenta and particle colours may be read
+    pdl_trigger();
+    TL_BEGIN(d, B200MPM_KERNEL_G2P);
+    request_grid(0);
 
     for (uint32_t i = 0;; ++i) {
         const bool cur_new = dq[i % G2P_DQ].block != NONE && new_tile(i);
@@ -216,7 +225,8 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
         else __syncwarp();
         const G2PItem& item = dq[i % G2P_DQ];
         if (item.block == NONE) break;
-        request_item(i + 1);
+        request_records(i + 1);
+        request_grid(i + 1);
         request_id(i + 2);
         request_desc(i + 3);
 

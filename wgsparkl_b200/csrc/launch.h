@@ -7,9 +7,11 @@ namespace b2 {
 
 // Programmatic dependent launch for the kernels of the substep's critical path (touch -> count -> scan -> scatter ->
 // p2g -> g2p -> integrate): the dependent kernel is launched while its predecessor drains and parks at
-// pdl_wait() (griddepcontrol.wait: full completion + memory flush of the predecessor), so the ~2-3 us of launch
-// latency per graph edge overlap the predecessor's tail. Every such kernel starts with pdl_start().
-// B200MPM_NO_PDL=1 switches the attribute off (plain stream order; the device-side instructions are then no-ops).
+// pdl_wait() (griddepcontrol.wait: full completion + memory flush of the predecessor). Every such kernel starts with
+// pdl_start(). OFF by default (B200MPM_PDL=1 switches the launch attribute on; without it the device-side
+// instructions are no-ops): measured, it gains 1 % on the 2M-particle dam slab and LOSES 5 % on the 1M cube - the
+// kernels of this path are persistent grids that fill the machine, so an early-launched successor mostly waits for
+// SM resources, and the launch gaps it could hide are ~1 us (tools/timeline.py).
 bool pdl_enabled();
 template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
@@ -26,9 +28,14 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #if defined(__CUDACC__)
+// wait, THEN let the dependent launch: at most one kernel is ever parked, and when it starts its predecessor has passed
+// its own wait - so code a kernel runs BEFORE pdl_wait() may read anything produced two or more kernels back (k_g2p
+// starts its descriptor / id / record requests while k_p2g drains; only the node tile and the colours wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_start() {
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); // (the dependents park at their own wait)
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    pdl_wait();
+    pdl_trigger();
 }
 #endif
 

@@ -458,8 +458,8 @@ static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b)
 
 bool pdl_enabled() {
     static const bool on = []() {
-        const char* e = getenv("B200MPM_NO_PDL");
-        return !(e && e[0] && e[0] != '0');
+        const char* e = getenv("B200MPM_PDL");
+        return e && e[0] && e[0] != '0';
     }();
     return on;
 }
