@@ -397,7 +397,8 @@ def run_ours(args):
     e2e_value = n_total * spf * args.steps / (ms_e2e * 1e-3)
     nb = len(scene["bodies"])
     h2d = nb * (poses.dtype.itemsize + vels.dtype.itemsize)
-    d2h = nb * poses.dtype.itemsize + n_local * 16
+    # (a slab copies all its particle slots, spare capacity included: a fixed-size copy needs no host synchronisation)
+    d2h = nb * poses.dtype.itemsize + (n_local if runner.sharded is None else runner.data.particle_capacity) * 16
     nblocks, overflow = runner.data.status()
 
     # Per-kernel durations for the roofline. At N > 1 this runs after both timed regions, on each rank's own slab with

@@ -374,9 +374,10 @@ int b200mpm_shard_p2p_connect(b200mpm_pipeline* p, b200mpm_data* d, const void* 
 /* Positions of the live particles in device order: xyz + the particle id's bits in w (B200MPM_NONE for a
  * particle that has emigrated). `out` holds 4 * capacity floats. */
 int b200mpm_read_positions_unordered(b200mpm_data* d, float* out, size_t capacity, size_t* count);
-/* Same, with the copy on the copy stream (see b200mpm_read_positions_async): waits for the enqueued substeps to
- * learn the live count (returned at once in *count), then gathers and copies without blocking; `out` is valid
- * after b200mpm_sync. */
+/* Same, with the copy on the copy stream (see b200mpm_read_positions_async) and WITHOUT any host synchronisation: the
+ * copy covers all particle_capacity slots (so `capacity` must be at least that; *count returns it), and the slots that
+ * hold no particle - spare capacity, emigrated particles - carry the id NONE (0xffffffff) in w. `out` is valid after
+ * b200mpm_sync. */
 int b200mpm_read_positions_unordered_async(b200mpm_data* d, float* out, size_t capacity, size_t* count);
 /* Live particles in device order with their ids (no un-permutation). */
 int b200mpm_read_particles_unordered(b200mpm_data* d, b200mpm_particle* out, uint32_t* ids, size_t capacity,

@@ -56,7 +56,7 @@ if json_args:
         full = r[idx["Kernel Name"]]
         key = "k_g2p" if full.startswith("k_g2p<") or "k_g2p<" in full.split("(")[0] else None
         if key is None and "k_p2g<" in full.split("(")[0]:
-            key = "k_p2g" if ", 0, 0>" in full or ",0,0>" in full else "k_p2g_cpic"
+            key = "k_p2g"  # one kernel for all blocks (collider side included) since round 2
         if key is None or "cdf" in full.split("(")[0]:
             continue
         rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale

@@ -1210,16 +1210,16 @@ int b200mpm_read_positions_unordered_async(b200mpm_data* d, float* out, size_t c
     b200mpm_pipeline* p = d->pipe;
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
-    // The live count decides the copy size, so it is read first (4 bytes; waits for the enqueued substeps).
-    uint32_t n_live = 0;
-    CU_TRY(cudaMemcpyAsync(&n_live, &d->dev.counters->n_live, sizeof(n_live), cudaMemcpyDeviceToHost, p->stream));
-    CU_TRY(cudaStreamSynchronize(p->stream));
-    *count = n_live;
-    if (n_live == 0) return B200MPM_OK;
-    if (!out || capacity < n_live) return fail(B200MPM_ERR_INVALID_ARGUMENT, "output too small");
+    // No host synchronisation: the copy has a FIXED size - every slot of the particle capacity, the spare ones marked
+    // "no particle" (id NONE) by the gather kernel - so it does not have to wait for the enqueued substeps to learn the
+    // live count (which used to cost one stream synchronisation per frame and rank, i.e. no overlap at all).
+    const size_t n = d->dev.n;
+    *count = n;
+    if (n == 0) return B200MPM_OK;
+    if (!out || capacity < n) return fail(B200MPM_ERR_INVALID_ARGUMENT, "output too small: it must hold particle_capacity entries");
     int r = ensure_async_readback(d);
     if (r) return r;
-    return enqueue_async_positions(p, d, out, n_live, 1);
+    return enqueue_async_positions(p, d, out, n, 1);
 }
 
 int b200mpm_prep_vertex_buffer(b200mpm_pipeline* p, b200mpm_data* d, b200mpm_instance* dev_instances, uint32_t mode) {

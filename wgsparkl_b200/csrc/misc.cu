@@ -271,7 +271,11 @@ __global__ void k_read_poses(DeviceData d, b200mpm_pose* poses, b200mpm_velocity
 // ---- particle / grid readback in the caller's layout ---------------------------------------------------------
 __global__ void k_gather_positions(DeviceData d, int cur, float4* out, int unordered) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.counters->n_live) return;
+    if (i >= d.counters->n_live) {
+        // unordered: the spare capacity is marked "no particle", so that a fixed-size copy needs no live count
+        if (unordered && i < d.n) out[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(NONE));
+        return;
+    }
     float4 p = d.pos4[cur][i];
     uint32_t orig = __float_as_uint(d.vel4[cur][i].w);
     if (unordered) { // device order; w carries the particle id (NONE for an emigrated particle)

@@ -449,8 +449,9 @@ class MpmData:
         return out[: n.value]
 
     def read_positions_unordered_async(self, out: np.ndarray) -> int:
-        """Like read_positions_unordered, but the copy overlaps with later work: returns the live count at once,
-        `out[:count]` (page-locked for a real overlap) is valid after `MpmPipeline.sync()`."""
+        """Like read_positions_unordered, but without any host synchronisation: copies all `particle_capacity` slots
+        (returns that number; `out` must hold as many rows, page-locked for a real overlap); rows whose id (w, as
+        uint32) is NONE hold no particle. Valid after `MpmPipeline.sync()`."""
         n = ctypes.c_size_t(0)
         _check(load_library().b200mpm_read_positions_unordered_async(self._h, abi.ptr(out), out.shape[0], ctypes.byref(n)))
         return int(n.value)
