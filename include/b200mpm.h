@@ -159,15 +159,15 @@ enum {
 /* Kernel-level timers of this implementation (b200mpm_get_kernel_timings): finer than the reference's pass names,
  * e.g. the two P2G instantiations, which the "p2g" pass sums. Used by bench.py's per-kernel roofline. */
 enum {
-    B200MPM_KERNEL_TOUCH = 0,
-    B200MPM_KERNEL_COUNT = 1,
-    B200MPM_KERNEL_SCAN = 2,
-    B200MPM_KERNEL_BLOCK_PREPARE = 3,
+    B200MPM_KERNEL_TOUCH = 0, /* touch_particle_blocks + update_block_particle_count */
+    B200MPM_KERNEL_COUNT = 1, /* (0: part of TOUCH) */
+    B200MPM_KERNEL_SCAN = 2, /* (0: the blocks' ranges are taken in BLOCK_PREPARE) */
+    B200MPM_KERNEL_BLOCK_PREPARE = 3, /* ranges + neighbour table + node reset + grid_update_cdf */
     B200MPM_KERNEL_SCATTER = 4,
-    B200MPM_KERNEL_G2P_CDF = 5,
-    B200MPM_KERNEL_P2G_CPIC = 6, /* blocks next to a collider */
-    B200MPM_KERNEL_P2G = 7, /* all other blocks */
-    B200MPM_KERNEL_BEGIN = 8, /* reset_hmap for the next substep */
+    B200MPM_KERNEL_G2P_CDF = 5, /* (0: inside P2G) */
+    B200MPM_KERNEL_P2G_CPIC = 6, /* (0: inside P2G) */
+    B200MPM_KERNEL_P2G = 7, /* particle colouring + collider-side blocks + all other blocks */
+    B200MPM_KERNEL_BEGIN = 8, /* reset_hmap for the next substep (0 inside a substep: the tail of G2P) */
     B200MPM_KERNEL_G2P = 9, /* grid_update + g2p + particles_update */
     B200MPM_KERNEL_INTEGRATE_BODIES = 10,
     B200MPM_KERNEL_RIGID = 11, /* mesh-collider kernels (transform, mark / touch, p2g_cdf) */

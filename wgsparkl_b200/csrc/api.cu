@@ -63,8 +63,8 @@ struct b200mpm_data {
     int cur = 0;
     bool sorted_indirect = true; // sorted_ids is an indirection into `cur` (no full substep since the last sort)
     // The hash map / per-cell bins still hold a sort (after creation, a grid reallocation or b200mpm_sort_only): the
-    // next substep has to launch k_begin_substep itself. A complete substep leaves the grid clean (its graph runs the
-    // clearing beside k_g2p).
+    // next substep has to launch k_begin_substep itself. A complete substep leaves the grid clean (the tail of its
+    // k_g2p is the clearing).
     bool grid_dirty = true;
     uint32_t num_bodies = 0;
     std::vector<void*> allocs;
@@ -101,8 +101,6 @@ struct b200mpm_data {
     // The ORDERED read-backs scatter by original particle id into a buffer of num_particles entries: only valid when
     // the ids are the default 0..n-1 and there is no spare capacity (b200mpm_data_create_ex may break both).
     bool ordered_readback_ok = true;
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // Asynchronous position readback (b200mpm_read_positions_async): two device staging slots, a copy stream.
     cudaStream_t copy_stream = nullptr;
     float4* pos_stage[2] = {nullptr, nullptr};
@@ -224,14 +222,6 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
             PassTimer k(p, K + B200MPM_KERNEL_RIGID);
             launch_touch_rigid(c, d->dev);
         }
-        {
-            PassTimer k(p, K + B200MPM_KERNEL_COUNT);
-            launch_count(c, d->dev);
-        }
-        {
-            PassTimer k(p, K + B200MPM_KERNEL_SCAN);
-            launch_scan_cells(c, d->dev);
-        }
     }
     {
         PassTimer t(p, B200MPM_PASS_GRID_UPDATE_CDF);
@@ -250,34 +240,28 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
     }
 }
 
-// Enqueues one substep. With `side` the independent kernels are forked onto a second stream:
-//   begin [-> transform_rigid] -> touch [-> mark_rigid -> touch_rigid]
-//     -> { block_prepare [-> p2g_cdf]  ||  count -> scan } -> scatter -> { g2p_cdf -> p2g(cpic)  ||  p2g } -> g2p -> integrate
-//   ([..]: only with mesh colliders)
+// Enqueues one substep, a plain chain of five kernels (seven launches more with mesh colliders, [..]):
+//   [transform_rigid ->] touch (+ count, + the previous substep's integrate) [-> mark_rigid -> touch_rigid]
+//     -> block_prepare (+ the blocks' ranges) [-> p2g_cdf] -> scatter -> p2g -> g2p (+ the clearing for the next substep)
+//     [-> integrate]
+// Round 1 forked the independent kernels onto a second stream; the persistent kernels take every SM slot, so the
+// side branch never ran beside them, only before or after (profiles/r02_timeline.md) - each was folded into the
+// kernel it used to run next to.
+// `deferrable`: the caller replays this substep back to back (graph capture), see defer_integrate.
 // phase: PHASE_ALL = the whole substep; PHASE_BEGIN = up to and including P2G; PHASE_END = from G2P on
 // (sharded runs exchange the node halo and the body impulses between the two).
 enum { PHASE_ALL = 0, PHASE_BEGIN = 1, PHASE_END = 2, PHASE_SHARDED = 3 };
 
-void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cudaStream_t side, uint64_t* counter,
+void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, bool deferrable, uint64_t* counter,
                      int phase) {
     LaunchCfg c{p->dim, p->num_sms, main, counter};
-    LaunchCfg cs{p->dim, p->num_sms, side ? side : main, counter};
     const DeviceData& dev = d->dev;
-    // From G2P on: nothing reads the hash map or the per-cell bins any more, so the clearing for the NEXT substep
-    // (k_begin_substep) runs beside k_g2p instead of at the top of the critical path.
     // The body integration (<= 16 bodies, one warp: a pure latency chain of ~7 us) is DEFERRED in the single-GPU
-    // graph: it opens the side branch of the next substep, in front of k_block_prepare (the first kernel that looks
-    // at the poses again) and beside touch / count / scan; b200mpm_step flushes the last one.
-    const bool defer_integrate = side && phase == PHASE_ALL && dev.num_rigid == 0; // (mesh colliders: k_transform_rigid needs the poses first)
+    // graph: it rides in an extra CTA of the next substep's k_touch, i.e. in front of k_block_prepare (the first kernel
+    // that looks at the poses again); b200mpm_step flushes the last one.
+    const bool defer_integrate = deferrable && phase == PHASE_ALL && dev.num_rigid == 0; // (mesh colliders: k_transform_rigid needs the poses first)
     auto finish_substep = [&]() {
-        if (side) {
-            cudaEventRecord(d->ev[4], main);
-            cudaStreamWaitEvent(side, d->ev[4], 0);
-        }
-        launch_begin_substep(cs, dev);
-        if (side) cudaEventRecord(d->ev[5], side);
-        launch_g2p_update(c, dev, d->cur);
-        if (side) cudaStreamWaitEvent(main, d->ev[5], 0);
+        launch_g2p_update(c, dev, d->cur); // (its retiring CTAs clear the hash map and the bins for the next substep)
         if (!defer_integrate) launch_integrate_bodies(c, dev);
     };
     if (phase == PHASE_SHARDED) {
@@ -318,7 +302,7 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
             launch_emigrate(c, dev, d->cur, ml, mr, d->mig_cap, pl ? flag(pl, 1, 0) : nullptr, pr ? flag(pr, 0, 0) : nullptr, true);
             launch_immigrate_p2p(c, dev, d->cur, pl ? mig_buf(d->arena, 0) : nullptr, pr ? mig_buf(d->arena, 1) : nullptr,
                                  flag(d->arena, 0, 0), flag(d->arena, 1, 0), d->mig_cap);
-            enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
+            enqueue_substep(p, d, main, deferrable, counter, PHASE_BEGIN);
             launch_halo_pack(c, dev, hl, hr, d->halo_cap, pl ? flag(pl, 1, 1) : nullptr, pr ? flag(pr, 0, 1) : nullptr, true);
             if (left >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 0), d->halo_cap, flag(d->arena, 0, 1));
             if (right >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 1), d->halo_cap, flag(d->arena, 1, 1));
@@ -335,7 +319,7 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
             exchange(d->mig_send, d->mig_recv, mig_bytes);
             if (left >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[0], d->mig_cap);
             if (right >= 0) launch_immigrate(c, dev, d->cur, d->mig_recv[1], d->mig_cap);
-            enqueue_substep(p, d, main, side, counter, PHASE_BEGIN);
+            enqueue_substep(p, d, main, deferrable, counter, PHASE_BEGIN);
             launch_halo_pack(c, dev, d->halo_send[0], d->halo_send[1], d->halo_cap);
             exchange(d->halo_send, d->halo_recv, halo_bytes);
             if (left >= 0) launch_halo_add(c, dev, d->halo_recv[0], d->halo_cap);
@@ -346,7 +330,7 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
             nc.AllReduce(d->imp_buf, d->imp_buf, B200MPM_MAX_BODIES * 6, ncclInt32, ncclSum, d->comm, main); // exact
             launch_impulses_io(c, dev, d->imp_buf, 1);
         }
-        enqueue_substep(p, d, main, side, counter, PHASE_END);
+        enqueue_substep(p, d, main, deferrable, counter, PHASE_END);
         return;
     }
     if (phase == PHASE_END) {
@@ -354,24 +338,11 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, cu
         launch_drop_dead_tail(c, dev);
         return;
     }
-    if (defer_integrate) { // the previous substep's integration (no-op on the very first substep)
-        cudaEventRecord(d->ev[4], main);
-        cudaStreamWaitEvent(side, d->ev[4], 0);
-        launch_integrate_bodies(cs, dev);
-    }
     launch_transform_rigid(c, dev);
-    launch_touch(c, dev, d->cur);
+    launch_touch(c, dev, d->cur, defer_integrate); // (+ the previous substep's body integration, no-op on the first)
     launch_touch_rigid(c, dev);
-    if (side) {
-        cudaEventRecord(d->ev[0], main);
-        cudaStreamWaitEvent(side, d->ev[0], 0);
-    }
-    launch_block_prepare(cs, dev);
-    launch_p2g_cdf(cs, dev);
-    if (side) cudaEventRecord(d->ev[1], side);
-    launch_count(c, dev);
-    launch_scan_cells(c, dev);
-    if (side) cudaStreamWaitEvent(main, d->ev[1], 0);
+    launch_block_prepare(c, dev); // (+ the blocks' ranges in the sorted array: what used to be the scan)
+    launch_p2g_cdf(c, dev);
     launch_scatter(c, dev, d->cur);
     launch_p2g(c, dev, d->cur); // (with bodies: particle colouring "g2p_cdf" + collider-side blocks + all others, one kernel)
     if (phase == PHASE_BEGIN) return;
@@ -389,18 +360,13 @@ void ensure_clean_grid(b200mpm_pipeline* p, b200mpm_data* d) {
 bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
     const int par = d->cur;
     if (!d->graph_exec[par][phase]) {
-        if (!d->side) {
-            if (cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking) != cudaSuccess) return false;
-            for (auto& e : d->ev)
-                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
-        }
         cudaGraph_t graph = nullptr;
         uint64_t count = 0;
         if (cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        enqueue_substep(p, d, p->stream, d->side, &count, phase);
+        enqueue_substep(p, d, p->stream, true, &count, phase);
         if (cudaStreamEndCapture(p->stream, &graph) != cudaSuccess || !graph) {
             cudaGetLastError();
             return false;
@@ -429,7 +395,7 @@ bool run_substep_graph(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
 void run_phase(b200mpm_pipeline* p, b200mpm_data* d, int phase) {
     if (p->use_graphs && run_substep_graph(p, d, phase)) return;
     if (phase != PHASE_END) ensure_clean_grid(p, d);
-    enqueue_substep(p, d, p->stream, nullptr, &p->launches, phase);
+    enqueue_substep(p, d, p->stream, false, &p->launches, phase);
     d->grid_dirty = (phase == PHASE_BEGIN);
     if (phase != PHASE_BEGIN) {
         d->cur ^= 1;
@@ -454,12 +420,8 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
         launch_p2g(c, d->dev, d->cur);
     }
     {
-        PassTimer t(p, B200MPM_PASS_GRID_SORT); // reset_hmap for the next substep (beside k_g2p in the graph)
-        PassTimer k(p, K + B200MPM_KERNEL_BEGIN);
-        launch_begin_substep(c, d->dev);
-    }
-    {
-        PassTimer t(p, B200MPM_PASS_G2P); // grid_update + g2p + particles_update are one kernel here
+        // grid_update + g2p + particles_update are one kernel here (whose tail is reset_hmap for the next substep)
+        PassTimer t(p, B200MPM_PASS_G2P);
         PassTimer k(p, K + B200MPM_KERNEL_G2P);
         launch_g2p_update(c, d->dev, d->cur);
     }
@@ -822,8 +784,6 @@ void b200mpm_data_destroy(b200mpm_data* d) {
     for (auto& gp : d->graph_exec)
         for (auto& g : gp)
             if (g) cudaGraphExecDestroy(g);
-    for (auto& e : d->ev)
-        if (e) cudaEventDestroy(e);
     if (d->comm && nccl_api().ok) nccl_api().CommDestroy(d->comm);
     for (int k = 0; k < 2; ++k) {
         if (d->mig_send[k]) cudaFree(d->mig_send[k]);
@@ -835,7 +795,6 @@ void b200mpm_data_destroy(b200mpm_data* d) {
     for (int k = 0; k < 2; ++k)
         if (d->peer_arena[k]) cudaIpcCloseMemHandle(d->peer_arena[k]);
     if (d->arena) cudaFree(d->arena);
-    if (d->side) cudaStreamDestroy(d->side);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     for (int k = 0; k < 2; ++k) {
         if (d->pos_stage[k]) cudaFree(d->pos_stage[k]);

@@ -126,40 +126,71 @@ __device__ inline bool project_local_point_on_boundary(const BodyDev& b, const f
     return true;
 }
 
-// collide() (collision/collide.wgsl:23-55): closest collider, distance and affinity/sign bits
-// of a grid node at world position `point`.
+// World point -> body frame -> boundary projection -> world: the vector from `point` to its projection on body b's
+// boundary, and whether the point is inside (collide.wgsl:39-45).
 template <int D>
-__device__ inline NodeCdf collide(const BodyDev* __restrict__ bodies, uint32_t num_bodies, float cell_width,
+__device__ inline bool project_on_body(const BodyDev& b, const float* point, float* dpt) {
+    float d[D], loc[D], lp[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) d[k] = point[k] - b.trans[k];
+#pragma unroll
+    for (int r = 0; r < D; ++r) { // local = R^T (point - t)
+        float s = b.rot[r * D + 0] * d[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) s = s + b.rot[r * D + k] * d[k];
+        loc[r] = s;
+    }
+    const bool inside = project_local_point_on_boundary<D>(b, loc, lp);
+#pragma unroll
+    for (int r = 0; r < D; ++r) { // world = R lp + t
+        float s = b.rot[r] * lp[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) s = s + b.rot[k * D + r] * lp[k];
+        dpt[r] = (s + b.trans[r]) - point[r];
+    }
+    return inside;
+}
+
+// Can body b colour ANY node of the block whose first node sits at `origin`? Conservative: the block's nodes lie
+// within R = (BLOCK - 1) / 2 * h * sqrt(D) of its centre; if the centre is outside the body and farther than
+// R + 1.5 h sqrt(D) from its boundary, every node is outside too and farther than 1.5 h sqrt(D) from it, i.e. at
+// least one component of its projection vector exceeds the 1.5 h cap of collide(): the body leaves no trace on the
+// block and its per-node evaluation can be skipped (most blocks see no body at all).
+template <int D>
+__device__ inline bool body_may_touch_block(const BodyDev& b, float cell_width, const float* origin) {
+    if (b.shape_type == B200MPM_SHAPE_TRIMESH || b.shape_type == B200MPM_SHAPE_POLYLINE) return false; // collide.wgsl:41
+    const float half = 0.5f * (float)(Dim<D>::BLOCK - 1) * cell_width;
+    float centre[D], dpt[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) centre[k] = origin[k] + half;
+    if (project_on_body<D>(b, centre, dpt)) return true;
+    float dist2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) dist2 += dpt[k] * dpt[k];
+    const float root_d = (D == 2) ? 1.41421356f : 1.73205081f;
+    const float reach = (half + 1.5f * cell_width) * root_d * 1.001f; // (+ 0.1 % for the rounding of both sides)
+    return !(dist2 > reach * reach); // (NaN: keep the body)
+}
+
+// collide() (collision/collide.wgsl:23-55): closest collider, distance and affinity/sign bits
+// of a grid node at world position `point`. `body_mask`: the bodies to look at (see body_may_touch_block).
+template <int D>
+__device__ inline NodeCdf collide(const BodyDev* __restrict__ bodies, uint32_t body_mask, float cell_width,
                                   const float* point) {
     NodeCdf cdf{1.0e10f, 0u, NONE};
     const float dist_cap = cell_width * 1.5f;
-    for (uint32_t i = 0; i < num_bodies; ++i) {
+    for (uint32_t m = body_mask; m != 0u; m &= m - 1u) {
+        const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
         const BodyDev& b = bodies[i];
         if (b.shape_type == B200MPM_SHAPE_TRIMESH || b.shape_type == B200MPM_SHAPE_POLYLINE) continue; // collide.wgsl:41
-        // local = R^T (point - t)
-        float d[D], loc[D], lp[D], wp[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) d[k] = point[k] - b.trans[k];
-#pragma unroll
-        for (int r = 0; r < D; ++r) {
-            float s = b.rot[r * D + 0] * d[0];
-#pragma unroll
-            for (int k = 1; k < D; ++k) s = s + b.rot[r * D + k] * d[k];
-            loc[r] = s;
-        }
-        bool inside = project_local_point_on_boundary<D>(b, loc, lp);
-        // world = R lp + t
+        float dpt[D];
+        const bool inside = project_on_body<D>(b, point, dpt);
         bool all_le = true;
         float dist2 = 0.0f;
 #pragma unroll
         for (int r = 0; r < D; ++r) {
-            float s = b.rot[r] * lp[0];
-#pragma unroll
-            for (int k = 1; k < D; ++k) s = s + b.rot[k * D + r] * lp[k];
-            wp[r] = s + b.trans[r];
-            float dpt = wp[r] - point[r];
-            all_le = all_le && (fabsf(dpt) <= dist_cap);
-            dist2 = (r == 0) ? dpt * dpt : dist2 + dpt * dpt;
+            all_le = all_le && (fabsf(dpt[r]) <= dist_cap);
+            dist2 = (r == 0) ? dpt[r] * dpt[r] : dist2 + dpt[r] * dpt[r];
         }
         if (inside || all_le) {
             float dist = sqrtf(dist2);

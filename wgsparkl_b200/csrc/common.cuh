@@ -10,6 +10,7 @@
 namespace b2 {
 
 constexpr uint32_t NONE = 0xffffffffu; // grid.wgsl:80
+constexpr uint32_t HVAL_DROPPED = 0xfffffffeu; // hvals entry of a block created beyond the grid capacity
 constexpr int CELLS_PER_BLOCK = 64; // grid.wgsl:43
 constexpr uint32_t MAT_ID_MASK = 0x0fffffffu;
 constexpr uint32_t FLAG_DEAD = 0x40000000u; // the particle emigrated to a neighbour slab; dropped at the end of the substep
@@ -241,7 +242,10 @@ __device__ __forceinline__ uint32_t find_block(const uint32_t* __restrict__ hkey
     uint32_t slot = hash_key(packed) & cap_mask;
     for (uint32_t k = 0; k <= cap_mask; ++k) {
         uint32_t s = __ldg(hkeys + slot);
-        if (s == packed) return __ldg(hvals + slot);
+        if (s == packed) {
+            const uint32_t hid = __ldg(hvals + slot);
+            return hid == HVAL_DROPPED ? NONE : hid;
+        }
         if (s == NONE) return NONE;
         slot = (slot + 1) & cap_mask;
     }
@@ -328,6 +332,21 @@ __device__ __forceinline__ unsigned long long tl_now() {
 #define TL_BEGIN(d, k) do { } while (0)
 #define TL_END(d, k) do { } while (0)
 #endif
+// ---- reset_hmap (grid.wgsl:186-203) + clearing of the last sort's per-cell bins -------------------------------------
+// Nothing after P2G (and the halo exchange of sharded runs) reads the hash map or the bins any more - G2P works from
+// its item list - so the clearing for the NEXT substep does not sit at the top of the critical path: the CTAs of k_g2p
+// do it as they retire (as a kernel on a side branch it either ran in front of k_g2p, delaying part of its
+// statically scheduled grid, or waited for its first CTAs to retire anyway).
+__device__ __forceinline__ void clear_sparse_grid(const DeviceData& d, uint32_t tid, uint32_t stride) {
+    for (uint32_t i = tid; i < d.capacity; i += stride) d.hkeys[i] = NONE, d.hvals[i] = NONE; // (hvals: see publish_block)
+    // prev_active_blocks was published by the last k_scatter (0 before the first sort: the arrays are
+    // zero-initialised at creation)
+    const uint32_t prev = min(d.counters->prev_active_blocks, d.capacity);
+    const uint32_t nbins = prev * CELLS_PER_BLOCK + 1;
+    for (uint32_t i = tid; i < nbins; i += stride) d.cell_start[i] = 0;
+    if (tid == 0) d.counters->num_active_blocks = 0;
+}
+
 // ---- cp.async (LDGSTS): global -> shared without register staging -------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);

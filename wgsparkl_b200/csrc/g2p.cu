@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     }
     cp_async_wait_all();
     TL_END(d, B200MPM_KERNEL_G2P);
+    clear_sparse_grid(d, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x); // for the next substep
 
     // Particles of dropped blocks (capacity overflow only): carried over unchanged.
     const uint32_t dropped = d.counters->dropped_particles;
@@ -527,8 +528,8 @@ static void launch_g2p_dim(const LaunchCfg& c, const DeviceData& d, int cur) {
     }
 }
 
-void launch_g2p_update(const LaunchCfg& c, const DeviceData& d, int cur) {
-    if (d.n == 0) return;
+void launch_g2p_update(const LaunchCfg& c, const DeviceData& d, int cur) { // (+ the clearing for the next substep)
+    if (d.n == 0) return launch_begin_substep(c, d);
     if (c.dim == 2) launch_g2p_dim<2>(c, d, cur);
     else launch_g2p_dim<3>(c, d, cur);
     ++*c.launch_counter;

@@ -51,9 +51,7 @@ void launch_begin_substep(const LaunchCfg& c, const DeviceData& d);
 // update_world_mass_properties for all bodies (after data creation; pose / velocity writers refresh on their own).
 void launch_refresh_bodies(const LaunchCfg& c, const DeviceData& d);
 // "grid sort" pass (WgGrid::queue_sort, src/grid/grid.rs:30-207).
-void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur);
-void launch_count(const LaunchCfg& c, const DeviceData& d);
-void launch_scan_cells(const LaunchCfg& c, const DeviceData& d);
+void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur, bool integrate_first = false);
 void launch_block_prepare(const LaunchCfg& c, const DeviceData& d); // + "grid_update_cdf" pass
 void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur);
 // "p2g" pass.

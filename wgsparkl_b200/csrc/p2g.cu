@@ -334,11 +334,14 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
             b = d.p2g_list[(size_t)k * d.capacity + ((w - s_cum[k]) >> 1)];
         }
         const uint32_t cell = half * HALF + lane; // this lane's cell of the block
+        // (the blocks' ranges follow each other in arbitrary order - k_block_alloc - so the end of the block's last cell
+        // is the block's own end, not the next block's first bin)
+        const uint2 range = d.block_range[b];
         const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK + half * HALF];
-        const uint32_t last = d.cell_start[b * CELLS_PER_BLOCK + half * HALF + HALF];
+        const uint32_t last = half ? range.x + range.y : d.cell_start[b * CELLS_PER_BLOCK + HALF];
         if (first == last) continue; // nothing to scatter from this half
         const uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + cell];
-        const uint32_t end = d.cell_start[b * CELLS_PER_BLOCK + cell + 1];
+        const uint32_t end = (cell + 1u < (uint32_t)CELLS_PER_BLOCK) ? d.cell_start[b * CELLS_PER_BLOCK + cell + 1] : range.x + range.y;
         const int lx = cell & (B - 1), ly = (cell >> LB) & (B - 1), lz = (D == 3) ? (cell >> (2 * LB)) : 0;
         const int tb = lx + T * ly + T * T * lz;
         __syncwarp(); // the previous work item's tile / s_nbr are no longer read

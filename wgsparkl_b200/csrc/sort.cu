@@ -13,6 +13,7 @@
 // scatter atomic-free. The streaming kernels carry 4 particles per thread (memory-level parallelism).
 // Also here: the rigid-particle kernels of mesh colliders (transform, block activation, p2g_cdf as a scatter).
 #include "launch.h"
+#include "bodies.cuh"
 
 namespace b2 {
 
@@ -51,11 +52,11 @@ __device__ __forceinline__ uint32_t claim_block(const DeviceData& d, int bx, int
     return NONE;
 }
 
+// hvals[slot] is NONE from k_begin_substep until the block's creator publishes the dense index here (k_touch waits on
+// exactly that); a block beyond the capacity is published as HVAL_DROPPED, which every lookup treats as "absent".
 __device__ __forceinline__ void publish_block(const DeviceData& d, uint32_t slot, uint32_t hid, int4 vid) {
-    if (hid < d.capacity) {
-        d.block_vid[hid] = vid;
-        d.hvals[slot] = hid;
-    }
+    if (hid < d.capacity) d.block_vid[hid] = vid;
+    *((volatile uint32_t*)(d.hvals + slot)) = (hid < d.capacity) ? hid : HVAL_DROPPED;
 }
 
 // ---- touch_particle_blocks (sort.wgsl:26-36) ------------------------------------------------------
@@ -74,15 +75,45 @@ __device__ __forceinline__ void publish_block(const DeviceData& d, uint32_t slot
 constexpr int SORT_ITEMS = 4; // 2 is as fast, 8 is 3 % slower (measured)
 constexpr int SORT_PER_WARP = 32 * SORT_ITEMS;
 constexpr int SORT_PER_CTA = SORT_THREADS * SORT_ITEMS;
+#ifndef TOUCH_MIN_CTAS
+#define TOUCH_MIN_CTAS 6 // resident CTAs per SM that k_touch is compiled for (register cap)
+#endif
 
 template <int D>
-__global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
+__global__ void __launch_bounds__(SORT_THREADS, TOUCH_MIN_CTAS) k_touch(DeviceData d, int cur, int integrate) {
     pdl_start();
-    TL_BEGIN(d, B200MPM_KERNEL_TOUCH);
+    // `integrate`: the deferred body integration of the PREVIOUS substep (api.cu, enqueue_substep) rides along as an
+    // extra first CTA - nothing in this kernel looks at the bodies, k_block_prepare is the first that does. As a
+    // kernel of its own on a side branch it could not start before this kernel's single wave had drained.
     constexpr int NA = Dim<D>::NASSOC, WARPS = SORT_THREADS / 32, PER_ROUND = 32 / NA;
     __shared__ int4 s_lead[WARPS][SORT_PER_WARP]; // run leaders of a warp: block (x, y, z), then the slot in .w
+    static_assert(sizeof(s_lead) >= sizeof(BodyDev) * B200MPM_MAX_BODIES, "the integration stages the bodies in s_lead");
+    if (integrate) {
+        if (blockIdx.x == 0) {
+            if (threadIdx.x < 32) integrate_bodies_warp<D>(d, threadIdx.x, reinterpret_cast<BodyDev*>(&s_lead[0][0]));
+            return;
+        }
+    }
+    const uint32_t cta = blockIdx.x - (integrate ? 1u : 0u);
+    TL_BEGIN(d, B200MPM_KERNEL_TOUCH);
+    if (cta == 0 && threadIdx.x == 0) {
+        // Housekeeping for the kernels that follow (nobody reads these before k_block_alloc / k_scatter, and the readers
+        // of the last substep are long done): the work-list counters.
+        Counters* c = d.counters;
+        c->scan_ticket = 0;
+        c->work_p2g = 0;
+        c->work_p2g_cpic = 0;
+        c->work_g2p = 0;
+        c->work_cdf = 0;
+        c->num_cpic_blocks = 0;
+        c->num_g2p_items = 0;
+        c->num_g2p_back = 0;
+        for (uint32_t k = 0; k < P2G_BUCKETS; ++k) c->num_p2g[k] = 0;
+        c->dropped_particles = 0;
+        c->sorted_total = 0; // (bumped by k_block_alloc; the sharded tick has read the previous value already)
+    }
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t warp_base = (blockIdx.x * WARPS + warp) * SORT_PER_WARP;
+    const uint32_t warp_base = (cta * WARPS + warp) * SORT_PER_WARP;
     const uint32_t n_live = d.counters->n_live;
     const float h = d.sim->cell_width;
     const float inv_h = 1.0f / h;
@@ -143,19 +174,54 @@ __global__ void __launch_bounds__(SORT_THREADS) k_touch(DeviceData d, int cur) {
         }
     }
     __syncwarp();
+    // update_block_particle_count (sort.wgsl:89-99), one bin per cell, in the same kernel: the run's dense block index
+    // is there as soon as the block's creator has published it. Every publish of THIS warp is behind us, so the wait
+    // below only ever depends on warps that are already running and never wait before their own publishes.
+    for (uint32_t q = lane; q < num_leaders; q += 32) {
+        const uint32_t slot = (uint32_t)s_lead[warp][q].w;
+        uint32_t hid = NONE;
+        if (slot != NONE) {
+            const volatile uint32_t* hv = d.hvals + slot;
+            while ((hid = *hv) == NONE) {}
+            if (hid >= d.capacity) hid = NONE;
+        }
+        s_lead[warp][q].w = (int)hid;
+    }
+    __syncwarp();
+    uint32_t ck[SORT_ITEMS];
     before = 0;
 #pragma unroll
     for (int j = 0; j < SORT_ITEMS; ++j) {
-        const uint32_t i = warp_base + j * 32 + lane;
         const uint32_t upto = before + __popc(lmask[j] & (0xffffffffu >> (31 - lane))); // leaders at or before me
         before += __popc(lmask[j]);
+        ck[j] = NONE;
+        if (alive[j]) {
+            const uint32_t hid = (uint32_t)s_lead[warp][upto - 1].w;
+            if (hid != NONE) ck[j] = hid * CELLS_PER_BLOCK + cell[j];
+        }
+    }
+    // Runs of consecutive lanes in the same cell (the buffers are nearly sorted already) share one atomic.
+    uint32_t base[SORT_ITEMS];
+    int lead[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, ck[j], 1);
+        const bool leader = (lane == 0) || (prev != ck[j]);
+        const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
+        const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
+        const int L = 31 - __clz(below);
+        const uint32_t above = (L == 31) ? 0u : (leaders >> (L + 1));
+        const int run = above ? __ffs(above) : (32 - L);
+        lead[j] = L;
+        base[j] = (leader && ck[j] != NONE) ? atomicAdd(d.cell_start + ck[j], (uint32_t)run) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; ++j) {
+        const uint32_t i = warp_base + j * 32 + lane;
+        const uint32_t b = __shfl_sync(0xffffffffu, base[j], lead[j]);
         if (i < n_live) {
-            uint32_t pk = NONE;
-            if (alive[j]) {
-                const uint32_t slot = (uint32_t)s_lead[warp][upto - 1].w;
-                if (slot != NONE) pk = slot * CELLS_PER_BLOCK + cell[j];
-            }
-            d.pkey[i] = pk;
+            d.pkey[i] = ck[j];
+            d.rank[i] = b + (lane - (uint32_t)lead[j]);
         }
     }
     TL_END(d, B200MPM_KERNEL_TOUCH);
@@ -302,74 +368,6 @@ __global__ void k_p2g_cdf(DeviceData d) {
     }
 }
 
-// ---- update_block_particle_count (sort.wgsl:89-99), one bin per cell ---------------------------------
-__global__ void __launch_bounds__(SORT_THREADS) k_count(DeviceData d) {
-    pdl_start();
-    TL_BEGIN(d, B200MPM_KERNEL_COUNT);
-    {
-        // Housekeeping for the kernels that follow (nobody reads these before k_scan / k_scatter, and the readers of
-        // the last substep are long done): the work-list counters and the scan's tile descriptors.
-        const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-        if (tid == 0) {
-            Counters* c = d.counters;
-            c->scan_ticket = 0;
-            c->work_p2g = 0;
-            c->work_p2g_cpic = 0;
-            c->work_g2p = 0;
-            c->work_cdf = 0;
-            c->num_cpic_blocks = 0;
-            c->num_g2p_items = 0;
-            c->num_g2p_back = 0;
-            for (uint32_t k = 0; k < P2G_BUCKETS; ++k) c->num_p2g[k] = 0;
-            c->dropped_particles = 0;
-        }
-        const uint32_t nbins = min(d.counters->num_active_blocks, d.capacity) * CELLS_PER_BLOCK + 1;
-        const uint32_t ntiles = (nbins + SCAN_TILE - 1u) / SCAN_TILE;
-        for (uint32_t i = tid; i < ntiles + 1u; i += gridDim.x * blockDim.x) d.scan_state[i] = 0ull;
-    }
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SORT_PER_WARP;
-    const uint32_t n_live = d.counters->n_live;
-    uint32_t ck[SORT_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        const uint32_t i = warp_base + j * 32 + lane;
-        ck[j] = (i < n_live) ? d.pkey[i] : NONE;
-    }
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        if (ck[j] != NONE) {
-            const uint32_t hid = d.hvals[ck[j] >> 6];
-            ck[j] = (hid < d.capacity) ? hid * CELLS_PER_BLOCK + (ck[j] & 63u) : NONE;
-        }
-    }
-    // Runs of consecutive lanes in the same cell (the buffers are nearly sorted already) share one atomic.
-    uint32_t base[SORT_ITEMS];
-    int lead[SORT_ITEMS];
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        const uint32_t prev = __shfl_up_sync(0xffffffffu, ck[j], 1);
-        const bool leader = (lane == 0) || (prev != ck[j]);
-        const uint32_t leaders = __ballot_sync(0xffffffffu, leader);
-        const uint32_t below = leaders & (0xffffffffu >> (31 - lane));
-        const int L = 31 - __clz(below);
-        const uint32_t above = (L == 31) ? 0u : (leaders >> (L + 1));
-        const int run = above ? __ffs(above) : (32 - L);
-        lead[j] = L;
-        base[j] = (leader && ck[j] != NONE) ? atomicAdd(d.cell_start + ck[j], (uint32_t)run) : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
-        const uint32_t i = warp_base + j * 32 + lane;
-        const uint32_t b = __shfl_sync(0xffffffffu, base[j], lead[j]);
-        if (i < n_live) {
-            d.pkey[i] = ck[j];
-            d.rank[i] = b + (lane - (uint32_t)lead[j]);
-        }
-    }
-    TL_END(d, B200MPM_KERNEL_COUNT);
-}
-
 // ---- exclusive scan, single pass with decoupled look-back (replaces prefix_sum.wgsl) -----------------
 // Same result as WgPrefixSum::eval_cpu (prefix_sum.rs:71-83): out[i] = sum_{j<i} in[j].
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ data, uint32_t len_value,
@@ -473,30 +471,70 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(uint32_t* __restrict__ da
 #include "collide.cuh"
 namespace b2 {
 
+// One WARP per block (lane l owns cells / nodes l and l + 32), one block per warp in a single wave: everything a block
+// needs between k_touch and k_scatter.
+//  * copy_particles_len_to_scan_value + prefix sum + copy_scan_values_to_first_particles (sort.wgsl:101-115). The
+//    reference scans the per-block counts over the whole capacity. All the sort needs, though, is that every block
+//    owns a contiguous range of the sorted array - in WHICH order the blocks follow each other is immaterial (the
+//    reference's own order is the atomic order of its header ids). So there is no scan across blocks at all: the warp
+//    sums the block's 64 per-cell counts, takes the block's range with ONE atomicAdd on a bump counter (sorted_total)
+//    and turns the counts into the cells' first slots in place. No look-back chain, no tile descriptors (k_scan
+//    remains as the stand-alone b200mpm_prefix_sum_u32).
+//  * the neighbour table, the node reset (grid.wgsl:362-379) and grid_update_cdf (grid_update_cdf.wgsl:16-39).
+constexpr int PREPARE_THREADS = 256;
 template <int D>
-__global__ void __launch_bounds__(CELLS_PER_BLOCK) k_block_prepare(DeviceData d) {
+__global__ void __launch_bounds__(PREPARE_THREADS) k_block_prepare(DeviceData d) {
+    pdl_start();
     TL_BEGIN(d, B200MPM_KERNEL_BLOCK_PREPARE);
     const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-    const uint32_t t = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const float h = d.sim->cell_width;
     const uint32_t num_bodies = d.sim->num_bodies;
-    for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += warps) {
         const int4 vid = d.block_vid[b];
-        if (t < Dim<D>::NASSOC) {
-            int ox = t & 1, oy = (t >> 1) & 1, oz = (D == 3) ? (t >> 2) & 1 : 0;
-            uint32_t key = pack_key<D>(vid.x + ox, vid.y + oy, vid.z + oz);
-            d.nbr[b * Dim<D>::NASSOC + t] = (t == 0) ? b : find_block(d.hkeys, d.hvals, d.capacity - 1, key);
+        uint32_t* bins = d.cell_start + b * CELLS_PER_BLOCK;
+        const uint32_t c0 = bins[lane], c1 = bins[32 + lane];
+        if (lane < (uint32_t)Dim<D>::NASSOC) {
+            const int ox = lane & 1, oy = (lane >> 1) & 1, oz = (D == 3) ? (lane >> 2) & 1 : 0;
+            const uint32_t key = pack_key<D>(vid.x + ox, vid.y + oy, vid.z + oz);
+            d.nbr[b * Dim<D>::NASSOC + lane] = (lane == 0) ? b : find_block(d.hkeys, d.hvals, d.capacity - 1, key);
         }
-        d.node_mv[b * CELLS_PER_BLOCK + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t i0 = c0, i1 = c1; // inclusive scans of the two halves
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y0 = __shfl_up_sync(0xffffffffu, i0, o), y1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if ((int)lane >= o) i0 += y0, i1 += y1;
+        }
+        const uint32_t t0 = __shfl_sync(0xffffffffu, i0, 31), t1 = __shfl_sync(0xffffffffu, i1, 31);
+        uint32_t base = 0;
+        if (lane == 0 && t0 + t1 != 0u) base = atomicAdd(&d.counters->sorted_total, t0 + t1);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        bins[lane] = base + i0 - c0;
+        bins[32 + lane] = base + t0 + i1 - c1;
+        if (lane == 0) d.block_range[b] = make_uint2(base, t0 + t1);
+        d.node_mv[b * CELLS_PER_BLOCK + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        d.node_mv[b * CELLS_PER_BLOCK + 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (d.has_bodies) { // grid_update_cdf.wgsl:16-39
-            int lx = t & (Dim<D>::BLOCK - 1), ly = (t >> Dim<D>::LOG_BLOCK) & (Dim<D>::BLOCK - 1),
-                lz = (D == 3) ? (t >> (2 * Dim<D>::LOG_BLOCK)) : 0;
-            float pt[3] = {(float)(vid.x * Dim<D>::BLOCK + lx) * h, (float)(vid.y * Dim<D>::BLOCK + ly) * h,
-                           (float)(vid.z * Dim<D>::BLOCK + lz) * h};
-            NodeCdf c = collide<D>(d.bodies, num_bodies, h, pt);
-            d.node_cdf[b * CELLS_PER_BLOCK + t] = make_uint4(c.closest_id, __float_as_uint(c.distance), c.affinities, 0u);
-            const int any = __syncthreads_or(c.affinities != 0u);
-            if (t == 0) d.block_f0[b] = any ? 1 : 0;
+            // lane i looks at body i once for the whole block; the nodes then only visit the bodies within reach
+            const float origin[3] = {(float)(vid.x * Dim<D>::BLOCK) * h, (float)(vid.y * Dim<D>::BLOCK) * h,
+                                     (float)(vid.z * Dim<D>::BLOCK) * h};
+            const uint32_t body_mask =
+                __ballot_sync(0xffffffffu, lane < num_bodies && body_may_touch_block<D>(d.bodies[lane], h, origin));
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t t = lane + 32 * k;
+                const int lx = t & (Dim<D>::BLOCK - 1), ly = (t >> Dim<D>::LOG_BLOCK) & (Dim<D>::BLOCK - 1),
+                          lz = (D == 3) ? (t >> (2 * Dim<D>::LOG_BLOCK)) : 0;
+                float pt[3] = {(float)(vid.x * Dim<D>::BLOCK + lx) * h, (float)(vid.y * Dim<D>::BLOCK + ly) * h,
+                               (float)(vid.z * Dim<D>::BLOCK + lz) * h};
+                const NodeCdf c = collide<D>(d.bodies, body_mask, h, pt);
+                d.node_cdf[b * CELLS_PER_BLOCK + t] = make_uint4(c.closest_id, __float_as_uint(c.distance), c.affinities, 0u);
+                any |= c.affinities != 0u;
+            }
+            any = __any_sync(0xffffffffu, any);
+            if (lane == 0) d.block_f0[b] = any ? 1 : 0;
         }
     }
     TL_END(d, B200MPM_KERNEL_BLOCK_PREPARE);
@@ -515,12 +553,10 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
     {
         // Per-block work lists (i doubles as a block index here; the grid covers capacity blocks).
         const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-        if (i == 0) d.counters->sorted_total = d.cell_start[nb * CELLS_PER_BLOCK];
         uint32_t np = 0, first = 0;
         if (i < nb) {
-            first = d.cell_start[i * CELLS_PER_BLOCK];
-            np = d.cell_start[(i + 1) * CELLS_PER_BLOCK] - first;
-            d.block_range[i] = make_uint2(first, np);
+            const uint2 range = d.block_range[i]; // (k_block_alloc)
+            first = range.x, np = range.y;
         }
         uint32_t nbr[8];
 #pragma unroll
@@ -609,8 +645,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
         } else {
             // Particle of a dropped block (capacity overflow): parked after the sorted range so that
             // its state survives the ping-pong (see k_g2p tail).
-            uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
-            uint32_t total = d.cell_start[nb * CELLS_PER_BLOCK];
+            uint32_t total = d.counters->sorted_total;
             uint32_t k = atomicAdd(&d.counters->dropped_particles, 1u);
             d.sorted_ids[total + k] = p;
             // a LIVE particle without a block (capacity / hash overflow): sharded runs compact the parked tail away
@@ -624,10 +659,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
 // ---- launch wrappers ------------------------------------------------------------------------------------
 static inline int div_up(uint64_t a, uint64_t b) { return (int)((a + b - 1) / b); }
 
-void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur) {
-    if (d.n == 0) return;
-    if (c.dim == 2) launch_pdl(k_touch<2>, div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream, d, cur);
-    else launch_pdl(k_touch<3>, div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream, d, cur);
+void launch_touch(const LaunchCfg& c, const DeviceData& d, int cur, bool integrate_first) {
+    const int integrate = (integrate_first && d.has_bodies) ? 1 : 0;
+    if (d.n == 0) {
+        if (integrate) launch_integrate_bodies(c, d);
+        return;
+    }
+    const int ctas = div_up(d.n, SORT_PER_CTA) + integrate;
+    if (c.dim == 2) launch_pdl(k_touch<2>, ctas, SORT_THREADS, 0, c.stream, d, cur, integrate);
+    else launch_pdl(k_touch<3>, ctas, SORT_THREADS, 0, c.stream, d, cur, integrate);
     ++*c.launch_counter;
 }
 void launch_transform_rigid(const LaunchCfg& c, const DeviceData& d) {
@@ -656,24 +696,10 @@ void launch_p2g_cdf(const LaunchCfg& c, const DeviceData& d) {
     else k_p2g_cdf<3><<<div_up(d.num_rigid, 128), 128, 0, c.stream>>>(d);
     ++*c.launch_counter;
 }
-void launch_count(const LaunchCfg& c, const DeviceData& d) {
-    if (d.n == 0) return;
-    launch_pdl(k_count, div_up(d.n, SORT_PER_CTA), SORT_THREADS, 0, c.stream, d);
-    ++*c.launch_counter;
-}
-void launch_scan_cells(const LaunchCfg& c, const DeviceData& d) {
-    // Upper bound on tiles: every particle activates at most 2^D blocks, and never more than capacity.
-    uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
-    if (max_blocks > d.capacity) max_blocks = d.capacity;
-    uint32_t tiles = scan_num_tiles(max_blocks * CELLS_PER_BLOCK + 1);
-    launch_pdl(k_scan, tiles, SCAN_THREADS, 0, c.stream, d.cell_start, 0u, (const Counters*)d.counters, d.capacity, d.scan_state,
-               &d.counters->scan_ticket);
-    ++*c.launch_counter;
-}
 void launch_block_prepare(const LaunchCfg& c, const DeviceData& d) {
-    int grid = c.num_sms * 16;
-    if (c.dim == 2) k_block_prepare<2><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d);
-    else k_block_prepare<3><<<grid, CELLS_PER_BLOCK, 0, c.stream>>>(d);
+    const int grid = c.num_sms * (2048 / PREPARE_THREADS);
+    if (c.dim == 2) launch_pdl(k_block_prepare<2>, grid, PREPARE_THREADS, 0, c.stream, d);
+    else launch_pdl(k_block_prepare<3>, grid, PREPARE_THREADS, 0, c.stream, d);
     ++*c.launch_counter;
 }
 void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur) {
