@@ -166,10 +166,10 @@ def test_two_way_coupling_bodies(pipe3, oracle_mod):
     gv, ov = data.read_body_vels(), sim.read_body_vels()
     assert parity.field_rel_err(gp["translation"], op["translation"]) <= 1e-6
     assert parity.field_rel_err(gp["rotation"], op["rotation"]) <= 1e-6
-    # impulses are accumulated as i32(x * 1e5) per node (rigid_impulses.wgsl:50-58); the CUDA path
-    # truncates per (node, contributing block): a few 1e-5 absolute per node
-    assert parity.field_rel_err(gv["linear"], ov["linear"]) <= 1e-4
-    assert parity.field_rel_err(gv["angular"], ov["angular"]) <= 1e-4
+    # impulses are accumulated as i32(x * 1e5) per node (p2g.wgsl:142-155, rigid_impulses.wgsl:50-58) on both sides;
+    # what is left is the summation order of the node's float total in front of the truncation
+    el, ea = parity.field_rel_err(gv["linear"], ov["linear"]), parity.field_rel_err(gv["angular"], ov["angular"])
+    assert el <= 2e-6 and ea <= 2e-6, (el, ea)
     data.close()
 
 

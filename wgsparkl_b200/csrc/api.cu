@@ -156,6 +156,7 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
     if ((r = dev_alloc(d, &dev.nbr, (size_t)capacity * na, true, L))) return r;
     if ((r = dev_alloc(d, &dev.node_mv, (size_t)capacity * CELLS_PER_BLOCK, true, L))) return r;
     if (dev.has_bodies && (r = dev_alloc(d, &dev.node_cdf, (size_t)capacity * CELLS_PER_BLOCK, true, L))) return r;
+    if (dev.has_bodies && (r = dev_alloc(d, &dev.node_imp, (size_t)capacity * CELLS_PER_BLOCK * 2, true, L))) return r;
     if ((r = dev_alloc(d, &dev.block_flags, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.block_f0, capacity, true, L))) return r;
     if ((r = dev_alloc(d, &dev.cpic_list, capacity, true, L))) return r;

@@ -176,6 +176,10 @@ struct DeviceData {
     // one 64-bit key (distance in the high half; distances are >= 0, so the key orders like the distance) that the
     // mesh-collider scatter lowers with a single atomicMin (k_p2g_cdf).
     uint4* node_cdf;
+    // capacity*64*2 (with bodies): the node's body impulse (linear, angular) in float, summed over every block that
+    // scatters to it and converted to fixed point ONCE per node (p2g.wgsl:142-155) by k_node_impulses, which also
+    // clears it again: all zero outside launch_p2g.
+    float4* node_imp;
     uint64_t* scan_state; // single-pass scan tile descriptors
     uint8_t* block_f0; // capacity: 1 if one of the block's own nodes is near / inside a collider (k_block_prepare)
     uint32_t* block_flags; // capacity: 1 if the block's (BLOCK+2)^D tile holds a collider (k_scatter)

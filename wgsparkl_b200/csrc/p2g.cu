@@ -464,22 +464,64 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceDat
             if (D == 2) c.w = 0.0f; // 2D stores (px, py, mass, 0)
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f) atomicAdd(d.node_mv + node, c);
             if (IMP && cpic_item) {
-                uint32_t cid = tcdf[n].y;
-                if (cid != NONE) { // p2g.wgsl:142-155: integer atomics, i32(x * 1e5)
-                    BodyDev& body = d.bodies[cid];
+                // p2g.wgsl:142-155 converts the NODE's impulse to fixed point, once; this work item only holds a part
+                // of it, so the parts meet in float (node_imp) and k_node_impulses does the conversion.
+                if (tcdf[n].y != NONE) {
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; // (lin.xyz, 0, ang.xyz, 0); 2D: (lin.xy, 0, 0, ang, 0, 0, 0)
+                    bool any_lin = false, any_ang = false;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        float li = timp[n * WI + k];
-                        if (li != 0.0f) atomicAdd(&body.imp_lin[k], flt2int(li));
-                    }
+                    for (int k = 0; k < D; ++k) v[k] = timp[n * WI + k], any_lin |= v[k] != 0.0f;
 #pragma unroll
-                    for (int k = 0; k < WI - D; ++k) {
-                        float ai = timp[n * WI + D + k];
-                        if (ai != 0.0f) atomicAdd(&body.imp_ang[k], flt2int(ai));
-                    }
+                    for (int k = 0; k < WI - D; ++k) v[4 + k] = timp[n * WI + D + k], any_ang |= v[4 + k] != 0.0f;
+                    if (any_lin) atomicAdd(d.node_imp + 2 * node, make_float4(v[0], v[1], v[2], 0.0f));
+                    if (any_ang) atomicAdd(d.node_imp + 2 * node + 1, make_float4(v[4], v[5], v[6], 0.0f));
                 }
             }
         }
+    }
+}
+
+// Apply the impulse to the closest body (p2g.wgsl:142-155): IntegerImpulseAtomic, i32(x * 1e5) of the node's total.
+// One warp per block that holds a coloured node (block_f0), two nodes per lane; the fixed-point values are summed
+// per CTA in shared memory first (integer sums are exact in any order) and node_imp is left cleared.
+constexpr int IMPULSE_THREADS = 256;
+__global__ void __launch_bounds__(IMPULSE_THREADS) k_node_impulses(DeviceData d) {
+    __shared__ int s_imp[B200MPM_MAX_BODIES][6];
+    for (int i = threadIdx.x; i < (int)B200MPM_MAX_BODIES * 6; i += blockDim.x) (&s_imp[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t nb = min(d.counters->num_active_blocks, d.capacity);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += warps) {
+        if (!d.block_f0[b]) continue;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t node = b * CELLS_PER_BLOCK + lane + 32 * k;
+            const uint32_t cid = d.node_cdf[node].x;
+            if (cid >= B200MPM_MAX_BODIES) continue; // NONE: nobody scattered an impulse here
+            const float4 lin = d.node_imp[2 * node], ang = d.node_imp[2 * node + 1];
+            const float v[6] = {lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
+            bool any = false;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                if (v[c] != 0.0f) {
+                    atomicAdd(&s_imp[cid][c], flt2int(v[c]));
+                    any = true;
+                }
+            }
+            if (any) {
+                d.node_imp[2 * node] = make_float4(0.f, 0.f, 0.f, 0.f);
+                d.node_imp[2 * node + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)B200MPM_MAX_BODIES * 6; i += blockDim.x) {
+        const int v = (&s_imp[0][0])[i];
+        if (v == 0) continue;
+        BodyDev& body = d.bodies[i / 6];
+        const int c = i % 6;
+        atomicAdd(c < 3 ? &body.imp_lin[c] : &body.imp_ang[c - 3], v);
     }
 }
 
@@ -495,6 +537,8 @@ void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
         const int grid = c.num_sms * 7;
         if (c.dim == 2) launch_pdl(k_p2g<2, true, true>, grid, 32, 0, c.stream, d, cur);
         else launch_pdl(k_p2g<3, true, true>, grid, 32, 0, c.stream, d, cur);
+        k_node_impulses<<<c.num_sms * (2048 / IMPULSE_THREADS), IMPULSE_THREADS, 0, c.stream>>>(d);
+        ++*c.launch_counter;
     } else { // every body is immovable and at rest: no impulse can have an effect (rigid_impulses.wgsl:94-137)
         const int grid = c.num_sms * 9;
         if (c.dim == 2) launch_pdl(k_p2g<2, true, false>, grid, 32, 0, c.stream, d, cur);

@@ -72,12 +72,22 @@ __device__ __forceinline__ void publish_block(const DeviceData& d, uint32_t slot
 //
 // Dense block indices come from ONE counter (num_active_blocks); every substep re-creates ~20 k blocks per
 // million particles, so the blocks a warp creates in one round share a single atomic on it.
-constexpr int SORT_ITEMS = 4; // 2 is as fast, 8 is 3 % slower (measured)
+#ifndef TOUCH_ITEMS
+#define TOUCH_ITEMS 4
+#endif
+#ifndef SCATTER_ITEMS
+#define SCATTER_ITEMS 4
+#endif
+#ifndef TOUCH_MIN_CTAS
+#define TOUCH_MIN_CTAS 8 // resident CTAs per SM that k_touch is compiled for (register cap)
+#endif
+#ifndef SCATTER_MIN_CTAS
+#define SCATTER_MIN_CTAS 1
+#endif
+constexpr int SORT_ITEMS = TOUCH_ITEMS;
 constexpr int SORT_PER_WARP = 32 * SORT_ITEMS;
 constexpr int SORT_PER_CTA = SORT_THREADS * SORT_ITEMS;
-#ifndef TOUCH_MIN_CTAS
-#define TOUCH_MIN_CTAS 6 // resident CTAs per SM that k_touch is compiled for (register cap)
-#endif
+constexpr int SCATTER_PER_WARP = 32 * SCATTER_ITEMS;
 
 template <int D>
 __global__ void __launch_bounds__(SORT_THREADS, TOUCH_MIN_CTAS) k_touch(DeviceData d, int cur, int integrate) {
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(PREPARE_THREADS) k_block_prepare(DeviceData d)
 
 // ---- finalize_particles_sort (sort.wgsl:117-137): atomic-free scatter ------------------------------
 template <int D>
-__global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur) {
+__global__ void __launch_bounds__(SORT_THREADS, SCATTER_MIN_CTAS) k_scatter(DeviceData d, int cur) {
     pdl_start();
     TL_BEGIN(d, B200MPM_KERNEL_SCATTER);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -618,25 +628,25 @@ __global__ void __launch_bounds__(SORT_THREADS) k_scatter(DeviceData d, int cur)
             if (in) d.p2g_list[(size_t)k * d.capacity + pos] = i;
         }
     }
-    // particles: SORT_ITEMS per thread, see k_touch
+    // particles: SCATTER_ITEMS per thread, see k_touch
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SORT_PER_WARP;
+    const uint32_t warp_base = (blockIdx.x * (SORT_THREADS / 32) + warp) * SCATTER_PER_WARP;
     const uint32_t n_live = d.counters->n_live;
     if (warp_base >= n_live) {
         TL_END(d, B200MPM_KERNEL_SCATTER);
         return;
     }
-    uint32_t ck[SORT_ITEMS], rk[SORT_ITEMS], dest[SORT_ITEMS];
+    uint32_t ck[SCATTER_ITEMS], rk[SCATTER_ITEMS], dest[SCATTER_ITEMS];
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
+    for (int j = 0; j < SCATTER_ITEMS; ++j) {
         const uint32_t p = warp_base + j * 32 + lane;
         ck[j] = (p < n_live) ? d.pkey[p] : NONE;
         rk[j] = (p < n_live) ? d.rank[p] : 0u;
     }
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) dest[j] = (ck[j] != NONE) ? d.cell_start[ck[j]] + rk[j] : NONE;
+    for (int j = 0; j < SCATTER_ITEMS; ++j) dest[j] = (ck[j] != NONE) ? d.cell_start[ck[j]] + rk[j] : NONE;
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; ++j) {
+    for (int j = 0; j < SCATTER_ITEMS; ++j) {
         const uint32_t p = warp_base + j * 32 + lane;
         if (p >= n_live) continue;
         if (ck[j] != NONE) {
@@ -708,7 +718,7 @@ void launch_scatter(const LaunchCfg& c, const DeviceData& d, int cur) {
     // and in practice far fewer; the grid is sized for whichever is larger)
     uint64_t max_blocks = (uint64_t)d.n * (c.dim == 2 ? 4 : 8);
     if (max_blocks > d.capacity) max_blocks = d.capacity;
-    uint64_t ctas_p = div_up(d.n, SORT_PER_CTA), ctas_b = div_up(max_blocks, SORT_THREADS);
+    uint64_t ctas_p = div_up(d.n, SORT_THREADS * SCATTER_ITEMS), ctas_b = div_up(max_blocks, SORT_THREADS);
     int ctas = (int)(ctas_p > ctas_b ? ctas_p : ctas_b);
     if (c.dim == 2) launch_pdl(k_scatter<2>, ctas, SORT_THREADS, 0, c.stream, d, cur);
     else launch_pdl(k_scatter<3>, ctas, SORT_THREADS, 0, c.stream, d, cur);
