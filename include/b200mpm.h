@@ -217,9 +217,11 @@ int b200mpm_set_timestamps(b200mpm_pipeline* p, int enabled);
 int b200mpm_get_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_PASSES]);
 /* The same accumulation per kernel of this implementation (no reference counterpart; timestamps mode only). Syncs. */
 int b200mpm_get_kernel_timings(b200mpm_pipeline* p, double ms[B200MPM_NUM_KERNELS]);
-/* Debug: [2k] earliest start / [2k+1] latest end (GPU %globaltimer, ns) of kernel k since the last call, then reset.
- * Only libraries built with -DB200MPM_TIMELINE record anything (tools/timeline.py); otherwise the reset values
- * (all ones / zero) come back. Syncs. */
+/* Debug: [2k] earliest start / [2k+1] latest end (GPU %globaltimer, ns; all ones / zero for a kernel that did not run)
+ * of kernel k since the last call, then reset - what ran when INSIDE the graph replay, where events cannot look
+ * (tools/timeline.py, bench.py's in-graph kernel durations). The first call switches the recording on (thread 0 of
+ * every CTA stamps its start and end: two atomics) and returns the reset values; ns = NULL switches it off again.
+ * Either switch re-captures the substep graphs. Syncs. */
 int b200mpm_debug_timeline(b200mpm_data* d, uint64_t ns[2 * B200MPM_NUM_KERNELS]);
 
 /* ---- per-frame host writes / reads (src_testbed/step.rs:79-119,175-176, ui.rs:98-103) -- */

@@ -206,6 +206,38 @@ def test_timings_use_reference_pass_names(pipe3):
     data.close()
 
 
+def test_kernel_timings_and_in_graph_timeline(pipe3):
+    """Per-kernel event timers (booked on the reference's pass names as well) and the %globaltimer timeline of the
+    graph replay: the substep is a chain touch -> block_prepare -> scatter -> p2g -> g2p."""
+    scene = scenes.elastic_cube_3d(16, y_offset=-1.0)
+    data = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    pipe3.set_timestamps(True)
+    pipe3.queue_step(data, 4)
+    passes, kernels = pipe3.timings_ms(), pipe3.kernel_timings_ms()
+    pipe3.set_timestamps(False)
+    assert tuple(kernels.keys()) == abi.KERNEL_NAMES
+    for k in ("touch", "block_prepare", "scatter", "p2g", "g2p"):
+        assert kernels[k] > 0.0, k
+    assert abs(passes["p2g"] - kernels["p2g"]) <= 1e-6 and abs(passes["g2p"] - kernels["g2p"]) <= 1e-6
+    assert abs(sum(passes.values()) - sum(kernels.values())) <= 1e-4  # every kernel timer is booked on one pass
+    first = data.debug_timeline()  # switches the recording on
+    assert all(v is None for v in first.values())
+    ref = data.read_positions()
+    pipe3.queue_step(data, 1)
+    pipe3.sync()
+    tl = data.debug_timeline()
+    chain = [tl[k] for k in ("touch", "block_prepare", "scatter", "p2g", "g2p")]
+    assert all(c is not None and c[1] >= c[0] for c in chain)
+    for a, b in zip(chain, chain[1:]):
+        assert b[0] >= a[1] - 2000, (a, b)  # (the stamps are taken by thread 0 of a CTA: allow 2 us of skew)
+    assert chain[-1][1] - chain[0][0] < 5_000_000
+    data.debug_timeline(enable=False)
+    pipe3.queue_step(data, 1)
+    pipe3.sync()
+    assert np.isfinite(data.read_positions()).all() and not np.array_equal(ref, data.read_positions())
+    data.close()
+
+
 def test_async_position_readback_matches_blocking(pipe3):
     """b200mpm_read_positions_async: snapshots taken between steps land (after sync) with exactly the values
     the blocking read returns at the same points (up to atomic-order noise), also with three readbacks enqueued back to back."""

@@ -1,7 +1,6 @@
 """Timeline of ONE substep inside the graph replay (who starts / ends when, gaps, overlaps), from %globaltimer stamps
-that the kernels of a -DB200MPM_TIMELINE build take at their first and last CTA:
-    python tools/build_variant.py tl -DB200MPM_TIMELINE
-    B200MPM_LIB=wgsparkl_b200/_variants/lib_tl.so python tools/timeline.py cube1m [substeps_before]
+that the kernels take at their first and last CTA while b200mpm_debug_timeline has the recording switched on:
+    python tools/timeline.py cube1m [substeps_before]
 """
 import os
 import sys

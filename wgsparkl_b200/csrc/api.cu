@@ -33,7 +33,7 @@ int fail(int code, const std::string& msg) {
 
 struct EventPair {
     cudaEvent_t a, b;
-    int pass;
+    int kernel, pass; // B200MPM_KERNEL_*, and the reference pass (B200MPM_PASS_*) the kernel belongs to
 };
 
 } // namespace
@@ -46,6 +46,7 @@ struct b200mpm_pipeline {
     cudaStream_t own_stream = nullptr;
     uint64_t launches = 0;
     bool timestamps = false;
+    int cur_pass = 0; // the reference pass the kernel timers are booked on (PassTimer)
     bool use_graphs = true;
     std::vector<EventPair> events;
     std::vector<cudaEvent_t> event_pool;
@@ -169,12 +170,20 @@ int alloc_grid(b200mpm_data* d, uint32_t capacity) {
     return 0;
 }
 
-struct PassTimer { // queue.compute_pass(name, add_timestamps) (src/pipeline.rs:201)
+// queue.compute_pass(name, add_timestamps) (src/pipeline.rs:201). ONE pair of events per kernel: a PassTimer with a
+// pass id only names the reference pass that the kernel timers inside it are booked on (a second, nested pair of
+// events per pass added ~6 us of event overhead to every kernel measured inside it).
+struct PassTimer {
     b200mpm_pipeline* p;
     cudaEvent_t a = nullptr;
-    int pass; // pass id, or B200MPM_NUM_PASSES + kernel id for the kernel-level timers
-    PassTimer(b200mpm_pipeline* pipe, int pass_id) : p(pipe), pass(pass_id) {
+    int id, outer_pass = 0; // pass id, or B200MPM_NUM_PASSES + kernel id for the kernel-level timers
+    PassTimer(b200mpm_pipeline* pipe, int pass_or_kernel) : p(pipe), id(pass_or_kernel) {
         if (!p->timestamps) return;
+        if (id < B200MPM_NUM_PASSES) {
+            outer_pass = p->cur_pass;
+            p->cur_pass = id;
+            return;
+        }
         a = take();
         cudaEventRecord(a, p->stream);
     }
@@ -190,9 +199,13 @@ struct PassTimer { // queue.compute_pass(name, add_timestamps) (src/pipeline.rs:
     }
     ~PassTimer() {
         if (!p->timestamps) return;
+        if (id < B200MPM_NUM_PASSES) {
+            p->cur_pass = outer_pass;
+            return;
+        }
         cudaEvent_t b = take();
         cudaEventRecord(b, p->stream);
-        p->events.push_back(EventPair{a, b, pass});
+        p->events.push_back(EventPair{a, b, id - B200MPM_NUM_PASSES, p->cur_pass});
     }
 };
 
@@ -202,8 +215,8 @@ void fold_events(b200mpm_pipeline* p) {
     for (auto& e : p->events) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, e.a, e.b);
-        if (e.pass < B200MPM_NUM_PASSES) p->pass_ms[e.pass] += ms;
-        else p->kernel_ms[e.pass - B200MPM_NUM_PASSES] += ms;
+        p->pass_ms[e.pass] += ms;
+        p->kernel_ms[e.kernel] += ms;
         p->event_pool.push_back(e.a);
         p->event_pool.push_back(e.b);
     }
@@ -409,6 +422,7 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
     LaunchCfg c = p->cfg();
     {
         PassTimer t(p, B200MPM_PASS_UPDATE_RIGID_PARTICLES);
+        PassTimer k(p, B200MPM_NUM_PASSES + B200MPM_KERNEL_RIGID);
         ensure_clean_grid(p, d);
         launch_transform_rigid(c, d->dev);
     }
@@ -970,14 +984,28 @@ int b200mpm_set_timestamps(b200mpm_pipeline* p, int enabled) {
 }
 
 int b200mpm_debug_timeline(b200mpm_data* d, uint64_t ns[2 * B200MPM_NUM_KERNELS]) {
-    if (!d || !ns) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
+    if (!d) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     b200mpm_pipeline* p = d->pipe;
     if (!p) return fail(B200MPM_ERR_INVALID_ARGUMENT, "the pipeline of this data object was destroyed");
     CU_TRY(cudaSetDevice(p->device));
-    CU_TRY(cudaMemcpyAsync(ns, d->dev.timeline, sizeof(uint64_t) * 2 * B200MPM_NUM_KERNELS, cudaMemcpyDeviceToHost, p->stream));
-    CU_TRY(cudaStreamSynchronize(p->stream));
+    const bool want = ns != nullptr;
     uint64_t init[2 * B200MPM_NUM_KERNELS];
     for (int k = 0; k < B200MPM_NUM_KERNELS; ++k) init[2 * k] = ~0ull, init[2 * k + 1] = 0ull;
+    if (want != (d->dev.timeline_on != 0)) { // the switch is a kernel argument: the captured substeps are stale
+        CU_TRY(cudaStreamSynchronize(p->stream));
+        for (auto& gp : d->graph_exec)
+            for (auto& g : gp)
+                if (g) {
+                    cudaGraphExecDestroy(g);
+                    g = nullptr;
+                }
+        d->dev.timeline_on = want ? 1 : 0;
+        if (want) std::memcpy(ns, init, sizeof(init)); // nothing recorded yet
+    } else if (want) {
+        CU_TRY(cudaMemcpyAsync(ns, d->dev.timeline, sizeof(uint64_t) * 2 * B200MPM_NUM_KERNELS, cudaMemcpyDeviceToHost, p->stream));
+        CU_TRY(cudaStreamSynchronize(p->stream));
+    }
+    if (!want) return B200MPM_OK;
     CU_TRY(cudaMemcpyAsync(d->dev.timeline, init, sizeof(init), cudaMemcpyHostToDevice, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
     return B200MPM_OK;

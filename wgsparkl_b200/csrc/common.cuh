@@ -202,9 +202,10 @@ struct DeviceData {
     uint32_t* mv_body;
     SimState* sim;
     Counters* counters;
-    // Debug timeline (builds with -DB200MPM_TIMELINE only): [2k] = earliest start, [2k+1] = latest end of kernel k
-    // (B200MPM_KERNEL_*) in %globaltimer nanoseconds; read and reset by b200mpm_debug_timeline.
+    // Debug timeline (only while timeline_on, b200mpm_debug_timeline): [2k] = earliest start, [2k+1] = latest end of
+    // kernel k (B200MPM_KERNEL_*) in %globaltimer nanoseconds, stamped by thread 0 of every CTA.
     unsigned long long* timeline;
+    int timeline_on;
 };
 
 // ---- small math --------------------------------------------------------------------------
@@ -324,18 +325,13 @@ __device__ __forceinline__ int flt2int(float f) {
 }
 
 #if defined(__CUDACC__)
-#ifdef B200MPM_TIMELINE
 __device__ __forceinline__ unsigned long long tl_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define TL_BEGIN(d, k) do { if (threadIdx.x == 0) atomicMin((d).timeline + 2 * (k), tl_now()); } while (0)
-#define TL_END(d, k) do { if (threadIdx.x == 0) atomicMax((d).timeline + 2 * (k) + 1, tl_now()); } while (0)
-#else
-#define TL_BEGIN(d, k) do { } while (0)
-#define TL_END(d, k) do { } while (0)
-#endif
+#define TL_BEGIN(d, k) do { if ((d).timeline_on && threadIdx.x == 0) atomicMin((d).timeline + 2 * (k), tl_now()); } while (0)
+#define TL_END(d, k) do { if ((d).timeline_on && threadIdx.x == 0) atomicMax((d).timeline + 2 * (k) + 1, tl_now()); } while (0)
 // ---- reset_hmap (grid.wgsl:186-203) + clearing of the last sort's per-cell bins -------------------------------------
 // Nothing after P2G (and the halo exchange of sharded runs) reads the hash map or the bins any more - G2P works from
 // its item list - so the clearing for the NEXT substep does not sit at the top of the critical path: the CTAs of k_g2p

@@ -28,7 +28,15 @@
 
 namespace b2 {
 
-constexpr int P2G_CHUNK = 256; // particles staged per pass and warp: 32 cells x 8 (the reference's seeding density)
+#ifndef P2G_CHUNK_SIZE
+#define P2G_CHUNK_SIZE 256
+#endif
+#ifndef P2G_WARPS_PLAIN
+#define P2G_WARPS_PLAIN 10 // resident single-warp CTAs per SM: no bodies / bodies / bodies that react
+#define P2G_WARPS_CPIC 9
+#define P2G_WARPS_IMP 7
+#endif
+constexpr int P2G_CHUNK = P2G_CHUNK_SIZE; // particles staged per pass and warp: 32 cells x 8 (the reference's seeding density)
 
 enum { P2G_FAST = 0, P2G_CPIC_MOMENTUM = 1, P2G_CPIC_IMPULSE = 2 };
 
@@ -184,7 +192,7 @@ __device__ __forceinline__ bool p2g_accumulate(const DeviceData& d, int cur, uin
 //   IMP (with CPIC): some body can react to impulses (DeviceData::bodies_react) - without it the per-node impulse
 //   accumulators (27 x 6 registers, 5 KB of shared memory) and the second pass are compiled out.
 template <int D, bool CPIC, bool IMP>
-__global__ void __launch_bounds__(32, CPIC ? (IMP ? 7 : 9) : 10) k_p2g(DeviceData d, int cur) {
+__global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CPIC) : P2G_WARPS_PLAIN) k_p2g(DeviceData d, int cur) {
     constexpr int B = Dim<D>::BLOCK, LB = Dim<D>::LOG_BLOCK, T = Dim<D>::TILE, TC = Dim<D>::TILE_CELLS;
     constexpr int NA = Dim<D>::NASSOC, NBH = Dim<D>::NBH;
     constexpr int WI = (D == 3) ? 6 : 3; // impulse components per node
@@ -530,17 +538,17 @@ void launch_p2g(const LaunchCfg& c, const DeviceData& d, int cur) {
     // single-warp CTAs, as many per SM as the shared memory allows (22 KB each without bodies, 24.5 KB with, 29.6 KB
     // with impulse accumulators)
     if (!d.has_bodies) {
-        const int grid = c.num_sms * 10;
+        const int grid = c.num_sms * P2G_WARPS_PLAIN;
         if (c.dim == 2) launch_pdl(k_p2g<2, false, false>, grid, 32, 0, c.stream, d, cur);
         else launch_pdl(k_p2g<3, false, false>, grid, 32, 0, c.stream, d, cur);
     } else if (d.bodies_react) {
-        const int grid = c.num_sms * 7;
+        const int grid = c.num_sms * P2G_WARPS_IMP;
         if (c.dim == 2) launch_pdl(k_p2g<2, true, true>, grid, 32, 0, c.stream, d, cur);
         else launch_pdl(k_p2g<3, true, true>, grid, 32, 0, c.stream, d, cur);
         k_node_impulses<<<c.num_sms * (2048 / IMPULSE_THREADS), IMPULSE_THREADS, 0, c.stream>>>(d);
         ++*c.launch_counter;
     } else { // every body is immovable and at rest: no impulse can have an effect (rigid_impulses.wgsl:94-137)
-        const int grid = c.num_sms * 9;
+        const int grid = c.num_sms * P2G_WARPS_CPIC;
         if (c.dim == 2) launch_pdl(k_p2g<2, true, false>, grid, 32, 0, c.stream, d, cur);
         else launch_pdl(k_p2g<3, true, false>, grid, 32, 0, c.stream, d, cur);
     }

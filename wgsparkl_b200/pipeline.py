@@ -372,9 +372,12 @@ class MpmData:
             _check(code)
         return int(nb.value), code == ERR_GRID_OVERFLOW
 
-    def debug_timeline(self):
-        """{kernel: (first start, last end)} in GPU nanoseconds since the last call (libraries built with
-        -DB200MPM_TIMELINE only; None for kernels that did not run)."""
+    def debug_timeline(self, enable=True):
+        """{kernel: (first start, last end)} in GPU nanoseconds since the last call (None for kernels that did not
+        run). The first call switches the recording on and returns nothing but None; enable=False switches it off."""
+        if not enable:
+            _check(load_library().b200mpm_debug_timeline(self._h, None))
+            return {}
         raw = np.zeros(2 * len(abi.KERNEL_NAMES), dtype=np.uint64)
         _check(load_library().b200mpm_debug_timeline(self._h, abi.ptr(raw)))
         out = {}
