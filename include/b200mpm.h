@@ -171,7 +171,10 @@ enum {
     B200MPM_KERNEL_G2P = 9, /* grid_update + g2p + particles_update */
     B200MPM_KERNEL_INTEGRATE_BODIES = 10,
     B200MPM_KERNEL_RIGID = 11, /* mesh-collider kernels (transform, mark / touch, p2g_cdf) */
-    B200MPM_NUM_KERNELS = 12
+    B200MPM_KERNEL_SHARD_MIGRATE = 12, /* sharded runs: emigrate .. immigrate */
+    B200MPM_KERNEL_SHARD_HALO = 13, /* sharded runs: node-halo pack .. add */
+    B200MPM_KERNEL_SHARD_END = 14, /* sharded runs: live count of the next substep */
+    B200MPM_NUM_KERNELS = 15
 };
 
 typedef struct b200mpm_pipeline b200mpm_pipeline; /* MpmPipeline (src/pipeline.rs:24-39) */

@@ -211,6 +211,7 @@ def test_kernel_timings_and_in_graph_timeline(pipe3):
     graph replay: the substep is a chain touch -> block_prepare -> scatter -> p2g -> g2p."""
     scene = scenes.elastic_cube_3d(16, y_offset=-1.0)
     data = MpmData(pipe3, scene["params"], scene["particles"], scene["bodies"], scene["cell_width"], scene["grid_capacity"])
+    pipe3.timings_ms(), pipe3.kernel_timings_ms()  # (both accumulate since their last call: reset)
     pipe3.set_timestamps(True)
     pipe3.queue_step(data, 4)
     passes, kernels = pipe3.timings_ms(), pipe3.kernel_timings_ms()

@@ -35,7 +35,7 @@ PASS_NAMES = (  # src/pipeline.rs:201-271
 
 KERNEL_NAMES = (  # include/b200mpm.h B200MPM_KERNEL_*
     "touch", "count", "scan", "block_prepare", "scatter", "g2p_cdf", "p2g_cpic", "p2g", "begin", "g2p",
-    "integrate_bodies", "rigid",
+    "integrate_bodies", "rigid", "shard_migrate", "shard_halo", "shard_end",
 )
 
 sim_params_dtype = np.dtype([("gravity", "<f4", 3), ("dt", "<f4")])

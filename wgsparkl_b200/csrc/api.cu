@@ -267,13 +267,16 @@ void run_sort(b200mpm_pipeline* p, b200mpm_data* d) {
 enum { PHASE_ALL = 0, PHASE_BEGIN = 1, PHASE_END = 2, PHASE_SHARDED = 3 };
 
 void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, bool deferrable, uint64_t* counter,
-                     int phase) {
+                     int phase, bool outer_defers = false) {
     LaunchCfg c{p->dim, p->num_sms, main, counter};
     const DeviceData& dev = d->dev;
     // The body integration (<= 16 bodies, one warp: a pure latency chain of ~7 us) is DEFERRED in the single-GPU
     // graph: it rides in an extra CTA of the next substep's k_touch, i.e. in front of k_block_prepare (the first kernel
     // that looks at the poses again); b200mpm_step flushes the last one.
-    const bool defer_integrate = deferrable && phase == PHASE_ALL && dev.num_rigid == 0; // (mesh colliders: k_transform_rigid needs the poses first)
+    // (mesh colliders: k_transform_rigid needs the poses first; sharded: the peer-to-peer substep only - its PHASE_BEGIN
+    // half is told through outer_defers)
+    const bool defer_integrate = outer_defers || (deferrable && dev.num_rigid == 0 &&
+                                                  (phase == PHASE_ALL || (phase == PHASE_SHARDED && d->p2p_ready)));
     auto finish_substep = [&]() {
         launch_g2p_update(c, dev, d->cur); // (its retiring CTAs clear the hash map and the bins for the next substep)
         if (!defer_integrate) launch_integrate_bodies(c, dev);
@@ -312,14 +315,14 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, bo
             void* mr = pr ? (void*)mig_buf(pr, 0) : d->mig_send[1];
             void* hl = pl ? (void*)halo_buf(pl, 1) : d->halo_send[0];
             void* hr = pr ? (void*)halo_buf(pr, 0) : d->halo_send[1];
-            launch_shard_tick(c, dev);
-            launch_emigrate(c, dev, d->cur, ml, mr, d->mig_cap, pl ? flag(pl, 1, 0) : nullptr, pr ? flag(pr, 0, 0) : nullptr, true);
+            // tick + the emigrants k_g2p listed + publication: one CTA
+            launch_emigrate_listed(c, dev, d->cur, ml, mr, d->mig_cap, pl ? flag(pl, 1, 0) : nullptr, pr ? flag(pr, 0, 0) : nullptr);
             launch_immigrate_p2p(c, dev, d->cur, pl ? mig_buf(d->arena, 0) : nullptr, pr ? mig_buf(d->arena, 1) : nullptr,
                                  flag(d->arena, 0, 0), flag(d->arena, 1, 0), d->mig_cap);
-            enqueue_substep(p, d, main, deferrable, counter, PHASE_BEGIN);
+            enqueue_substep(p, d, main, deferrable, counter, PHASE_BEGIN, defer_integrate);
             launch_halo_pack(c, dev, hl, hr, d->halo_cap, pl ? flag(pl, 1, 1) : nullptr, pr ? flag(pr, 0, 1) : nullptr, true);
-            if (left >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 0), d->halo_cap, flag(d->arena, 0, 1));
-            if (right >= 0) launch_halo_add(c, dev, halo_buf(d->arena, 1), d->halo_cap, flag(d->arena, 1, 1));
+            launch_halo_add(c, dev, left >= 0 ? halo_buf(d->arena, 0) : nullptr, right >= 0 ? halo_buf(d->arena, 1) : nullptr,
+                            d->halo_cap, flag(d->arena, 0, 1), flag(d->arena, 1, 1));
             if (d->bodies_react) {
                 launch_impulses_io(c, dev, d->imp_buf, 0);
                 nc.AllReduce(d->imp_buf, d->imp_buf, B200MPM_MAX_BODIES * 6, ncclInt32, ncclSum, d->comm, main); // exact
@@ -336,8 +339,7 @@ void enqueue_substep(b200mpm_pipeline* p, b200mpm_data* d, cudaStream_t main, bo
             enqueue_substep(p, d, main, deferrable, counter, PHASE_BEGIN);
             launch_halo_pack(c, dev, d->halo_send[0], d->halo_send[1], d->halo_cap);
             exchange(d->halo_send, d->halo_recv, halo_bytes);
-            if (left >= 0) launch_halo_add(c, dev, d->halo_recv[0], d->halo_cap);
-            if (right >= 0) launch_halo_add(c, dev, d->halo_recv[1], d->halo_cap);
+            launch_halo_add(c, dev, left >= 0 ? d->halo_recv[0] : nullptr, right >= 0 ? d->halo_recv[1] : nullptr, d->halo_cap);
         }
         if (d->bodies_react) {
             launch_impulses_io(c, dev, d->imp_buf, 0);
@@ -1427,7 +1429,7 @@ int b200mpm_shard_halo_pack(b200mpm_pipeline* p, b200mpm_data* d, void* dev_left
 int b200mpm_shard_halo_add(b200mpm_pipeline* p, b200mpm_data* d, const void* dev_buffer, uint32_t cap_blocks) {
     if (!p || !d || d->pipe != p || !dev_buffer) return fail(B200MPM_ERR_INVALID_ARGUMENT, "null argument");
     CU_TRY(cudaSetDevice(p->device));
-    launch_halo_add(p->cfg(), d->dev, dev_buffer, cap_blocks);
+    launch_halo_add(p->cfg(), d->dev, dev_buffer, nullptr, cap_blocks);
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;
 }
@@ -1527,10 +1529,20 @@ int b200mpm_shard_p2p_connect(b200mpm_pipeline* p, b200mpm_data* d, const void* 
         d->peer_arena[k] = (char*)ptr;
     }
     for (auto& gp : d->graph_exec)
-        if (gp[PHASE_SHARDED]) {
-            cudaGraphExecDestroy(gp[PHASE_SHARDED]);
-            gp[PHASE_SHARDED] = nullptr;
-        }
+        for (auto& g : gp)
+            if (g) { // (k_g2p's argument block changes below: every captured substep is stale)
+                cudaGraphExecDestroy(g);
+                g = nullptr;
+            }
+    // From here on k_g2p lists the particles that leave the slab, and the migration packs that list instead of
+    // scanning the slab (shard.cu); whoever is outside already is listed once, now.
+    if (!d->dev.emig_list) {
+        d->dev.emig_cap = 2 * d->mig_cap;
+        int r = dev_alloc(d, &d->dev.emig_list, d->dev.emig_cap);
+        if (r) return r;
+        launch_list_emigrants(p->cfg(), d->dev, d->cur);
+        CU_TRY(cudaStreamSynchronize(p->stream));
+    }
     d->p2p_ready = true;
     return B200MPM_OK;
 }
@@ -1544,6 +1556,7 @@ int b200mpm_shard_step(b200mpm_pipeline* p, b200mpm_data* d, uint32_t num_subste
         if (r) return r;
     }
     for (uint32_t s = 0; s < num_substeps; ++s) run_phase(p, d, PHASE_SHARDED);
+    launch_integrate_bodies(p->cfg(), d->dev); // flushes the integration the last graph replay deferred (else a no-op)
     CU_TRY(cudaGetLastError());
     return B200MPM_OK;
 }

@@ -114,6 +114,8 @@ struct Counters {
     uint32_t halo_count[2]; // blocks packed for the -x / +x neighbour (sharded runs)
     uint32_t shard_seq; // substep sequence number of the peer-to-peer exchange flags
     uint32_t n_base; // live count at the start of the substep: where the immigrants are appended
+    uint32_t emig_count; // entries of emig_list (k_g2p appends, k_emigrate_listed consumes and resets)
+    uint32_t halo_ticket; // CTAs of k_halo_pack that are done (the last one publishes)
     uint32_t num_p2g[P2G_BUCKETS]; // entries of every population bucket of p2g_list (bucket 0 = most particles)
     uint32_t sorted_total; // particles in the sorted range this substep (== cell_start[num_active_blocks * 64])
     uint32_t integrate_pending; // a substep ran since the last k_integrate_bodies (which may be deferred, api.cu)
@@ -206,6 +208,10 @@ struct DeviceData {
     // kernel k (B200MPM_KERNEL_*) in %globaltimer nanoseconds, stamped by thread 0 of every CTA.
     unsigned long long* timeline;
     int timeline_on;
+    // Peer-to-peer sharded runs: slots (in the buffers k_g2p writes) of the particles whose new position left the slab,
+    // so that the migration packs a few hundred particles instead of scanning all of them. Null otherwise.
+    uint32_t* emig_list;
+    uint32_t emig_cap;
 };
 
 // ---- small math --------------------------------------------------------------------------

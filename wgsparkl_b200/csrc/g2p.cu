@@ -66,9 +66,10 @@ struct __align__(16) G2PShared {
     uint32_t ids[G2P_IQ][G2P_THREADS]; // item i's particle ids in row i % G2P_IQ (each thread reads its own)
     Material mats[G2P_SMEM_MATS];
     float h, dt, grav[3], inv_h, inv_d, vel_limit;
+    int slab_lo, slab_hi;
 };
 
-template <int D, bool PLASTIC, bool CPIC, int CTAS>
+template <int D, bool PLASTIC, bool CPIC, int CTAS, bool SHARDED>
 __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     // The launch wrapper hands over the ping-pong arrays already swapped: index 0 = current, 1 = next, so that every
     // array base is a constant-bank operand instead of a register pair.
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
         sm.inv_h = 1.0f / sm.h;
         sm.inv_d = 4.0f / (sm.h * sm.h); // kernel.wgsl:57-59
         sm.vel_limit = sm.h / sm.dt;
+        sm.slab_lo = d.sim->slab_lo, sm.slab_hi = d.sim->slab_hi;
     }
     if (mats_in_smem && t < (int)(d.num_materials * 4u)) ((float4*)sm.mats)[t] = ((const float4*)d.materials)[t];
 
@@ -443,6 +445,13 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
 
             // ---- write to the other buffer at the sorted slot
             d.pos4[nxt][k] = make_float4(new_pos.x, new_pos.y, new_pos.z, __uint_as_float(flags));
+            if (SHARDED) { // whoever left the slab is listed for the next substep's migration (shard.cu)
+                const int bx = assoc_cell(new_pos.x, h, inv_h) >> Dim<D>::LOG_BLOCK;
+                if (bx < sm.slab_lo || bx >= sm.slab_hi) {
+                    const uint32_t slot = atomicAdd(&d.counters->emig_count, 1u);
+                    if (slot < d.emig_cap) d.emig_list[slot] = k;
+                }
+            }
             d.vel4[nxt][k] = make_float4(vel.x, vel.y, vel.z, v4.w);
             d.Fa[nxt][k] = make_float4(Fn[0], Fn[1], Fn[2], Fn[3]);
             d.Ca[nxt][k] = make_float4(Cn[0], Cn[1], Cn[2], Cn[3]);
@@ -487,10 +496,12 @@ __global__ void __launch_bounds__(G2P_THREADS, CTAS) k_g2p(DeviceData d) {
     }
 }
 
-template <int D, bool PLASTIC, bool CPIC>
+// SHARDED: peer-to-peer slab runs (DeviceData::emig_list); an instantiation of its own because the kernel sits at its
+// register cap - the few extra instructions cost the unsharded path 1 % when they were merely branched over.
+template <int D, bool PLASTIC, bool CPIC, bool SHARDED>
 static void launch_g2p_inst(const LaunchCfg& c, const DeviceData& d, int cur) {
     constexpr int CTAS = PLASTIC ? G2P_CTAS_PLASTIC : G2P_CTAS_ELASTIC;
-    auto kernel = k_g2p<D, PLASTIC, CPIC, CTAS>;
+    auto kernel = k_g2p<D, PLASTIC, CPIC, CTAS, SHARDED>;
     constexpr size_t smem = sizeof(G2PShared<D, PLASTIC, CPIC>);
     static int resident = 0; // CTAs per SM (one process drives one device). The static work split needs the whole grid resident.
     if (!resident) {
@@ -517,21 +528,26 @@ static void launch_g2p_inst(const LaunchCfg& c, const DeviceData& d, int cur) {
     launch_pdl(kernel, c.num_sms * resident, G2P_THREADS, smem, c.stream, dd);
 }
 
-template <int D>
+template <int D, bool SHARDED>
 static void launch_g2p_dim(const LaunchCfg& c, const DeviceData& d, int cur) {
     if (d.has_plastic) {
-        if (d.has_bodies) launch_g2p_inst<D, true, true>(c, d, cur);
-        else launch_g2p_inst<D, true, false>(c, d, cur);
+        if (d.has_bodies) launch_g2p_inst<D, true, true, SHARDED>(c, d, cur);
+        else launch_g2p_inst<D, true, false, SHARDED>(c, d, cur);
     } else {
-        if (d.has_bodies) launch_g2p_inst<D, false, true>(c, d, cur);
-        else launch_g2p_inst<D, false, false>(c, d, cur);
+        if (d.has_bodies) launch_g2p_inst<D, false, true, SHARDED>(c, d, cur);
+        else launch_g2p_inst<D, false, false, SHARDED>(c, d, cur);
     }
 }
 
 void launch_g2p_update(const LaunchCfg& c, const DeviceData& d, int cur) { // (+ the clearing for the next substep)
     if (d.n == 0) return launch_begin_substep(c, d);
-    if (c.dim == 2) launch_g2p_dim<2>(c, d, cur);
-    else launch_g2p_dim<3>(c, d, cur);
+    if (d.emig_list) {
+        if (c.dim == 2) launch_g2p_dim<2, true>(c, d, cur);
+        else launch_g2p_dim<3, true>(c, d, cur);
+    } else {
+        if (c.dim == 2) launch_g2p_dim<2, false>(c, d, cur);
+        else launch_g2p_dim<3, false>(c, d, cur);
+    }
     ++*c.launch_counter;
 }
 

@@ -72,8 +72,11 @@ void launch_gather_positions(const LaunchCfg& c, const DeviceData& d, int cur, f
 void launch_gather_particles(const LaunchCfg& c, const DeviceData& d, int cur, b200mpm_particle* out, uint32_t* ids);
 
 // Slab sharding (shard.cu)
-void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap,
-                     uint32_t* left_flag = nullptr, uint32_t* right_flag = nullptr, bool p2p = false);
+void launch_emigrate(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap);
+// peer-to-peer: tick + the particles k_g2p listed + publication, one CTA
+void launch_emigrate_listed(const LaunchCfg& c, const DeviceData& d, int cur, void* left, void* right, uint32_t cap,
+                            uint32_t* left_flag, uint32_t* right_flag);
+void launch_list_emigrants(const LaunchCfg& c, const DeviceData& d, int cur);
 void launch_shard_tick(const LaunchCfg& c, const DeviceData& d);
 void launch_immigrate_p2p(const LaunchCfg& c, const DeviceData& d, int cur, const void* from_left, const void* from_right,
                           const uint32_t* flag_left, const uint32_t* flag_right, uint32_t cap);
@@ -81,7 +84,8 @@ void launch_immigrate(const LaunchCfg& c, const DeviceData& d, int cur, const vo
 void launch_drop_dead_tail(const LaunchCfg& c, const DeviceData& d);
 void launch_halo_pack(const LaunchCfg& c, const DeviceData& d, void* left, void* right, uint32_t cap,
                       uint32_t* left_flag = nullptr, uint32_t* right_flag = nullptr, bool p2p = false);
-void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in, uint32_t cap, const uint32_t* flag = nullptr);
+void launch_halo_add(const LaunchCfg& c, const DeviceData& d, const void* in_left, const void* in_right, uint32_t cap,
+                     const uint32_t* flag_left = nullptr, const uint32_t* flag_right = nullptr);
 void launch_impulses_io(const LaunchCfg& c, const DeviceData& d, int* buf, int write);
 void launch_gather_grid(const LaunchCfg& c, const DeviceData& d, b200mpm_block_info* blocks, b200mpm_node* nodes,
                         uint32_t max_blocks);
