@@ -322,36 +322,62 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
         __syncwarp();
     };
 
-    while (true) {
-        uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(work, 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= nwork) {
-            TL_END(d, B200MPM_KERNEL_P2G);
-            break;
-        }
+    // The work loop is software-pipelined by hand: every item starts with a chain of dependent L2 round trips (work
+    // counter -> block list -> ranges / bins, ~2.5 us that a single-warp CTA cannot hide by itself), so the NEXT item's
+    // chain is issued piecewise while the current item stages and scatters: its queue index is requested before the
+    // staging, its block id after the staging has landed, its ranges after the first chunk.
+    struct Meta {
+        uint32_t first, last, start, end; // sorted range of the half block, and of this lane's cell
+        int vx, vy, vz; // block coordinates
+    };
+    const auto lookup = [&](uint32_t w) -> uint32_t { // work index -> block
+        if (CPIC && w < ncpic) return d.cpic_list[w >> 1];
+        uint32_t k = 0;
+#pragma unroll
+        for (uint32_t q = 1; q < P2G_BUCKETS; ++q) k += (w >= s_cum[q]) ? 1u : 0u;
+        return d.p2g_list[(size_t)k * d.capacity + ((w - s_cum[k]) >> 1)];
+    };
+    const auto load_meta = [&](uint32_t w, uint32_t b) -> Meta {
+        const uint32_t half = w & 1u, cell = half * HALF + lane;
+        // (the blocks' ranges follow each other in arbitrary order - k_block_prepare - so the end of the block's last
+        // cell is the block's own end, not the next block's first bin)
+        const uint2 range = d.block_range[b];
+        const int4 vid = d.block_vid[b];
+        Meta m;
+        m.first = d.cell_start[b * CELLS_PER_BLOCK + half * HALF];
+        m.last = half ? range.x + range.y : d.cell_start[b * CELLS_PER_BLOCK + HALF];
+        m.start = d.cell_start[b * CELLS_PER_BLOCK + cell];
+        m.end = (cell + 1u < (uint32_t)CELLS_PER_BLOCK) ? d.cell_start[b * CELLS_PER_BLOCK + cell + 1] : range.x + range.y;
+        m.vx = vid.x, m.vy = vid.y, m.vz = vid.z;
+        return m;
+    };
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(work, 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    uint32_t b = (w < nwork) ? lookup(w) : 0u;
+    Meta meta = {};
+    if (w < nwork) meta = load_meta(w, b);
+    while (w < nwork) {
+        uint32_t wn = 0; // (1) the next item's queue index: requested now, read after the staging
+        if (lane == 0) wn = atomicAdd(work, 1u);
+        uint32_t bn = 0;
+        Meta meta_n = {};
         const uint32_t half = w & 1u; // (ncpic is even)
         const bool cpic_item = CPIC && w < ncpic; // (warp-uniform)
-        uint32_t b;
-        if (cpic_item) {
-            b = d.cpic_list[w >> 1];
-        } else {
-            uint32_t k = 0;
-#pragma unroll
-            for (uint32_t q = 1; q < P2G_BUCKETS; ++q) k += (w >= s_cum[q]) ? 1u : 0u;
-            b = d.p2g_list[(size_t)k * d.capacity + ((w - s_cum[k]) >> 1)];
-        }
         const uint32_t cell = half * HALF + lane; // this lane's cell of the block
-        // (the blocks' ranges follow each other in arbitrary order - k_block_alloc - so the end of the block's last cell
-        // is the block's own end, not the next block's first bin)
-        const uint2 range = d.block_range[b];
-        const uint32_t first = d.cell_start[b * CELLS_PER_BLOCK + half * HALF];
-        const uint32_t last = half ? range.x + range.y : d.cell_start[b * CELLS_PER_BLOCK + HALF];
-        if (first == last) continue; // nothing to scatter from this half
-        const uint32_t start = d.cell_start[b * CELLS_PER_BLOCK + cell];
-        const uint32_t end = (cell + 1u < (uint32_t)CELLS_PER_BLOCK) ? d.cell_start[b * CELLS_PER_BLOCK + cell + 1] : range.x + range.y;
+        const uint32_t first = meta.first, last = meta.last, start = meta.start, end = meta.end;
+        const bool empty = first == last; // nothing to scatter from this half (warp-uniform)
         const int lx = cell & (B - 1), ly = (cell >> LB) & (B - 1), lz = (D == 3) ? (cell >> (2 * LB)) : 0;
         const int tb = lx + T * ly + T * T * lz;
+        if (empty) { // (rare: just keep the pipeline going)
+            wn = __shfl_sync(0xffffffffu, wn, 0);
+            if (wn < nwork) {
+                bn = lookup(wn);
+                meta_n = load_meta(wn, bn);
+            }
+            w = wn, b = bn, meta = meta_n;
+            continue;
+        }
         __syncwarp(); // the previous work item's tile / s_nbr are no longer read
         if (lane < NA) s_nbr[lane] = d.nbr[b * NA + lane];
         for (int n = lane; n < TC; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -381,8 +407,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
             __syncwarp();
         }
 
-        const int4 vid = d.block_vid[b];
-        const float cellpos[3] = {(float)(vid.x * B + lx) * h, (float)(vid.y * B + ly) * h, (float)(vid.z * B + lz) * h};
+        const float cellpos[3] = {(float)(meta.vx * B + lx) * h, (float)(meta.vy * B + ly) * h, (float)(meta.vz * B + lz) * h};
         bool incompatible = false;
         {
             P2GAcc<NBH, D + 1> acc;
@@ -400,9 +425,12 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
                     p2g_accumulate<D, P2G_FAST, D + 1>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, cellpos, h, inv_h, tb, tcdf, acc);
             };
             stage(first, (int)min((uint32_t)CHUNK, last - first), false);
+            wn = __shfl_sync(0xffffffffu, wn, 0); // (2) arrived while the chunk was staged: request the next block id
+            if (wn < nwork) bn = lookup(wn);
             if (cpic_item && any_cdf) colour(first, (int)min((uint32_t)CHUNK, last - first), true);
             acc.clear();
             scatter_chunk(first);
+            if (wn < nwork) meta_n = load_meta(wn, bn); // (3) ... and, one chunk later, its ranges
             for (uint32_t base = first + CHUNK; base < last; base += CHUNK) {
                 const int cn = (int)min((uint32_t)CHUNK, last - base);
                 __syncwarp(); // the previous chunk is no longer in use
@@ -486,7 +514,9 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
                 }
             }
         }
+        w = wn, b = bn, meta = meta_n;
     }
+    TL_END(d, B200MPM_KERNEL_P2G);
 }
 
 // Apply the impulse to the closest body (p2g.wgsl:142-155): IntegerImpulseAtomic, i32(x * 1e5) of the node's total.
