@@ -246,13 +246,17 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
     // near-identity permutation of the current buffers).
     // reload_colour: second (impulse) pass over a half block of several chunks - the colours come back from
     // cdf_aff[next], where the first pass left them.
-    auto stage = [&](uint32_t base, int cn, bool reload_colour) {
+    auto stage = [&](uint32_t base, int cn, bool reload_colour, bool ids_prefetched) {
         // ids go through shared memory so that the request loop below stays rolled (few live registers
         // next to the 108 accumulators); each lane only reads back the ids it wrote itself.
+        if (ids_prefetched) {
+            cp_async_wait_all(); // (requested while the previous item was flushed)
+        } else {
 #pragma unroll
-        for (int j = 0; j < CHUNK / 32; ++j) {
-            const int i = lane + j * 32;
-            if (i < cn) s_ids[i] = __ldg(d.sorted_ids + base + i);
+            for (int j = 0; j < CHUNK / 32; ++j) {
+                const int i = lane + j * 32;
+                if (i < cn) s_ids[i] = __ldg(d.sorted_ids + base + i);
+            }
         }
 #pragma unroll 1
         for (int i = lane; i < cn; i += 32) {
@@ -361,6 +365,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
     uint32_t b = (w < nwork) ? lookup(w) : 0u;
     Meta meta = {};
     if (w < nwork) meta = load_meta(w, b);
+    bool ids_prefetched = false; // s_ids holds the ids of this item's first chunk already
     while (w < nwork) {
         uint32_t wn = 0; // (1) the next item's queue index: requested now, read after the staging
         if (lane == 0) wn = atomicAdd(work, 1u);
@@ -380,6 +385,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
                 meta_n = load_meta(wn, bn);
             }
             w = wn, b = bn, meta = meta_n;
+            ids_prefetched = false;
             continue;
         }
         __syncwarp(); // the previous work item's tile / s_nbr are no longer read
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
                 else // no coloured node in reach: every particle keeps the default colour k_scatter wrote
                     p2g_accumulate<D, P2G_FAST, D + 1>(d, cur, base, lo, hi, sp, sv, sa, sb, sc, cellpos, h, inv_h, tb, tcdf, acc);
             };
-            stage(first, (int)min((uint32_t)CHUNK, last - first), false);
+            stage(first, (int)min((uint32_t)CHUNK, last - first), false, ids_prefetched);
             wn = __shfl_sync(0xffffffffu, wn, 0); // (2) arrived while the chunk was staged: request the next block id
             if (wn < nwork) bn = lookup(wn);
             if (cpic_item && any_cdf) colour(first, (int)min((uint32_t)CHUNK, last - first), true);
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
             for (uint32_t base = first + CHUNK; base < last; base += CHUNK) {
                 const int cn = (int)min((uint32_t)CHUNK, last - base);
                 __syncwarp(); // the previous chunk is no longer in use
-                stage(base, cn, false);
+                stage(base, cn, false, false);
                 if (cpic_item && any_cdf) colour(base, cn, true);
                 scatter_chunk(base);
             }
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
                     const int cn = (int)min((uint32_t)CHUNK, last - base);
                     if (!single_chunk) {
                         __syncwarp();
-                        stage(base, cn, true);
+                        stage(base, cn, true, false);
                     }
                     const int lo = (int)(max(start, base) - base);
                     const int hi = (int)(min(end, base + (uint32_t)cn) - base);
@@ -493,6 +499,17 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
             }
         }
 
+        // (4) the next item's particle ids, requested before this item's flush: they land while the tile is written out
+        // and the next tile is set up (the id buffer is free: every chunk of this item has been staged and coloured)
+        const bool prefetch_ids = wn < nwork && meta_n.first != meta_n.last;
+        if (prefetch_ids) {
+            const int cn_n = (int)min((uint32_t)CHUNK, meta_n.last - meta_n.first);
+#pragma unroll
+            for (int j = 0; j < CHUNK / 32; ++j) {
+                const int i = lane + j * 32;
+                if (i < cn_n) cp_async4(&s_ids[i], d.sorted_ids + meta_n.first + i);
+            }
+        }
         // Flush the tile: one 16-byte reduction per touched node.
         for (int n = lane; n < TC; n += 32) {
             int x = n % T, y = (n / T) % T, z = n / (T * T);
@@ -519,6 +536,7 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
             }
         }
         w = wn, b = bn, meta = meta_n;
+        ids_prefetched = prefetch_ids;
     }
     TL_END(d, B200MPM_KERNEL_P2G);
 }
