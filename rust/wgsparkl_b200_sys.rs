@@ -5,6 +5,8 @@ use std::os::raw::{c_char, c_int, c_void};
 
 pub const B200MPM_MAX_BODIES: usize = 16;
 pub const B200MPM_NUM_PASSES: usize = 10;
+/// Length of the arrays of `b200mpm_get_kernel_timings` (f64) and, doubled, `b200mpm_debug_timeline` (u64).
+pub const B200MPM_NUM_KERNELS: usize = 15;
 
 #[repr(C)]
 #[derive(Copy, Clone, Debug, Default)]

@@ -42,6 +42,21 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(pipeline.EXPORTS), set(names) ^ set(pipeline.EXPORTS)
 
 
+def test_pass_and_kernel_enums_match_the_bindings():
+    """B200MPM_PASS_* / B200MPM_KERNEL_* (include/b200mpm.h) against the Python names and the Rust constants."""
+    src = open(HEADER).read()
+    passes = re.findall(r"\bB200MPM_PASS_([A-Z0-9_]+)\s*=\s*(\d+)", src)
+    kernels = re.findall(r"\bB200MPM_KERNEL_([A-Z0-9_]+)\s*=\s*(\d+)", src)
+    num_passes = int(re.search(r"B200MPM_NUM_PASSES\s*=\s*(\d+)", src).group(1))
+    num_kernels = int(re.search(r"B200MPM_NUM_KERNELS\s*=\s*(\d+)", src).group(1))
+    assert [int(v) for _, v in passes] == list(range(num_passes)) and num_passes == len(abi.PASS_NAMES)
+    assert [int(v) for _, v in kernels] == list(range(num_kernels)) and num_kernels == len(abi.KERNEL_NAMES)
+    assert [n.lower() for n, _ in kernels] == list(abi.KERNEL_NAMES)
+    rust = open(os.path.join(ROOT, "rust", "wgsparkl_b200_sys.rs")).read()
+    assert int(re.search(r"B200MPM_NUM_PASSES: usize = (\d+)", rust).group(1)) == num_passes
+    assert int(re.search(r"B200MPM_NUM_KERNELS: usize = (\d+)", rust).group(1)) == num_kernels
+
+
 def test_struct_layouts_match_numpy(tmp_path):
     prog = tmp_path / "sizes.c"
     prog.write_text(
