@@ -452,8 +452,6 @@ void run_substep(b200mpm_pipeline* p, b200mpm_data* d) {
     if (p->timestamps && p->events.size() > 4096) fold_events(p);
 }
 
-bool is_pow2(uint32_t x) { return x && !(x & (x - 1)); }
-
 } // namespace
 
 extern "C" {
