@@ -449,23 +449,44 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
                 scatter_chunk(base);
             }
             // Merge the per-cell stencils into the tile: 3^D conflict-free phases (within a phase the 32 lanes
-            // add to 32 distinct nodes).
+            // add to 32 distinct nodes). In 3D the half block is two cells thick in z, so the phases sz = 0 and sz = 2
+            // touch disjoint node layers and go as ONE step (two independent load-add-store chains, one barrier).
+            auto merge_phase = [&](int sx, int sy, int sz) {
+                const int n = sx + 3 * sy + 9 * sz;
+                const int idx = tb + sx + T * sy + T * T * sz;
+                float4 c = tile[idx];
+                c.x += acc.a[n][0];
+                c.y += acc.a[n][1];
+                c.z += acc.a[n][2];
+                if (D == 3) c.w += acc.a[n][D];
+                tile[idx] = c;
+            };
 #pragma unroll
-            for (int sz = 0; sz < (D == 3 ? 3 : 1); ++sz)
+            for (int sy = 0; sy < 3; ++sy)
+#pragma unroll
+                for (int sx = 0; sx < 3; ++sx) {
+                    if (D == 3) {
+                        const int n0 = sx + 3 * sy, n2 = n0 + 18;
+                        const int i0 = tb + sx + T * sy, i2 = i0 + 2 * T * T;
+                        float4 c0 = tile[i0], c2 = tile[i2];
+                        c0.x += acc.a[n0][0], c0.y += acc.a[n0][1], c0.z += acc.a[n0][2], c0.w += acc.a[n0][D];
+                        c2.x += acc.a[n2][0], c2.y += acc.a[n2][1], c2.z += acc.a[n2][2], c2.w += acc.a[n2][D];
+                        tile[i0] = c0;
+                        tile[i2] = c2;
+                    } else {
+                        merge_phase(sx, sy, 0);
+                    }
+                    __syncwarp();
+                }
+            if (D == 3) {
 #pragma unroll
                 for (int sy = 0; sy < 3; ++sy)
 #pragma unroll
                     for (int sx = 0; sx < 3; ++sx) {
-                        const int n = sx + 3 * sy + 9 * sz;
-                        const int idx = tb + sx + T * sy + T * T * sz;
-                        float4 c = tile[idx];
-                        c.x += acc.a[n][0];
-                        c.y += acc.a[n][1];
-                        c.z += acc.a[n][2];
-                        if (D == 3) c.w += acc.a[n][D];
-                        tile[idx] = c;
+                        merge_phase(sx, sy, 1);
                         __syncwarp();
                     }
+            }
         }
         if (IMP && cpic_item) {
             // Second pass, only if some particle/node pair of this work item is CPIC-incompatible with a collider
