@@ -38,7 +38,7 @@ namespace b2 {
 // compressed material).
 #define P2G_WARPS_PLAIN 8
 #define P2G_WARPS_CPIC 8
-#define P2G_WARPS_IMP 7
+#define P2G_WARPS_IMP 6
 #endif
 constexpr int P2G_CHUNK = P2G_CHUNK_SIZE; // particles staged per pass and warp: 32 cells x 9 (the reference seeds 8 per cell)
 
@@ -219,6 +219,15 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
     // hold particles and see no collider, by decreasing population - longest items first keeps the last round short).
     __shared__ uint32_t s_cum[P2G_BUCKETS + 1]; // first work index of every bucket
     __shared__ float s_mass[16]; // masses of the first 16 materials (saves a dependent global load per staged chunk)
+    // tile node -> (which of the 2^D neighbour blocks) << 6 | node inside that block: the index arithmetic of the tile
+    // staging and of the flush, done once per warp instead of once per node and work item
+    __shared__ uint16_t s_node[TC];
+    for (int n = lane; n < TC; n += 32) {
+        const int x = n % T, y = (n / T) % T, z = n / (T * T);
+        const int ox = x >= B, oy = y >= B, oz = z >= B;
+        s_node[n] = (uint16_t)(((ox + 2 * oy + 4 * oz) << 6) | ((x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B));
+        tile[n] = make_float4(0.f, 0.f, 0.f, 0.f); // (every flush leaves the tile zeroed for the next work item)
+    }
     const bool mass_in_smem = d.num_materials <= 16u;
     if (mass_in_smem && lane < (int)d.num_materials) s_mass[lane] = d.materials[lane].mass;
     const uint32_t ncpic = CPIC ? d.counters->num_cpic_blocks * 2u : 0u;
@@ -390,18 +399,16 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
         }
         __syncwarp(); // the previous work item's tile / s_nbr are no longer read
         if (lane < NA) s_nbr[lane] = d.nbr[b * NA + lane];
-        for (int n = lane; n < TC; n += 32) tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
         bool any_cdf = false; // the tile holds a coloured node
         if (cpic_item) {
             for (int n = lane; n < TC; n += 32) {
-                int x = n % T, y = (n / T) % T, z = n / (T * T);
-                int ox = x >= B, oy = y >= B, oz = z >= B;
-                uint32_t hn = s_nbr[ox + 2 * oy + 4 * oz];
+                const uint32_t where = s_node[n];
+                uint32_t hn = s_nbr[where >> 6];
                 uint2 c = make_uint2(0u, NONE);
                 float dist = 0.0f;
                 if (hn != NONE) {
-                    uint4 g = d.node_cdf[hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B];
+                    uint4 g = d.node_cdf[hn * CELLS_PER_BLOCK + (where & 63u)];
                     c = make_uint2(g.z, g.x); // (affinities, closest_id)
                     dist = __uint_as_float(g.y);
                 }
@@ -533,12 +540,12 @@ __global__ void __launch_bounds__(32, CPIC ? (IMP ? P2G_WARPS_IMP : P2G_WARPS_CP
         }
         // Flush the tile: one 16-byte reduction per touched node.
         for (int n = lane; n < TC; n += 32) {
-            int x = n % T, y = (n / T) % T, z = n / (T * T);
-            int ox = x >= B, oy = y >= B, oz = z >= B;
-            uint32_t hn = s_nbr[ox + 2 * oy + 4 * oz];
-            if (hn == NONE) continue; // only after a capacity overflow
-            uint32_t node = hn * CELLS_PER_BLOCK + (x - ox * B) + (y - oy * B) * B + (z - oz * B) * B * B;
+            const uint32_t where = s_node[n];
+            const uint32_t hn = s_nbr[where >> 6];
             float4 c = tile[n];
+            tile[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hn == NONE) continue; // only after a capacity overflow
+            const uint32_t node = hn * CELLS_PER_BLOCK + (where & 63u);
             if (D == 2) c.w = 0.0f; // 2D stores (px, py, mass, 0)
             if (c.x != 0.0f || c.y != 0.0f || c.z != 0.0f || c.w != 0.0f) atomicAdd(d.node_mv + node, c);
             if (IMP && cpic_item) {
