@@ -241,7 +241,9 @@ __host__ __device__ inline uint32_t hash_key(uint32_t k) { // grid.wgsl:98-105 (
 __device__ __forceinline__ float round_div(float p, float h, float inv_h) {
     const float q = p * inv_h;
     const float r = rintf(q);
-    if (0.5f - fabsf(q - r) <= 4e-7f * fabsf(q) || !(fabsf(q) < 4194304.0f)) return rintf(__fdiv_rn(p, h));
+    // (|q| >= 2^22: q - r == 0 and 4e-7 |q| > 0.5, so the test sends those to the division as well; NaN / inf come
+    // out of rintf(q) as they would out of the division)
+    if (0.5f - fabsf(q - r) <= 4e-7f * fabsf(q)) return rintf(__fdiv_rn(p, h));
     return r;
 }
 
