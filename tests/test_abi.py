@@ -167,3 +167,18 @@ def test_shared_svd_code_on_the_host(tmp_path):
         n3 += d == 3
         n2 += d == 2
     assert n3 == 300 and n2 == 100
+
+
+def test_block_level_collider_culling_is_conservative(tmp_path):
+    """k_block_prepare skips, per block, the colliders body_may_touch_block() rules out (csrc/collide.cuh, compiled
+    for the host here): over 2 x 20000 random blocks next to random balls / cuboids / capsules in random poses, the
+    per-node collide() results with and without the culling are bit-identical, and the culling does cull."""
+    exe = tmp_path / "collide_host"
+    subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "cpp", "collide_host.cu")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    for dim, line in zip((3, 2), out):
+        d, blocks, pairs, culled, mismatches = (int(x) for x in line.split())
+        assert d == dim and blocks == 20000
+        assert mismatches == 0
+        assert 0.3 * pairs < culled < 0.95 * pairs  # (the sample holds both kinds of pairs in numbers)

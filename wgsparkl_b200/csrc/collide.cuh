@@ -15,7 +15,7 @@ struct NodeCdf { // grid.wgsl:233-240
 
 // parry's project_local_point(pt, solid = false) on the shape boundary, local frame.
 template <int D>
-__device__ inline bool project_local_point_on_boundary(const BodyDev& b, const float* pt, float* out) {
+__host__ __device__ inline bool project_local_point_on_boundary(const BodyDev& b, const float* pt, float* out) {
     if (b.shape_type == B200MPM_SHAPE_BALL) {
         float d2 = 0.0f;
 #pragma unroll
@@ -129,7 +129,7 @@ __device__ inline bool project_local_point_on_boundary(const BodyDev& b, const f
 // World point -> body frame -> boundary projection -> world: the vector from `point` to its projection on body b's
 // boundary, and whether the point is inside (collide.wgsl:39-45).
 template <int D>
-__device__ inline bool project_on_body(const BodyDev& b, const float* point, float* dpt) {
+__host__ __device__ inline bool project_on_body(const BodyDev& b, const float* point, float* dpt) {
     float d[D], loc[D], lp[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) d[k] = point[k] - b.trans[k];
@@ -157,7 +157,7 @@ __device__ inline bool project_on_body(const BodyDev& b, const float* point, flo
 // least one component of its projection vector exceeds the 1.5 h cap of collide(): the body leaves no trace on the
 // block and its per-node evaluation can be skipped (most blocks see no body at all).
 template <int D>
-__device__ inline bool body_may_touch_block(const BodyDev& b, float cell_width, const float* origin) {
+__host__ __device__ inline bool body_may_touch_block(const BodyDev& b, float cell_width, const float* origin) {
     if (b.shape_type == B200MPM_SHAPE_TRIMESH || b.shape_type == B200MPM_SHAPE_POLYLINE) return false; // collide.wgsl:41
     const float half = 0.5f * (float)(Dim<D>::BLOCK - 1) * cell_width;
     float centre[D], dpt[D];
@@ -175,12 +175,16 @@ __device__ inline bool body_may_touch_block(const BodyDev& b, float cell_width, 
 // collide() (collision/collide.wgsl:23-55): closest collider, distance and affinity/sign bits
 // of a grid node at world position `point`. `body_mask`: the bodies to look at (see body_may_touch_block).
 template <int D>
-__device__ inline NodeCdf collide(const BodyDev* __restrict__ bodies, uint32_t body_mask, float cell_width,
+__host__ __device__ inline NodeCdf collide(const BodyDev* __restrict__ bodies, uint32_t body_mask, float cell_width,
                                   const float* point) {
     NodeCdf cdf{1.0e10f, 0u, NONE};
     const float dist_cap = cell_width * 1.5f;
     for (uint32_t m = body_mask; m != 0u; m &= m - 1u) {
+#ifdef __CUDA_ARCH__
         const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
+#else
+        const uint32_t i = (uint32_t)__builtin_ffs((int)m) - 1u; // (host build of the culling property test)
+#endif
         const BodyDev& b = bodies[i];
         if (b.shape_type == B200MPM_SHAPE_TRIMESH || b.shape_type == B200MPM_SHAPE_POLYLINE) continue; // collide.wgsl:41
         float dpt[D];
