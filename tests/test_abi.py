@@ -182,3 +182,14 @@ def test_block_level_collider_culling_is_conservative(tmp_path):
         assert d == dim and blocks == 20000
         assert mismatches == 0
         assert 0.3 * pairs < culled < 0.95 * pairs  # (the sample holds both kinds of pairs in numbers)
+
+
+def test_round_div_equals_the_ieee_division_everywhere(tmp_path):
+    """round_div (csrc/common.cuh: round(p / h) without the division except next to half-integers; SURVEY A.1 asks
+    for the true IEEE quotient) compiled for the host: all ties k + 0.5 with their +-4 ulp neighbours for |k| < 2^20
+    and seven cell widths, 2e8 random quotients and the special values - 3.4e8 cases, no mismatch."""
+    exe = tmp_path / "round_div_host"
+    subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "cpp", "round_div_host.cu")])
+    n, bad = (int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
+    assert n > 300_000_000 and bad == 0

@@ -238,12 +238,16 @@ __host__ __device__ inline uint32_t hash_key(uint32_t k) { // grid.wgsl:98-105 (
 // particle3d.wgsl:42 (never roundf) - without paying for the division: q = p * (1/h) is within
 // 1.8e-7 |q| of the correctly rounded quotient, so rint(q) can only differ from rint(p / h) when a half-integer
 // lies that close to q. Those (rare) lanes take the IEEE division; everyone else a multiply and a compare.
-__device__ __forceinline__ float round_div(float p, float h, float inv_h) {
+__host__ __device__ __forceinline__ float round_div(float p, float h, float inv_h) {
     const float q = p * inv_h;
     const float r = rintf(q);
     // (|q| >= 2^22: q - r == 0 and 4e-7 |q| > 0.5, so the test sends those to the division as well; NaN / inf come
     // out of rintf(q) as they would out of the division)
+#ifdef __CUDA_ARCH__
     if (0.5f - fabsf(q - r) <= 4e-7f * fabsf(q)) return rintf(__fdiv_rn(p, h));
+#else
+    if (0.5f - fabsf(q - r) <= 4e-7f * fabsf(q)) return rintf(p / h); // (host build: tests/cpp/round_div_host.cu)
+#endif
     return r;
 }
 
